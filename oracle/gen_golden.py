@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE.
+
+TEST INFRASTRUCTURE.  This script is the only place in the repo that imports
+`/root/reference/pearl` (read-only, via the test-only stubs in oracle/stubs/).
+It cannot run on the GPU box (no /root/reference there); its outputs are
+committed as small .npz/.json fixtures and everything else (oracle tests,
+GPU parity tests, smoke) reads those.
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+What is recorded, per case (see `run_dqn_case`):
+  * the pushed transitions (quantised to a 1/256 grid, stored as int16, so the
+    fixture is small and exactly representable in fp32),
+  * the CPython `random` state before and after `learn()`
+    (reference call site: pearl/replay_buffers/tensor_based_replay_buffer.py:276),
+  * per training round: the sampled logical indices (0 = oldest element of the
+    deque), Q(s,a) (`state_action_values`, deep_td_learning.py:342), the
+    Bellman target y (`expected_state_action_values`, :313-317) and the
+    reported "loss" (mean |q - y|, :358-360),
+  * parameter snapshots of `_Q` / `_Q_target` after selected rounds, and the
+    final AdamW(amsgrad) state (torch/optim/adam.py `_single_tensor_adam`).
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.dont_write_bytecode = True
+sys.path.insert(0, os.path.join(HERE, "stubs"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from oracle.synth import make_transitions  # noqa: E402
+
+from pearl.action_representation_modules.one_hot_action_representation_module import (  # noqa: E402
+    OneHotActionTensorRepresentationModule,
+)
+from pearl.pearl_agent import PearlAgent  # noqa: E402
+from pearl.policy_learners.sequential_decision_making.deep_q_learning import (  # noqa: E402
+    DeepQLearning,
+)
+from pearl.policy_learners.sequential_decision_making.double_dqn import DoubleDQN  # noqa: E402
+from pearl.replay_buffers.basic_replay_buffer import BasicReplayBuffer  # noqa: E402
+from pearl.utils.instantiations.spaces.discrete_action import DiscreteActionSpace  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def state_words(st) -> np.ndarray:
+    """random.getstate() -> uint32[625] (624 MT words + position index)."""
+    assert st[0] == 3 and st[2] is None
+    return np.asarray(st[1], dtype=np.uint64).astype(np.uint32)
+
+
+def flat_params(module) -> np.ndarray:
+    return np.concatenate([p.detach().numpy().ravel() for p in module.parameters()])
+
+
+def run_dqn_case(name, *, obs, n_act, hidden, capacity, n_push, batch, rounds,
+                 target_update_freq, tau, double, seed, data_seed, dynamic=False,
+                 snap_rounds=(1, 2, 5), lr=1e-3, gamma=0.99, learn_calls=1):
+    torch.manual_seed(seed)
+    random.seed(seed)
+    torch.set_num_threads(1)
+    cls = DoubleDQN if double else DeepQLearning
+    full_space = DiscreteActionSpace(actions=list(torch.arange(n_act).view(-1, 1)))
+    learner = cls(
+        state_dim=obs,
+        action_space=full_space,
+        hidden_dims=list(hidden),
+        learning_rate=lr,
+        discount_factor=gamma,
+        training_rounds=rounds,
+        batch_size=batch,
+        target_update_freq=target_update_freq,
+        soft_update_tau=tau,
+        action_representation_module=OneHotActionTensorRepresentationModule(n_act),
+    )
+    buf = BasicReplayBuffer(capacity)
+    agent = PearlAgent(policy_learner=learner, replay_buffer=buf, device_id=-1)
+    assert str(agent.device) == "cpu"
+
+    data = make_transitions(n_push, obs, n_act, seed=data_seed, dynamic=dynamic)
+    for i in range(n_push):
+        if dynamic:
+            ids = data["next_avail_ids"][i, : data["next_avail_n"][i]]
+            nxt = DiscreteActionSpace(actions=[torch.tensor([int(a)]) for a in ids])
+        else:
+            nxt = full_space
+        buf.push(
+            state=torch.from_numpy(data["state"][i]),
+            action=torch.tensor(int(data["action"][i])),
+            reward=float(data["reward"][i]),
+            terminated=bool(data["terminated"][i]),
+            truncated=bool(data["truncated"][i]),
+            curr_available_actions=full_space,
+            next_state=torch.from_numpy(data["next_state"][i]),
+            next_available_actions=nxt,
+            max_number_actions=n_act,
+        )
+
+    init_q = flat_params(learner._Q).copy()
+    init_qt = flat_params(learner._Q_target).copy()
+
+    # --- instrument the reference (observation only; arithmetic untouched) ----
+    rec = {"idx": [], "q": [], "y": [], "mae": []}
+    snaps_q, snaps_qt = {}, {}
+    orig_sample = buf.sample
+    orig_loss = learner.loss
+    orig_learn_batch = learner.learn_batch
+
+    def sample_spy(batch_size):
+        pos = {id(t): j for j, t in enumerate(buf.memory)}
+        # same call the reference makes, with the transitions identified afterwards
+        st = random.getstate()
+        picked = random.sample(buf.memory, batch_size)
+        rec["idx"].append([pos[id(t)] for t in picked])
+        random.setstate(st)
+        return orig_sample(batch_size)
+
+    def loss_spy(batch_, predictions):
+        loss, y = orig_loss(batch_, predictions)
+        rec["q"].append(predictions.detach().numpy().copy())
+        rec["y"].append(y.detach().numpy().copy())
+        return loss, y
+
+    def learn_batch_spy(batch_):
+        out = orig_learn_batch(batch_)
+        rec["mae"].append(out["loss"])
+        r = len(rec["mae"])
+        if r in snap_rounds or r == rounds * learn_calls:
+            snaps_q[r] = flat_params(learner._Q).copy()
+            snaps_qt[r] = flat_params(learner._Q_target).copy()
+        return out
+
+    buf.sample = sample_spy
+    learner.loss = loss_spy
+    learner.learn_batch = learn_batch_spy
+
+    state0 = state_words(random.getstate())
+    reports = []
+    for _ in range(learn_calls):
+        reports.append(agent.learn())
+    state1 = state_words(random.getstate())
+    total = rounds * learn_calls
+    assert len(rec["mae"]) == total
+    assert [v for r in reports for v in r["loss"]] == rec["mae"]
+
+    opt_state = learner.optimizer.state_dict()["state"]
+    exp_avg = np.concatenate([opt_state[i]["exp_avg"].numpy().ravel() for i in range(len(opt_state))])
+    exp_avg_sq = np.concatenate([opt_state[i]["exp_avg_sq"].numpy().ravel() for i in range(len(opt_state))])
+    max_sq = np.concatenate([opt_state[i]["max_exp_avg_sq"].numpy().ravel() for i in range(len(opt_state))])
+    step = float(opt_state[0]["step"])
+    assert step == total
+
+    cfg = dict(name=name, obs=obs, n_act=n_act, hidden=list(hidden), capacity=capacity,
+               n_push=n_push, batch=batch, rounds=rounds, learn_calls=learn_calls,
+               target_update_freq=target_update_freq, tau=tau, double=bool(double),
+               seed=seed, data_seed=data_seed, dynamic=bool(dynamic), lr=lr, gamma=gamma,
+               betas=[0.9, 0.999], eps=1e-8, weight_decay=0.01, amsgrad=True,
+               snap_rounds=sorted(snaps_q.keys()), torch=torch.__version__,
+               reference="facebookresearch/Pearl @ 48f1fbb")
+    out = dict(
+        config=np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8),
+        state_q=data["state_q"], next_state_q=data["next_state_q"],
+        action=data["action"].astype(np.int16), reward_q=data["reward_q"],
+        terminated=data["terminated"].astype(np.uint8),
+        truncated=data["truncated"].astype(np.uint8),
+        mt_state_before=state0, mt_state_after=state1,
+        idx=np.asarray(rec["idx"], dtype=np.int32),
+        q=np.asarray(rec["q"], dtype=np.float32),
+        y=np.asarray(rec["y"], dtype=np.float32),
+        mae=np.asarray(rec["mae"], dtype=np.float64),
+        init_q=init_q, init_q_target=init_qt,
+        exp_avg=exp_avg, exp_avg_sq=exp_avg_sq, max_exp_avg_sq=max_sq,
+    )
+    if dynamic:
+        out["next_avail_ids"] = data["next_avail_ids"].astype(np.int16)
+        out["next_avail_n"] = data["next_avail_n"].astype(np.int16)
+    for r in snaps_q:
+        out[f"q_after_{r}"] = snaps_q[r]
+        out[f"qt_after_{r}"] = snaps_qt[r]
+    path = os.path.join(GOLDEN, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB  mae[0]={rec['mae'][0]:.6f} "
+          f"mae[-1]={rec['mae'][-1]:.6f}")
+
+
+def gen_random_sample_vectors():
+    """Known-answer vectors for CPython's MT19937 + random.sample
+    (cpython Lib/random.py:242-250,359-452; Modules/_randommodule.c)."""
+    out = []
+    for seed, n, k, reps in [
+        (1234, 10**6, 256, 3),     # set branch, 20-bit draws (cfg2)
+        (1234, 1045, 256, 2),      # pool branch, largest n for k=256
+        (1234, 1046, 256, 2),      # set branch, smallest n for k=256
+        (7, 4_000_000, 256, 2),    # cfg5 size
+        (99, 10_000, 32, 4),       # cfg1
+        (99, 277, 32, 2), (99, 278, 32, 2),
+        (5, 256, 256, 2),          # k == n : a permutation
+        (5, 1, 1, 3),              # n == 1: getrandbits(1) rejection loop
+        (5, 65_536, 256, 2),       # n a power of two
+        (2**40 + 12345, 123_457, 512, 2),  # big-int seed (init_by_array, 2 keys), k=512
+        (0, 300, 200, 2),          # pool branch with k close to n
+        (31337, 5000, 4000, 1),    # large k: set branch, many duplicate retries
+    ]:
+        random.seed(seed)
+        st0 = state_words(random.getstate())
+        first_words = [random.getrandbits(32) for _ in range(4)]
+        random.seed(seed)
+        samples = [random.sample(range(n), k) for _ in range(reps)]
+        st1 = state_words(random.getstate())
+        tail = random.getrandbits(32)
+        out.append(dict(seed=seed, n=n, k=k, reps=reps, first_words=first_words,
+                        samples=samples, next_word_after=tail,
+                        state_before_xor=int(np.bitwise_xor.reduce(st0[:624])),
+                        state_after_index=int(st1[624]),
+                        state_after_xor=int(np.bitwise_xor.reduce(st1[:624]))))
+    with open(os.path.join(GOLDEN, "random_sample_kat.json"), "w") as f:
+        json.dump(dict(source="CPython %s random.seed/getrandbits/sample" % sys.version.split()[0],
+                       cases=out), f)
+    print("random_sample_kat.json:", len(out), "cases")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    gen_random_sample_vectors()
+    # small everything; ring wraps (n_push > capacity); pool branch (n=48 <= 85)
+    run_dqn_case("dqn_tiny", obs=8, n_act=4, hidden=(16, 16), capacity=48, n_push=70, batch=16,
+                 rounds=12, target_update_freq=5, tau=0.75, double=False, seed=11, data_seed=101,
+                 snap_rounds=(1, 2, 4, 5, 10))
+    run_dqn_case("ddqn_tiny", obs=8, n_act=4, hidden=(16, 16), capacity=48, n_push=70, batch=16,
+                 rounds=12, target_update_freq=5, tau=0.75, double=True, seed=12, data_seed=102,
+                 snap_rounds=(1, 2, 4, 5, 10))
+    # dynamic action space: per-transition next_available_actions subsets + masks
+    run_dqn_case("dqn_dynamic", obs=6, n_act=5, hidden=(16, 8), capacity=64, n_push=64, batch=32,
+                 rounds=8, target_update_freq=3, tau=0.5, double=False, seed=13, data_seed=103,
+                 dynamic=True, snap_rounds=(1, 3, 8))
+    run_dqn_case("ddqn_dynamic", obs=6, n_act=5, hidden=(16, 8), capacity=64, n_push=64, batch=32,
+                 rounds=8, target_update_freq=3, tau=0.5, double=True, seed=14, data_seed=104,
+                 dynamic=True, snap_rounds=(1, 3, 8))
+    # cfg1 shape (CartPole: obs=4, A=2, [64,64], B=32), two learn() calls
+    run_dqn_case("dqn_cfg1", obs=4, n_act=2, hidden=(64, 64), capacity=512, n_push=400, batch=32,
+                 rounds=10, learn_calls=2, target_update_freq=10, tau=0.75, double=False, seed=21,
+                 data_seed=201, snap_rounds=(1, 10, 20))
+    # cfg2 network shape (obs=128, A=16, [64,64], B=256) on a small buffer: pool branch (n<=1045)
+    run_dqn_case("dqn_cfg2_pool", obs=128, n_act=16, hidden=(64, 64), capacity=600, n_push=600,
+                 batch=256, rounds=20, target_update_freq=10, tau=0.75, double=False, seed=1234,
+                 data_seed=4321, snap_rounds=(1, 9, 10, 20))
+    # set branch (n = 1100 > 1045) with B=256; narrower obs to keep the fixture small
+    run_dqn_case("ddqn_setbranch", obs=32, n_act=16, hidden=(64, 64), capacity=1100, n_push=1500,
+                 batch=256, rounds=12, target_update_freq=10, tau=0.75, double=True, seed=77,
+                 data_seed=770, snap_rounds=(1, 10, 12))
+    # batch larger than buffer -> learn() clamps batch to len(buffer) (policy_learner.py:176-179)
+    run_dqn_case("dqn_short_buffer", obs=8, n_act=4, hidden=(16, 16), capacity=100, n_push=10,
+                 batch=32, rounds=3, target_update_freq=2, tau=0.75, double=False, seed=5,
+                 data_seed=55, snap_rounds=(1, 3))
