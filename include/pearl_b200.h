@@ -1,0 +1,240 @@
+/* pearl_b200.h — C ABI of libpearlb200.so: the B200-native learner hot path of
+ * facebookresearch/Pearl (`ReplayBuffer.sample -> PolicyLearner.learn()`).
+ *
+ * Conventions
+ *   - extern "C", plain ints / pointers / sizes; no C++ or torch types.
+ *   - every entry point returns 0 on success or a negative PRL_E* code; the
+ *     message for the calling thread is available from prl_last_error().
+ *   - the CALLER (PyTorch in pearl_b200/, or any other host) allocates and owns
+ *     every device buffer; the library owns only its opaque handles, a pinned
+ *     staging area for host pushes and small workspaces.  Pointers registered
+ *     by *_create / *_bind stay referenced until *_destroy.
+ *   - all device work is enqueued on the `stream` argument (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream).  No hidden
+ *     synchronisation except where stated.
+ *   - one handle is used from one host thread at a time (thread-compatible).
+ *
+ * Each group cites the reference interface it replaces (paths relative to
+ * /root/reference/pearl, commit 48f1fbb).
+ */
+#ifndef PEARL_B200_H
+#define PEARL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRL_OK 0
+#define PRL_EINVAL (-1)    /* contract violation (reference raises ValueError / assert) */
+#define PRL_ECUDA (-2)     /* CUDA runtime error */
+#define PRL_ENOMEM (-3)
+#define PRL_ESTATE (-4)    /* call not valid in the handle's current state */
+#define PRL_EUNSUPPORTED (-5)
+
+#define PRL_ABI_VERSION 1
+
+/* ---- library ----------------------------------------------------------- */
+int prl_abi_version(void);
+/* Select `device` for the calling thread and check it is sm_100 (B200).
+ * There is no CPU fallback: without a B200 this returns PRL_EUNSUPPORTED. */
+int prl_init(int device);
+const char *prl_last_error(void);
+/* multiprocessor count of the current device (grid sizing, reported by bench) */
+int prl_sm_count(void);
+
+/* ---- replay buffer ------------------------------------------------------
+ * Replaces BasicReplayBuffer / TensorBasedReplayBuffer
+ * (replay_buffers/basic_replay_buffer.py:17-48,
+ *  replay_buffers/tensor_based_replay_buffer.py:55-133,253-288).
+ *
+ * Storage is ONE caller-allocated device array of `capacity` fixed-size
+ * records ("array of transitions": sampling touches whole random transitions,
+ * so a transition is contiguous, 16-byte aligned, and moves with one bulk
+ * copy).  Record layout in 32-bit words (see prl_buf_layout):
+ *     [off_state      .. +obs_dim)   state        f32
+ *     [off_next_state .. +obs_dim)   next_state   f32
+ *     [off_action     .. +act_words) action       i32 (discrete) | f32[act_dim]
+ *     [off_reward]                   reward       f32
+ *     [off_flags]                    bit0 terminated, bit1 truncated,
+ *                                    bits 8..23 number of next available actions
+ *     [off_avail .. ) (PRL_BUF_DYNAMIC_ACTIONS only) n_actions u8 ids of the
+ *                     next available actions (padded with 0), as the reference
+ *                     pads `next_available_actions` (tensor_based_replay_buffer.py:179-251)
+ * FIFO eviction like deque(maxlen=capacity): logical index 0 = oldest.
+ */
+#define PRL_BUF_DISCRETE 0x1          /* action is one int32 id in [0, n_actions) */
+#define PRL_BUF_CONTINUOUS 0x2        /* action is act_dim floats */
+#define PRL_BUF_DYNAMIC_ACTIONS 0x4   /* per-transition next-available-action sets */
+
+typedef struct prl_buf_desc {
+    int64_t capacity;
+    int32_t obs_dim;
+    int32_t act_dim;     /* continuous: action dimension; discrete: 1 */
+    int32_t n_actions;   /* discrete: max_number_actions; continuous: 0 */
+    int32_t flags;       /* PRL_BUF_* */
+} prl_buf_desc;
+
+typedef struct prl_buf_layout {
+    int32_t record_words;   /* record stride in 32-bit words (multiple of 4) */
+    int32_t off_state, off_next_state, off_action, off_reward, off_flags, off_avail;
+    int32_t act_words;
+    int64_t storage_bytes;  /* capacity * record_words * 4 */
+} prl_buf_layout;
+
+typedef struct prl_buf prl_buf;
+
+int prl_buf_layout_of(const prl_buf_desc *desc, prl_buf_layout *out);
+/* `storage_dev`: device memory of layout.storage_bytes bytes, 16-byte aligned.
+ * `mt_state_dev`: device uint32[625], the MT19937 state in the layout of
+ * CPython's random.getstate()[1] (624 words + position). */
+int prl_buf_create(prl_buf **out, const prl_buf_desc *desc, void *storage_dev,
+                   uint32_t *mt_state_dev);
+int prl_buf_destroy(prl_buf *buf);
+int64_t prl_buf_len(const prl_buf *buf);          /* __len__  (:284-285) */
+int64_t prl_buf_capacity(const prl_buf *buf);
+int64_t prl_buf_head(const prl_buf *buf);         /* physical slot of logical index 0 */
+int prl_buf_clear(prl_buf *buf);                  /* clear()  (:287-288) */
+/* Restore occupancy after the caller refilled `storage_dev` itself
+ * (checkpoint load): `len` valid records, oldest at physical slot `head`. */
+int prl_buf_set_occupancy(prl_buf *buf, int64_t len, int64_t head);
+
+/* push n transitions given as HOST arrays (struct-of-arrays, C order):
+ * state/next_state f32[n][obs_dim]; action int32[n] or f32[n][act_dim];
+ * reward f32[n]; terminated/truncated u8[n]; next_avail_ids u8[n][n_actions]
+ * and next_avail_cnt i32[n] (both NULL => all n_actions available).
+ * Records are packed into the handle's pinned staging area and copied with
+ * at most two cudaMemcpyAsync (ring wrap).  Replaces push() (:55-133) +
+ * _store_transition (basic_replay_buffer.py:21-48), batched. */
+int prl_buf_push_host(prl_buf *buf, int64_t n, const float *state, const void *action,
+                      const float *reward, const float *next_state, const uint8_t *terminated,
+                      const uint8_t *truncated, const uint8_t *next_avail_ids,
+                      const int32_t *next_avail_cnt, void *stream);
+/* same, sources already on the device (pack kernel, no host round trip) */
+int prl_buf_push_device(prl_buf *buf, int64_t n, const float *state, const void *action,
+                        const float *reward, const float *next_state, const uint8_t *terminated,
+                        const uint8_t *truncated, const uint8_t *next_avail_ids,
+                        const int32_t *next_avail_cnt, void *stream);
+
+/* RNG state hand-off with CPython's global `random` module
+ * (the reference samples with random.sample, tensor_based_replay_buffer.py:276;
+ * state = random.getstate()[1]).  Host pointers, uint32[625].  get synchronises
+ * `stream`. */
+int prl_rng_set_state(prl_buf *buf, const uint32_t *state625_host, void *stream);
+int prl_rng_get_state(prl_buf *buf, uint32_t *state625_host, void *stream);
+/* random.seed(int): abs(seed) as little-endian 32-bit key words */
+int prl_rng_seed(prl_buf *buf, const uint32_t *key_host, int key_len, void *stream);
+
+/* Draw `rounds` consecutive samples of `k` distinct logical indices, exactly
+ * the values `random.sample(range(len), k)` would return `rounds` times in a
+ * row from the current MT19937 state (both CPython branches), advancing the
+ * state.  out_logical_dev / out_slot_dev: device int32[rounds][k] (either may
+ * be NULL); slot = physical record index.  PRL_EINVAL if k > len
+ * (reference: ValueError, :271-275). */
+int prl_buf_sample_indices(prl_buf *buf, int rounds, int k, int32_t *out_logical_dev,
+                           int32_t *out_slot_dev, void *stream);
+
+/* Gather k records into the reference's TransitionBatch field layout
+ * (_create_transition_batch :290-400; dtypes of SURVEY.md §8 a4), all device
+ * pointers, any of them may be NULL:
+ *   state/next_state f32[k][obs_dim]; action i64[k] (discrete) or
+ *   f32[k][act_dim]; reward f32[k]; terminated/truncated u8[k] (bool);
+ *   next_avail f32[k][n_actions] (action ids, 0-padded);
+ *   next_unavail_mask u8[k][n_actions] (1 = unavailable). */
+int prl_buf_gather(const prl_buf *buf, const int32_t *slot_dev, int k, float *state, void *action,
+                   float *reward, float *next_state, uint8_t *terminated, uint8_t *truncated,
+                   float *next_avail, uint8_t *next_unavail_mask, void *stream);
+
+/* ---- DQN / DoubleDQN learner ---------------------------------------------
+ * Replaces DeepTDLearning.learn_batch + DeepQLearning / DoubleDQN
+ * .get_next_state_values + VanillaQValueNetwork.get_q_values + AdamW(amsgrad)
+ * + update_target_network, driven by PolicyLearner.learn's training_rounds
+ * loop (policy_learners/policy_learner.py:162-195,
+ * policy_learners/sequential_decision_making/deep_td_learning.py:269-360,
+ * deep_q_learning.py:130-167, double_dqn.py:29-57,
+ * neural_networks/sequential_decision_making/q_value_networks.py:152-174,
+ * neural_networks/common/utils.py:214-226, torch/optim/adam.py).
+ *
+ * Network: VanillaQValueNetwork with two hidden layers,
+ *   x = [state | one_hot(action)]  ->  Linear(H1) ReLU Linear(H2) ReLU Linear(1).
+ * Parameters are ONE flat fp32 array in torch's own parameter order and
+ * layout (nn.Linear weight [out][in] row-major, then bias):
+ *   W1[H1][obs+A] b1[H1] W2[H2][H1] b2[H2] W3[1][H2] b3[1]
+ * so the caller can expose views of it as the module's state_dict.
+ */
+typedef struct prl_dqn_cfg {
+    int32_t obs_dim, n_actions, hidden1, hidden2;
+    int32_t double_dqn;            /* 0: DeepQLearning, 1: DoubleDQN */
+    int32_t target_update_freq;    /* soft update when (training_steps+1) % freq == 0 */
+    int32_t max_batch;             /* largest batch learn()/learn_batch() will be given */
+    int32_t max_rounds;            /* largest `rounds` per prl_dqn_learn call */
+    int32_t rows_per_cta;          /* 0 = choose automatically */
+    /* AdamW (amsgrad always on), discount, soft-update coefficient: doubles,
+     * because the reference evaluates these scalars in Python floats */
+    double lr, beta1, beta2, eps, weight_decay;
+    double gamma, tau;
+} prl_dqn_cfg;
+
+typedef struct prl_dqn prl_dqn;
+
+int64_t prl_dqn_param_count(const prl_dqn_cfg *cfg);
+/* bytes of device workspace the caller must provide to prl_dqn_create */
+int64_t prl_dqn_workspace_bytes(const prl_dqn_cfg *cfg);
+/* w, w_target, exp_avg, exp_avg_sq, max_exp_avg_sq: device f32[param_count].
+ * adam_step: number of optimizer steps already taken (torch's `step`). */
+int prl_dqn_create(prl_dqn **out, const prl_dqn_cfg *cfg, float *w, float *w_target,
+                   float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, int64_t adam_step,
+                   void *workspace_dev);
+int prl_dqn_destroy(prl_dqn *dqn);
+int64_t prl_dqn_adam_step(const prl_dqn *dqn);
+int prl_dqn_set_adam_step(prl_dqn *dqn, int64_t step);
+int prl_dqn_set_lr(prl_dqn *dqn, double lr);
+
+/* PolicyLearner.learn(replay_buffer) for `rounds` training rounds in ONE call:
+ * draws rounds x batch indices (bit-exact with random.sample), then runs a
+ * persistent kernel that per round gathers the batch, applies the scheduled
+ * soft target update, computes Q(s,a), the Bellman target, the MSE gradient,
+ * and the AdamW(amsgrad) step.  `training_steps0` is the learner's
+ * `_training_steps` BEFORE the call (round r uses training_steps0 + r + 1).
+ * out_mae_dev: device f32[rounds], the reference's reported "loss"
+ * (mean |q - y|, deep_td_learning.py:358-360).  Optional device outputs for
+ * parity tests (NULL to skip): out_q / out_y f32[rounds][batch],
+ * out_logical i32[rounds][batch].  Asynchronous on `stream`. */
+int prl_dqn_learn(prl_dqn *dqn, prl_buf *buf, int rounds, int batch, int64_t training_steps0,
+                  float *out_mae_dev, float *out_q_dev, float *out_y_dev,
+                  int32_t *out_logical_dev, void *stream);
+
+/* DeepTDLearning.learn_batch(batch) on a caller-supplied TransitionBatch
+ * (PearlAgent.learn_batch / offline learning, pearl_agent.py:222-231): device
+ * arrays in prl_buf_gather's output layout; next_avail / mask may be NULL
+ * (all actions available).  `do_target_update` = the caller's evaluation of
+ * (training_steps+1) % freq == 0.  out_mae_dev: f32[1]. */
+int prl_dqn_learn_batch(prl_dqn *dqn, int batch, const float *state, const int64_t *action,
+                        const float *reward, const float *next_state, const uint8_t *terminated,
+                        const float *next_avail, const uint8_t *next_unavail_mask,
+                        int do_target_update, float *out_mae_dev, float *out_q_dev,
+                        float *out_y_dev, void *stream);
+
+/* Q(s, a) for every action (act(): deep_td_learning.py:200-254): device
+ * state f32[n][obs_dim] -> out_q f32[n][n_actions], online (target=0) or
+ * target network. */
+int prl_dqn_q_values(prl_dqn *dqn, int n, const float *state, int target, float *out_q_dev,
+                     void *stream);
+
+/* how the last prl_dqn_learn was executed (bench / tests): number of kernel
+ * launches, CTAs of the persistent learner kernel, rows per CTA */
+int prl_dqn_last_launch_info(const prl_dqn *dqn, int32_t *launches, int32_t *ctas,
+                             int32_t *rows_per_cta);
+
+/* Device timing of the persistent learner kernel alone (CUDA events recorded on
+ * the launch stream around the kernel); used by bench.py for the roofline line.
+ * prl_dqn_last_kernel_ms synchronises on the end event. */
+int prl_dqn_set_timing(prl_dqn *dqn, int enable);
+int prl_dqn_last_kernel_ms(prl_dqn *dqn, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEARL_B200_H */

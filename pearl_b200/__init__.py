@@ -1,0 +1,14 @@
+"""pearl_b200 — B200-native (sm_100a) learner hot path of facebookresearch/Pearl:
+`ReplayBuffer.sample -> PolicyLearner.learn()` behind Pearl's own plugin API.
+
+    from pearl_b200 import B200ReplayBuffer, B200DeepQLearning, B200DoubleDQN
+
+Hand-written CUDA in libpearlb200.so (C ABI: include/pearl_b200.h), called through
+ctypes; PyTorch only allocates memory and provides streams.  No CPU fallback.
+"""
+from ._compat import HAVE_PEARL, OneHotActionTensorRepresentationModule, TransitionBatch  # noqa: F401
+from .dqn import B200DeepQLearning, B200DoubleDQN  # noqa: F401
+from .replay_buffer import B200ReplayBuffer  # noqa: F401
+
+__all__ = ["B200ReplayBuffer", "B200DeepQLearning", "B200DoubleDQN", "TransitionBatch",
+           "OneHotActionTensorRepresentationModule", "HAVE_PEARL"]

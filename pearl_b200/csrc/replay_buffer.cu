@@ -1,0 +1,626 @@
+// replay_buffer.cu — GPU-resident ring replay buffer, MT19937-exact sampler,
+// gather.  Replaces pearl/replay_buffers/{tensor_based,basic}_replay_buffer.py
+// (see include/pearl_b200.h for the per-function reference citations).
+#include <stdarg.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace prl {
+thread_local char g_err[512] = "";
+}
+using namespace prl;
+
+// --------------------------------------------------------------------------
+// library
+// --------------------------------------------------------------------------
+extern "C" int prl_abi_version(void) { return PRL_ABI_VERSION; }
+extern "C" const char *prl_last_error(void) { return g_err; }
+
+extern "C" int prl_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(PRL_EUNSUPPORTED, "no CUDA device (%s); libpearlb200 has no CPU path",
+                    e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    PRL_REQUIRE(device >= 0 && device < n, "device %d out of range (0..%d)", device, n - 1);
+    PRL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    PRL_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        return fail(PRL_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, p.major, p.minor);
+    return PRL_OK;
+}
+
+extern "C" int prl_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+}
+
+// --------------------------------------------------------------------------
+// layout
+// --------------------------------------------------------------------------
+extern "C" int prl_buf_layout_of(const prl_buf_desc *d, prl_buf_layout *out) {
+    PRL_REQUIRE(d && out, "null argument");
+    PRL_REQUIRE(d->capacity > 0 && d->capacity < (1ll << 31), "capacity must be in [1, 2^31)");
+    PRL_REQUIRE(d->obs_dim > 0, "obs_dim must be positive");
+    const bool disc = d->flags & PRL_BUF_DISCRETE, cont = d->flags & PRL_BUF_CONTINUOUS;
+    PRL_REQUIRE(disc != cont, "exactly one of PRL_BUF_DISCRETE / PRL_BUF_CONTINUOUS");
+    if (disc) PRL_REQUIRE(d->n_actions > 0 && d->n_actions <= 255, "n_actions must be in [1,255]");
+    if (cont) PRL_REQUIRE(d->act_dim > 0, "act_dim must be positive");
+    if (d->flags & PRL_BUF_DYNAMIC_ACTIONS) PRL_REQUIRE(disc, "dynamic action sets need a discrete space");
+    const int obs_p = round_up(d->obs_dim, 4);
+    prl_buf_layout l;
+    l.off_state = 0;
+    l.off_next_state = obs_p;
+    l.off_action = 2 * obs_p;
+    l.act_words = disc ? 1 : d->act_dim;
+    l.off_reward = l.off_action + l.act_words;
+    l.off_flags = l.off_reward + 1;
+    l.off_avail = l.off_flags + 1;
+    int words = l.off_avail;
+    if (d->flags & PRL_BUF_DYNAMIC_ACTIONS) words += (d->n_actions + 3) / 4;
+    l.record_words = round_up(words, 4);
+    l.storage_bytes = d->capacity * (int64_t)l.record_words * 4;
+    *out = l;
+    return PRL_OK;
+}
+
+// --------------------------------------------------------------------------
+// create / destroy / occupancy
+// --------------------------------------------------------------------------
+static const int64_t kStageBytes = 8ll << 20;  // per pinned staging buffer
+
+extern "C" int prl_buf_create(prl_buf **out, const prl_buf_desc *desc, void *storage_dev,
+                              uint32_t *mt_state_dev) {
+    PRL_REQUIRE(out && desc && storage_dev && mt_state_dev, "null argument");
+    PRL_REQUIRE(((uintptr_t)storage_dev & 15) == 0, "storage must be 16-byte aligned");
+    prl_buf_layout lay;
+    int rc = prl_buf_layout_of(desc, &lay);
+    if (rc) return rc;
+    prl_buf *b = new (std::nothrow) prl_buf();
+    if (!b) return fail(PRL_ENOMEM, "out of host memory");
+    b->desc = *desc;
+    b->lay = lay;
+    b->records = (uint32_t *)storage_dev;
+    b->mt_state = mt_state_dev;
+    b->len = 0;
+    b->write_pos = 0;
+    b->stage[0] = b->stage[1] = nullptr;
+    b->stage_records = 0;
+    b->stage_next = 0;
+    cudaGetDevice(&b->device);
+    *out = b;
+    return PRL_OK;
+}
+
+extern "C" int prl_buf_destroy(prl_buf *b) {
+    if (!b) return PRL_OK;
+    for (int i = 0; i < 2; i++)
+        if (b->stage[i]) {
+            cudaEventSynchronize(b->stage_done[i]);
+            cudaEventDestroy(b->stage_done[i]);
+            cudaFreeHost(b->stage[i]);
+        }
+    delete b;
+    return PRL_OK;
+}
+
+extern "C" int64_t prl_buf_len(const prl_buf *b) { return b ? b->len : 0; }
+extern "C" int64_t prl_buf_capacity(const prl_buf *b) { return b ? b->desc.capacity : 0; }
+extern "C" int64_t prl_buf_head(const prl_buf *b) {
+    if (!b) return 0;
+    int64_t h = b->write_pos - b->len;
+    return h < 0 ? h + b->desc.capacity : h;
+}
+extern "C" int prl_buf_clear(prl_buf *b) {
+    PRL_REQUIRE(b, "null buffer");
+    b->len = 0;
+    b->write_pos = 0;
+    return PRL_OK;
+}
+extern "C" int prl_buf_set_occupancy(prl_buf *b, int64_t len, int64_t head) {
+    PRL_REQUIRE(b, "null buffer");
+    PRL_REQUIRE(len >= 0 && len <= b->desc.capacity, "len out of range");
+    PRL_REQUIRE(head >= 0 && head < b->desc.capacity, "head out of range");
+    b->len = len;
+    b->write_pos = (head + len) % b->desc.capacity;
+    return PRL_OK;
+}
+
+// --------------------------------------------------------------------------
+// push
+// --------------------------------------------------------------------------
+static inline uint32_t f2u(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+
+static int ensure_staging(prl_buf *b) {
+    if (b->stage[0]) return PRL_OK;
+    int64_t rec_bytes = (int64_t)b->lay.record_words * 4;
+    int64_t n = kStageBytes / rec_bytes;
+    if (n < 1) n = 1;
+    for (int i = 0; i < 2; i++) {
+        PRL_CUDA(cudaHostAlloc((void **)&b->stage[i], n * rec_bytes, cudaHostAllocDefault));
+        PRL_CUDA(cudaEventCreateWithFlags(&b->stage_done[i], cudaEventDisableTiming));
+    }
+    b->stage_records = n;
+    return PRL_OK;
+}
+
+static int check_push_args(const prl_buf *b, int64_t n, const void *state, const void *action,
+                           const void *reward, const void *terminated, const void *truncated,
+                           const void *ids, const void *cnt) {
+    PRL_REQUIRE(b, "null buffer");
+    PRL_REQUIRE(n >= 0, "negative count");
+    if (n == 0) return PRL_OK;
+    PRL_REQUIRE(state && action && reward && terminated && truncated, "null field array");
+    PRL_REQUIRE((ids == nullptr) == (cnt == nullptr), "next_avail_ids and next_avail_cnt go together");
+    if (ids)
+        PRL_REQUIRE(b->desc.flags & PRL_BUF_DYNAMIC_ACTIONS,
+                    "buffer was created without PRL_BUF_DYNAMIC_ACTIONS");
+    return PRL_OK;
+}
+
+extern "C" int prl_buf_push_host(prl_buf *b, int64_t n, const float *state, const void *action,
+                                 const float *reward, const float *next_state,
+                                 const uint8_t *terminated, const uint8_t *truncated,
+                                 const uint8_t *next_avail_ids, const int32_t *next_avail_cnt,
+                                 void *stream_) {
+    int rc = check_push_args(b, n, state, action, reward, terminated, truncated, next_avail_ids,
+                             next_avail_cnt);
+    if (rc || n == 0) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    rc = ensure_staging(b);
+    if (rc) return rc;
+    const prl_buf_layout &L = b->lay;
+    const int obs = b->desc.obs_dim, A = b->desc.n_actions, W = L.record_words;
+    const int64_t C = b->desc.capacity;
+    // only the last `capacity` transitions of an oversized push can survive
+    int64_t skip = n > C ? n - C : 0;
+    if (skip) {
+        b->write_pos = (b->write_pos + skip) % C;
+        b->len = C;
+    }
+    for (int64_t i0 = skip; i0 < n;) {
+        int64_t m = n - i0;
+        if (m > b->stage_records) m = b->stage_records;
+        if (m > C - b->write_pos) m = C - b->write_pos;  // contiguous run up to the ring end
+        const int sb = b->stage_next;
+        b->stage_next ^= 1;
+        PRL_CUDA(cudaEventSynchronize(b->stage_done[sb]));
+        uint32_t *st = b->stage[sb];
+        for (int64_t i = 0; i < m; i++) {
+            const int64_t s = i0 + i;
+            uint32_t *r = st + i * W;
+            memcpy(r + L.off_state, state + s * obs, 4 * obs);
+            for (int p = obs; p < L.off_next_state; p++) r[p] = 0;
+            if (next_state)
+                memcpy(r + L.off_next_state, next_state + s * obs, 4 * obs);
+            else
+                memset(r + L.off_next_state, 0, 4 * obs);
+            for (int p = L.off_next_state + obs; p < L.off_action; p++) r[p] = 0;
+            if (b->desc.flags & PRL_BUF_DISCRETE)
+                r[L.off_action] = (uint32_t)((const int32_t *)action)[s];
+            else
+                memcpy(r + L.off_action, (const float *)action + s * L.act_words, 4 * L.act_words);
+            r[L.off_reward] = f2u(reward[s]);
+            uint32_t cnt = (b->desc.flags & PRL_BUF_DISCRETE) ? (uint32_t)A : 0u;
+            if (next_avail_cnt) cnt = (uint32_t)next_avail_cnt[s];
+            r[L.off_flags] = (terminated[s] ? 1u : 0u) | (truncated[s] ? 2u : 0u) | (cnt << 8);
+            for (int p = L.off_avail; p < W; p++) r[p] = 0;
+            if (b->desc.flags & PRL_BUF_DYNAMIC_ACTIONS) {
+                uint8_t *ids = (uint8_t *)(r + L.off_avail);
+                if (next_avail_ids)
+                    for (uint32_t a = 0; a < cnt && a < (uint32_t)A; a++) ids[a] = next_avail_ids[s * A + a];
+                else
+                    for (int a = 0; a < A; a++) ids[a] = (uint8_t)a;
+            }
+        }
+        PRL_CUDA(cudaMemcpyAsync(b->records + b->write_pos * W, st, m * (int64_t)W * 4,
+                                 cudaMemcpyHostToDevice, stream));
+        PRL_CUDA(cudaEventRecord(b->stage_done[sb], stream));
+        b->write_pos = (b->write_pos + m) % C;
+        b->len = b->len + m > C ? C : b->len + m;
+        i0 += m;
+    }
+    return PRL_OK;
+}
+
+// K1: pack struct-of-arrays device sources into ring records; one warp per
+// record, lanes stride the record's words (coalesced 128 B stores).
+__global__ void k_pack_records(uint32_t *__restrict__ records, prl_buf_layout L, int obs, int A,
+                               int flags, int64_t capacity, int64_t write_pos, int64_t first,
+                               int64_t n, const float *__restrict__ state,
+                               const void *__restrict__ action, const float *__restrict__ reward,
+                               const float *__restrict__ next_state,
+                               const uint8_t *__restrict__ terminated,
+                               const uint8_t *__restrict__ truncated,
+                               const uint8_t *__restrict__ ids, const int32_t *__restrict__ cnts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    const int64_t s = first + w;
+    uint32_t *r = records + ((write_pos + w) % capacity) * L.record_words;
+    for (int p = lane; p < L.record_words; p += 32) {
+        uint32_t v = 0;
+        if (p < L.off_next_state) {
+            if (p < obs) v = __float_as_uint(state[s * obs + p]);
+        } else if (p < L.off_action) {
+            int q = p - L.off_next_state;
+            if (q < obs && next_state) v = __float_as_uint(next_state[s * obs + q]);
+        } else if (p < L.off_reward) {
+            int q = p - L.off_action;
+            v = (flags & PRL_BUF_DISCRETE) ? (uint32_t)((const int32_t *)action)[s]
+                                           : __float_as_uint(((const float *)action)[s * L.act_words + q]);
+        } else if (p == L.off_reward) {
+            v = __float_as_uint(reward[s]);
+        } else if (p == L.off_flags) {
+            uint32_t c = (flags & PRL_BUF_DISCRETE) ? (uint32_t)A : 0u;
+            if (cnts) c = (uint32_t)cnts[s];
+            v = (terminated[s] ? 1u : 0u) | (truncated[s] ? 2u : 0u) | (c << 8);
+        } else if (flags & PRL_BUF_DYNAMIC_ACTIONS) {
+            int a0 = (p - L.off_avail) * 4;
+            uint32_t c = cnts ? (uint32_t)cnts[s] : (uint32_t)A;
+            for (int j = 0; j < 4; j++) {
+                int a = a0 + j;
+                uint32_t id = 0;
+                if (a < A && (uint32_t)a < c) id = ids ? ids[s * A + a] : (uint32_t)a;
+                v |= id << (8 * j);
+            }
+        }
+        r[p] = v;
+    }
+}
+
+extern "C" int prl_buf_push_device(prl_buf *b, int64_t n, const float *state, const void *action,
+                                   const float *reward, const float *next_state,
+                                   const uint8_t *terminated, const uint8_t *truncated,
+                                   const uint8_t *next_avail_ids, const int32_t *next_avail_cnt,
+                                   void *stream_) {
+    int rc = check_push_args(b, n, state, action, reward, terminated, truncated, next_avail_ids,
+                             next_avail_cnt);
+    if (rc || n == 0) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t C = b->desc.capacity;
+    int64_t first = n > C ? n - C : 0;
+    if (first) {
+        b->write_pos = (b->write_pos + first) % C;
+        b->len = C;
+    }
+    int64_t m = n - first;
+    const int threads = 256;
+    int64_t blocks = (m * 32 + threads - 1) / threads;
+    k_pack_records<<<(unsigned)blocks, threads, 0, stream>>>(
+        b->records, b->lay, b->desc.obs_dim, b->desc.n_actions, b->desc.flags, C, b->write_pos, first,
+        m, state, action, reward, next_state, terminated, truncated, next_avail_ids, next_avail_cnt);
+    PRL_CUDA(cudaGetLastError());
+    b->write_pos = (b->write_pos + m) % C;
+    b->len = b->len + m > C ? C : b->len + m;
+    return PRL_OK;
+}
+
+// --------------------------------------------------------------------------
+// RNG state hand-off
+// --------------------------------------------------------------------------
+extern "C" int prl_rng_set_state(prl_buf *b, const uint32_t *st, void *stream) {
+    PRL_REQUIRE(b && st, "null argument");
+    PRL_REQUIRE(st[624] <= 624, "MT19937 position must be in [0,624]");
+    PRL_CUDA(cudaMemcpyAsync(b->mt_state, st, 625 * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    PRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // `st` may be a temporary
+    return PRL_OK;
+}
+extern "C" int prl_rng_get_state(prl_buf *b, uint32_t *st, void *stream) {
+    PRL_REQUIRE(b && st, "null argument");
+    PRL_CUDA(cudaMemcpyAsync(st, b->mt_state, 625 * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return PRL_OK;
+}
+// CPython init_by_array (Modules/_randommodule.c), done on the host: 624 words.
+extern "C" int prl_rng_seed(prl_buf *b, const uint32_t *key, int key_len, void *stream) {
+    PRL_REQUIRE(b && key && key_len > 0, "bad key");
+    uint32_t st[625];
+    st[0] = 19650218u;
+    for (int i = 1; i < 624; i++) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1, j = 0;
+    for (int k = (624 > key_len ? 624 : key_len); k; k--) {
+        st[i] = (st[i] ^ ((st[i - 1] ^ (st[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        i++, j++;
+        if (i >= 624) { st[0] = st[623]; i = 1; }
+        if (j >= key_len) j = 0;
+    }
+    for (int k = 623; k; k--) {
+        st[i] = (st[i] ^ ((st[i - 1] ^ (st[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        i++;
+        if (i >= 624) { st[0] = st[623]; i = 1; }
+    }
+    st[0] = 0x80000000u;
+    st[624] = 624;
+    return prl_rng_set_state(b, st, stream);
+}
+
+// --------------------------------------------------------------------------
+// K2: MT19937-exact sampler (CPython random.sample, both branches)
+// --------------------------------------------------------------------------
+namespace {
+
+constexpr int MT_N = 624, MT_M = 397;
+constexpr int kSamplerThreads = 256;
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b) {
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+// One MT19937 block regeneration ("twist") by the whole CTA: old -> nw.
+// new[i] depends on old[i], old[i+1] and on old[i+397] (i<227) or new[i-227].
+__device__ void mt_twist_cta(const uint32_t *old, uint32_t *nw) {
+    const int t = threadIdx.x;
+    if (t < MT_N - MT_M) nw[t] = old[t + MT_M] ^ mt_mix(old[t], old[t + 1]);
+    __syncthreads();
+    if (t < MT_N - MT_M) {
+        int i = t + (MT_N - MT_M);  // 227..453
+        nw[i] = nw[i - (MT_N - MT_M)] ^ mt_mix(old[i], old[i + 1]);
+    }
+    __syncthreads();
+    if (t < MT_N - 1 - 2 * (MT_N - MT_M)) {
+        int i = t + 2 * (MT_N - MT_M);  // 454..622
+        nw[i] = nw[i - (MT_N - MT_M)] ^ mt_mix(old[i], old[i + 1]);
+    }
+    if (t == kSamplerThreads - 1) nw[MT_N - 1] = nw[MT_M - 1] ^ mt_mix(old[MT_N - 1], nw[0]);
+    __syncthreads();
+}
+
+struct SamplerShared {
+    uint32_t mt[2][MT_N];
+    int cur;      // which mt[] holds the live block
+    int pos;      // next unread word, 0..624
+    int done;     // completed samples
+    int cnt;      // accepted draws in the current sample
+    uint32_t epoch;
+    int pool_ready;
+};
+
+__device__ __forceinline__ int bit_length(uint32_t n) { return 32 - __clz(n); }
+
+// logical index -> physical slot
+__device__ __forceinline__ int32_t slot_of(uint32_t j, int64_t head, int64_t capacity) {
+    int64_t s = head + (int64_t)j;
+    if (s >= capacity) s -= capacity;
+    return (int32_t)s;
+}
+
+}  // namespace
+
+// dynamic smem: set branch -> uint64 table[cap]; pool branch -> int32 pool[n]
+__global__ void __launch_bounds__(kSamplerThreads, 1)
+k_sample_indices(uint32_t *__restrict__ mt_state, uint32_t n, int k, int rounds, int use_pool,
+                 uint32_t table_cap, int64_t head, int64_t capacity,
+                 int32_t *__restrict__ out_logical, int32_t *__restrict__ out_slot) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ SamplerShared S;
+    unsigned long long *table = reinterpret_cast<unsigned long long *>(dyn);
+    int32_t *pool = reinterpret_cast<int32_t *>(dyn);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < MT_N; i += kSamplerThreads) S.mt[0][i] = mt_state[i];
+    if (!use_pool)
+        for (uint32_t i = tid; i < table_cap; i += kSamplerThreads) table[i] = 0ull;
+    if (tid == 0) {
+        S.cur = 0;
+        S.pos = (int)mt_state[MT_N];
+        S.done = 0;
+        S.cnt = 0;
+        S.epoch = 1;
+        S.pool_ready = 0;
+    }
+    __syncthreads();
+    if (k == 0 || rounds == 0) return;  // random.sample(.., 0) draws nothing
+
+    const int shift = 32 - bit_length(n);  // set branch: getrandbits(n.bit_length())
+
+    while (true) {
+        if (use_pool && !S.pool_ready) {
+            for (uint32_t i = tid; i < n; i += kSamplerThreads) pool[i] = (int32_t)i;
+        }
+        if (S.pos >= MT_N) {  // uniform: S.pos only changes between barriers
+            mt_twist_cta(S.mt[S.cur], S.mt[S.cur ^ 1]);
+            if (tid == 0) { S.cur ^= 1; S.pos = 0; }
+        }
+        __syncthreads();
+        if (use_pool) {
+            // n <= setsize: partial Fisher-Yates on a pool copy, inherently
+            // sequential (Lib/random.py:435-442); only small buffers get here.
+            if (tid == 0) {
+                S.pool_ready = 1;
+                const uint32_t *mt = S.mt[S.cur];
+                int pos = S.pos, cnt = S.cnt, done = S.done;
+                while (pos < MT_N && done < rounds) {
+                    uint32_t m = n - (uint32_t)cnt;           // randbelow(n - i)
+                    uint32_t r = mt_temper(mt[pos++]) >> (32 - bit_length(m));
+                    if (r >= m) continue;
+                    int32_t v = pool[r];
+                    pool[r] = pool[m - 1];
+                    size_t o = (size_t)done * k + cnt;
+                    if (out_logical) out_logical[o] = v;
+                    if (out_slot) out_slot[o] = slot_of((uint32_t)v, head, capacity);
+                    if (++cnt == k) { cnt = 0; done++; S.pool_ready = 0; break; }
+                }
+                S.pos = pos; S.cnt = cnt; S.done = done;
+            }
+        } else if (warp == 0) {
+            // n > setsize: j = randbelow(n) until j not yet selected
+            // (Lib/random.py:443-451).  A word is consumed per draw whether it
+            // is accepted, out of range or a duplicate, so the accepted
+            // sequence is an order-preserving compaction of the word stream.
+            const uint32_t *mt = S.mt[S.cur];
+            int pos = S.pos, cnt = S.cnt, done = S.done;
+            uint32_t epoch = S.epoch;
+            const unsigned lt = (1u << lane) - 1u;
+            while (pos < MT_N && done < rounds) {
+                const int w = pos + lane;
+                const bool inb = w < MT_N;
+                const uint32_t r = inb ? (mt_temper(mt[w]) >> shift) : 0xffffffffu;
+                bool cand = inb && r < n;
+                uint32_t h = (r * 2654435761u) & (table_cap - 1);
+                if (cand) {  // already selected in an earlier chunk of this sample?
+                    while (true) {
+                        unsigned long long e = table[h];
+                        if ((uint32_t)(e >> 32) != epoch) break;
+                        if ((uint32_t)e == r) { cand = false; break; }
+                        h = (h + 1) & (table_cap - 1);
+                    }
+                }
+                const unsigned cm = __ballot_sync(0xffffffffu, cand);
+                bool first = false;
+                if (cand) {  // duplicates inside the chunk: the earliest word wins
+                    unsigned grp = __match_any_sync(cm, r);
+                    first = (grp & lt) == 0;
+                }
+                const unsigned am = __ballot_sync(0xffffffffu, first);
+                const int total = __popc(am), need = k - cnt;
+                int consumed;
+                unsigned take;
+                bool finished = false;
+                if (total >= need) {
+                    const int last = __fns(am, 0, need);  // lane of the need-th accepted word
+                    take = am & ((last == 31) ? 0xffffffffu : ((2u << last) - 1u));
+                    consumed = last + 1;
+                    finished = true;
+                } else {
+                    take = am;
+                    consumed = min(32, MT_N - pos);
+                }
+                if ((take >> lane) & 1u) {
+                    const int rank = __popc(take & lt);
+                    size_t o = (size_t)done * k + cnt + rank;
+                    if (out_logical) out_logical[o] = (int32_t)r;
+                    if (out_slot) out_slot[o] = slot_of(r, head, capacity);
+                    if (!finished) {  // remember it for the rest of this sample
+                        const unsigned long long mine = ((unsigned long long)epoch << 32) | r;
+                        while (true) {
+                            unsigned long long e = table[h];
+                            if ((uint32_t)(e >> 32) == epoch) { h = (h + 1) & (table_cap - 1); continue; }
+                            if (atomicCAS(&table[h], e, mine) == e) break;
+                        }
+                    }
+                }
+                __syncwarp();
+                pos += consumed;
+                if (finished) { done++; cnt = 0; epoch++; } else { cnt += __popc(take); }
+            }
+            if (lane == 0) { S.pos = pos; S.cnt = cnt; S.done = done; S.epoch = epoch; }
+        }
+        __syncthreads();
+        if (S.done >= rounds) break;
+    }
+    // hand the advanced state back (same layout as random.getstate()[1])
+    for (int i = tid; i < MT_N; i += kSamplerThreads) mt_state[i] = S.mt[S.cur][i];
+    if (tid == 0) mt_state[MT_N] = (uint32_t)S.pos;
+}
+
+static int64_t sample_setsize(int64_t k) {  // Lib/random.py:432-434
+    int64_t s = 21;
+    if (k > 5) { int64_t p = 1; while (p < 3 * k) p *= 4; s += p; }
+    return s;
+}
+
+extern "C" int prl_buf_sample_indices(prl_buf *b, int rounds, int k, int32_t *out_logical,
+                                      int32_t *out_slot, void *stream_) {
+    PRL_REQUIRE(b, "null buffer");
+    PRL_REQUIRE(rounds >= 0 && k >= 0, "negative rounds / k");
+    if (k > b->len)
+        return fail(PRL_EINVAL, "Can't get a batch of size %d from a replay buffer with only %lld elements",
+                    k, (long long)b->len);
+    if (rounds == 0 || k == 0) return PRL_OK;
+    const int64_t n = b->len;
+    const int use_pool = n <= sample_setsize(k);
+    uint32_t cap = 0;
+    size_t smem;
+    if (use_pool) {
+        smem = (size_t)n * 4;
+    } else {
+        cap = 64;
+        while (cap < (uint32_t)(2 * k)) cap <<= 1;
+        smem = (size_t)cap * 8;
+    }
+    if (smem > 200 * 1024) return fail(PRL_EUNSUPPORTED, "sample size %d too large for the on-chip sampler", k);
+    PRL_CUDA(cudaFuncSetAttribute(k_sample_indices, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_sample_indices<<<1, kSamplerThreads, smem, (cudaStream_t)stream_>>>(
+        b->mt_state, (uint32_t)n, k, rounds, use_pool, cap, prl_buf_head(b), b->desc.capacity, out_logical,
+        out_slot);
+    PRL_CUDA(cudaGetLastError());
+    return PRL_OK;
+}
+
+// --------------------------------------------------------------------------
+// gather into TransitionBatch field layout; one warp per sampled record
+// --------------------------------------------------------------------------
+__global__ void k_gather(const uint32_t *__restrict__ records, prl_buf_layout L, int obs, int A, int flags,
+                         const int32_t *__restrict__ slots, int k, float *__restrict__ state,
+                         void *__restrict__ action, float *__restrict__ reward,
+                         float *__restrict__ next_state, uint8_t *__restrict__ terminated,
+                         uint8_t *__restrict__ truncated, float *__restrict__ next_avail,
+                         uint8_t *__restrict__ next_mask) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= k) return;
+    const uint32_t *r = records + (size_t)slots[w] * L.record_words;
+    for (int p = lane; p < obs; p += 32) {
+        if (state) state[(size_t)w * obs + p] = __uint_as_float(r[L.off_state + p]);
+        if (next_state) next_state[(size_t)w * obs + p] = __uint_as_float(r[L.off_next_state + p]);
+    }
+    const uint32_t fl = r[L.off_flags];
+    if (lane == 0) {
+        if (reward) reward[w] = __uint_as_float(r[L.off_reward]);
+        if (terminated) terminated[w] = fl & 1u;
+        if (truncated) truncated[w] = (fl >> 1) & 1u;
+    }
+    if (action) {
+        if (flags & PRL_BUF_DISCRETE) {
+            if (lane == 0) ((long long *)action)[w] = (long long)(int32_t)r[L.off_action];
+        } else {
+            for (int p = lane; p < L.act_words; p += 32)
+                ((float *)action)[(size_t)w * L.act_words + p] = __uint_as_float(r[L.off_action + p]);
+        }
+    }
+    if ((flags & PRL_BUF_DISCRETE) && (next_avail || next_mask)) {
+        const uint32_t cnt = (fl >> 8) & 0xffffu;
+        const uint8_t *ids = (const uint8_t *)(r + L.off_avail);
+        for (int a = lane; a < A; a += 32) {
+            const bool avail = (uint32_t)a < cnt;
+            float id = 0.f;
+            if (avail) id = (flags & PRL_BUF_DYNAMIC_ACTIONS) ? (float)ids[a] : (float)a;
+            if (next_avail) next_avail[(size_t)w * A + a] = id;
+            if (next_mask) next_mask[(size_t)w * A + a] = avail ? 0 : 1;
+        }
+    }
+}
+
+extern "C" int prl_buf_gather(const prl_buf *b, const int32_t *slot_dev, int k, float *state, void *action,
+                              float *reward, float *next_state, uint8_t *terminated, uint8_t *truncated,
+                              float *next_avail, uint8_t *next_unavail_mask, void *stream_) {
+    PRL_REQUIRE(b && slot_dev, "null argument");
+    if (k <= 0) return PRL_OK;
+    const int threads = 256;
+    const int blocks = (k * 32 + threads - 1) / threads;
+    k_gather<<<blocks, threads, 0, (cudaStream_t)stream_>>>(b->records, b->lay, b->desc.obs_dim,
+                                                            b->desc.n_actions, b->desc.flags, slot_dev, k,
+                                                            state, action, reward, next_state, terminated,
+                                                            truncated, next_avail, next_unavail_mask);
+    PRL_CUDA(cudaGetLastError());
+    return PRL_OK;
+}

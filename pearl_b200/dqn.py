@@ -1,0 +1,319 @@
+"""B200DeepQLearning / B200DoubleDQN — drop-in policy learners whose `learn()` runs
+in one persistent CUDA kernel (libpearlb200.so), replacing
+
+    PolicyLearner.learn            pearl/policy_learners/policy_learner.py:162-195
+    DeepTDLearning.learn_batch     .../sequential_decision_making/deep_td_learning.py:269-360
+    DeepQLearning / DoubleDQN.get_next_state_values   deep_q_learning.py:130-167, double_dqn.py:29-57
+    VanillaQValueNetwork.get_q_values                 q_value_networks.py:152-174
+    torch.optim.AdamW(amsgrad=True).step, update_target_network (common/utils.py:214-226)
+
+Constructor arguments, attributes (`_Q`, `_Q_target`, `optimizer`, `_training_steps`,
+`batch_size`, ...), `state_dict()` keys and the `learn()` report
+(`{"loss": [mean |q - y| per round]}`) are those of the reference classes, which
+these subclass whenever `pearl` is importable (see _compat.py).
+
+Python keeps torch tensors only as containers: all parameters of `_Q` (and of
+`_Q_target`) are views into ONE flat fp32 CUDA tensor in torch's own parameter
+order, the AdamW state likewise, so `state_dict()` / `optimizer.state_dict()`
+need no copies and the kernels see one contiguous parameter vector.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+import torch
+
+from . import _lib
+from ._compat import _RefDeepQLearning, _RefDoubleDQN, TransitionBatch
+from .replay_buffer import B200ReplayBuffer, _stream_ptr
+
+
+def _linears(qnet) -> list:
+    mods = [m for m in qnet.modules() if isinstance(m, torch.nn.Linear)]
+    others = [m for m in qnet.modules()
+              if not isinstance(m, (torch.nn.Linear, torch.nn.ReLU, torch.nn.Sequential, type(qnet)))]
+    if len(mods) != 3 or others:
+        raise NotImplementedError(
+            "pearl_b200 fuses VanillaQValueNetwork with exactly two hidden Linear+ReLU layers; "
+            f"got {len(mods)} Linear layers and extra modules {[type(m).__name__ for m in others]}")
+    return mods
+
+
+class _B200DQNMixin:
+    _double = False
+
+    def __init__(self, *args: Any, max_rounds_per_call: int = 4096, rows_per_cta: int = 0,
+                 **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        if getattr(self, "_is_conservative", False):
+            raise NotImplementedError("conservative (CQL) updates are outside the fused path")
+        arm = self.action_representation_module
+        if type(arm).__name__ != "OneHotActionTensorRepresentationModule":
+            raise NotImplementedError("the fused Q network assumes a one-hot action representation")
+        self._n_actions = int(arm.max_number_actions)
+        lin = _linears(self._Q)
+        self._obs_dim = lin[0].in_features - self._n_actions
+        self._hidden = (lin[0].out_features, lin[1].out_features)
+        if lin[1].in_features != self._hidden[0] or lin[2].in_features != self._hidden[1] or lin[2].out_features != 1:
+            raise NotImplementedError("unexpected Q-network shape")
+        self._max_rounds = int(max_rounds_per_call)
+        self._rows_per_cta = int(rows_per_cta)
+        self._handle = C.c_void_p(0)
+        self._bound_ptr = None
+        self._bound_batch = 0
+        self._flat = {}
+
+    # ------------------------------------------------------------------ binding
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) and self._handle.value:
+                self._libh.prl_dqn_destroy(self._handle)
+                self._handle = C.c_void_p(0)
+        except Exception:
+            pass
+
+    def _adam_hparams(self) -> dict:
+        opt = self._optimizer
+        if not isinstance(opt, torch.optim.AdamW) or len(opt.param_groups) < 1:
+            raise NotImplementedError("the fused update implements torch.optim.AdamW(amsgrad=True)")
+        g = opt.param_groups[0]
+        if not g.get("amsgrad", False) or g.get("maximize", False):
+            raise NotImplementedError("the fused update implements torch.optim.AdamW(amsgrad=True)")
+        return dict(lr=float(g["lr"]), beta1=float(g["betas"][0]), beta2=float(g["betas"][1]),
+                    eps=float(g["eps"]), weight_decay=float(g["weight_decay"]))
+
+    def _flatten(self, module: torch.nn.Module, device) -> torch.Tensor:
+        params = list(module.parameters())
+        flat = torch.cat([p.detach().reshape(-1).to(device=device, dtype=torch.float32) for p in params])
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.data = flat[off:off + n].view(p.shape)
+            off += n
+        return flat
+
+    def _bind(self, need_batch: int) -> None:
+        params = list(self._Q.parameters())
+        device = params[0].device
+        if device.type != "cuda":
+            raise RuntimeError(
+                "B200 learner parameters are on %s: move the learner to a CUDA device "
+                "(PearlAgent(device_id=0) does this); pearl_b200 has no CPU path" % device)
+        if (self._handle.value and self._bound_ptr == params[0].data_ptr()
+                and need_batch <= self._bound_batch):
+            return
+        old_state = None
+        if self._handle.value:
+            old_state = {k: v.clone() for k, v in self._flat.items() if k in ("m", "v", "vmax")}
+            old_step = int(self._libh.prl_dqn_adam_step(self._handle))
+            self._libh.prl_dqn_destroy(self._handle)
+            self._handle = C.c_void_p(0)
+        self._libh = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
+        hp = self._adam_hparams()
+        w = self._flatten(self._Q, device)
+        wt = self._flatten(self._Q_target, device)
+        P = w.numel()
+        opt_state = self._optimizer.state
+        step = 0
+        if old_state is not None:
+            m, v, vmax, step = old_state["m"].to(device), old_state["v"].to(device), old_state["vmax"].to(device), old_step
+        elif len(opt_state) and all(p in opt_state and "exp_avg" in opt_state[p] for p in params):
+            cat = lambda key: torch.cat([opt_state[p][key].detach().reshape(-1).to(device, torch.float32) for p in params])
+            m, v, vmax = cat("exp_avg"), cat("exp_avg_sq"), cat("max_exp_avg_sq")
+            step = int(float(opt_state[params[0]]["step"]))
+        else:
+            m, v, vmax = (torch.zeros(P, dtype=torch.float32, device=device) for _ in range(3))
+        # expose the flat AdamW state through the torch optimizer (views, no copies)
+        off = 0
+        self._step_tensors = []
+        for p in params:
+            n = p.numel()
+            st = torch.tensor(float(step), dtype=torch.float32)
+            self._step_tensors.append(st)
+            opt_state[p] = dict(step=st, exp_avg=m[off:off + n].view(p.shape),
+                                exp_avg_sq=v[off:off + n].view(p.shape),
+                                max_exp_avg_sq=vmax[off:off + n].view(p.shape))
+            off += n
+        self._bound_batch = max(int(need_batch), int(self._batch_size) if self._batch_size > 0 else 0, 1)
+        cfg = _lib.DqnCfg(
+            obs_dim=self._obs_dim, n_actions=self._n_actions, hidden1=self._hidden[0], hidden2=self._hidden[1],
+            double_dqn=int(self._double), target_update_freq=int(self._target_update_freq),
+            max_batch=self._bound_batch, max_rounds=self._max_rounds, rows_per_cta=self._rows_per_cta,
+            lr=hp["lr"], beta1=hp["beta1"], beta2=hp["beta2"], eps=hp["eps"],
+            weight_decay=hp["weight_decay"], gamma=float(self._discount_factor),
+            tau=float(self._soft_update_tau))
+        if int(self._libh.prl_dqn_param_count(C.byref(cfg))) != P:
+            raise RuntimeError("parameter count mismatch between the module and the fused kernel")
+        ws_bytes = int(self._libh.prl_dqn_workspace_bytes(C.byref(cfg)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        handle = C.c_void_p(0)
+        with torch.cuda.device(device):
+            _lib.check(self._libh.prl_dqn_create(C.byref(handle), C.byref(cfg), _lib.ptr(w), _lib.ptr(wt),
+                                                 _lib.ptr(m), _lib.ptr(v), _lib.ptr(vmax), step, _lib.ptr(ws)))
+        self._handle, self._cfg = handle, cfg
+        self._flat = dict(w=w, wt=wt, m=m, v=v, vmax=vmax, ws=ws)
+        self._bound_ptr = params[0].data_ptr()
+        self._device = device
+
+    def _sync_step_tensors(self) -> None:
+        step = float(self._libh.prl_dqn_adam_step(self._handle))
+        for st in self._step_tensors:
+            st.fill_(step)
+
+    @property
+    def flat_parameters(self) -> torch.Tensor:
+        """The online network's parameters as one flat CUDA tensor (torch order)."""
+        self._bind(1)
+        return self._flat["w"]
+
+    @property
+    def flat_target_parameters(self) -> torch.Tensor:
+        self._bind(1)
+        return self._flat["wt"]
+
+    def adam_state(self) -> dict:
+        self._bind(1)
+        return dict(exp_avg=self._flat["m"], exp_avg_sq=self._flat["v"], max_exp_avg_sq=self._flat["vmax"],
+                    step=int(self._libh.prl_dqn_adam_step(self._handle)))
+
+    def launch_info(self) -> dict:
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._libh.prl_dqn_last_launch_info(self._handle, C.byref(a), C.byref(b), C.byref(c))
+        return dict(launches=a.value, ctas=b.value, rows_per_cta=c.value)
+
+    def set_kernel_timing(self, enable: bool = True) -> None:
+        self._bind(1)
+        _lib.check(self._libh.prl_dqn_set_timing(self._handle, int(enable)))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _lib.check(self._libh.prl_dqn_last_kernel_ms(self._handle, C.byref(ms)))
+        return ms.value
+
+    # ------------------------------------------------------------------ learn
+    def learn(self, replay_buffer, trace: bool = False) -> dict:
+        """`PolicyLearner.learn` (policy_learner.py:162-195): `training_rounds` gradient
+        steps.  With a B200ReplayBuffer the whole call is sampler + one persistent kernel;
+        `trace=True` additionally returns q, y and the sampled logical indices (tests)."""
+        n = len(replay_buffer)
+        if n == 0:
+            return {}
+        bs = n if (self._batch_size == -1 or n < self._batch_size) else self._batch_size
+        rounds = int(self._training_rounds)
+        if not isinstance(replay_buffer, B200ReplayBuffer):
+            report: dict = {}
+            for _ in range(rounds):  # foreign buffer: its own sample(), then the fused update
+                self._training_steps += 1
+                batch = replay_buffer.sample(bs)
+                if isinstance(batch, TransitionBatch):
+                    for k, v in self.learn_batch(self.preprocess_batch(batch)).items():
+                        report.setdefault(k, []).append(v)
+            return report
+        self._bind(bs)
+        dev = self._device
+        if replay_buffer.device != dev:
+            raise RuntimeError(f"replay buffer is on {replay_buffer.device}, learner on {dev}")
+        mae = torch.empty(rounds, dtype=torch.float32, device=dev)
+        q = y = idx = None
+        if trace:
+            q = torch.empty((rounds, bs), dtype=torch.float32, device=dev)
+            y = torch.empty((rounds, bs), dtype=torch.float32, device=dev)
+            idx = torch.empty((rounds, bs), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            stream = _stream_ptr(dev)
+            replay_buffer._rng_push()
+            done = 0
+            while done < rounds:
+                r = min(self._max_rounds, rounds - done)
+                off = lambda t, w=1: C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr() + 4 * done * w)
+                _lib.check(self._libh.prl_dqn_learn(self._handle, replay_buffer.handle, r, bs,
+                                                    int(self._training_steps), off(mae), off(q, bs), off(y, bs),
+                                                    off(idx, bs), stream))
+                self._training_steps += r
+                done += r
+            replay_buffer._rng_pull()
+        self._sync_step_tensors()
+        report = {"loss": mae.cpu().tolist()}  # the one device->host read of the call
+        if trace:
+            report.update(q=q, y=y, idx=idx)
+        return report
+
+    def preprocess_batch(self, batch):
+        """The fused kernel consumes action ids directly; the one-hot expansion of
+        policy_learner.py:197-218 is folded into the first layer (identity history only)."""
+        hsm = getattr(self, "_history_summarization_module", None)
+        if hsm is not None and type(hsm).__name__ != "IdentityHistorySummarizationModule":
+            raise NotImplementedError("only the identity history summarization module is fused")
+        return batch
+
+    def _action_ids(self, a: torch.Tensor, one_hot_last: bool) -> torch.Tensor:
+        A = self._n_actions
+        if a.is_floating_point() and a.dim() >= 2 and a.shape[-1] == A and one_hot_last and A > 1:
+            return a.argmax(-1)
+        if a.dim() >= 2 and a.shape[-1] == 1:
+            a = a.squeeze(-1)
+        return a.long()
+
+    def learn_batch(self, batch) -> dict:
+        """`DeepTDLearning.learn_batch` on a caller-supplied batch (raw ids, or the one-hot
+        tensors the reference's preprocess_batch produces)."""
+        B = len(batch)
+        self._bind(B)
+        dev = self._device
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        state, next_state = f32(batch.state), f32(batch.next_state)
+        reward = f32(batch.reward.reshape(B))
+        term = batch.terminated.reshape(B).to(device=dev, dtype=torch.uint8).contiguous()
+        action = self._action_ids(batch.action.to(dev), batch.action.dim() == 2).reshape(B).contiguous()
+        avail = mask = None
+        if batch.next_available_actions is not None:
+            na = batch.next_available_actions.to(dev)
+            avail = self._action_ids(na, na.dim() == 3).reshape(B, self._n_actions).to(torch.float32).contiguous()
+        if batch.next_unavailable_actions_mask is not None:
+            mask = batch.next_unavailable_actions_mask.to(device=dev, dtype=torch.uint8).contiguous()
+        mae = torch.empty(1, dtype=torch.float32, device=dev)
+        upd = int((self._training_steps + 1) % self._target_update_freq == 0)
+        with torch.cuda.device(dev):
+            _lib.check(self._libh.prl_dqn_learn_batch(
+                self._handle, B, _lib.ptr(state), _lib.ptr(action), _lib.ptr(reward), _lib.ptr(next_state),
+                _lib.ptr(term), _lib.ptr(avail), _lib.ptr(mask), upd, _lib.ptr(mae), None, None,
+                _stream_ptr(dev)))
+        out = mae.item()  # also keeps the inputs alive until the kernel is done
+        self._sync_step_tensors()
+        return {"loss": out}
+
+    # ------------------------------------------------------------------ act
+    def q_values(self, states: torch.Tensor, target: bool = False) -> torch.Tensor:
+        """Q(s, a) for every action id: [n, obs] -> [n, n_actions]."""
+        self._bind(1)
+        dev = self._device
+        s = states.to(device=dev, dtype=torch.float32).reshape(-1, self._obs_dim).contiguous()
+        out = torch.empty((s.shape[0], self._n_actions), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._libh.prl_dqn_q_values(self._handle, s.shape[0], _lib.ptr(s), int(target),
+                                                   _lib.ptr(out), _stream_ptr(dev)))
+        torch.cuda.current_stream(dev).synchronize()
+        return out
+
+    def act(self, subjective_state, available_action_space, exploit: bool = False):
+        """`DeepTDLearning.act` (deep_td_learning.py:200-254)."""
+        qs = self.q_values(torch.as_tensor(subjective_state).reshape(1, -1))[0]
+        ids = available_action_space.actions_batch.reshape(available_action_space.n, -1)[:, 0].long().to(qs.device)
+        q_avail = qs[ids]
+        best = int(torch.argmax(q_avail))
+        exploit_action = available_action_space.actions[best]
+        if exploit or self.exploration_module is None:
+            return exploit_action
+        return self.exploration_module.act(subjective_state=subjective_state, action_space=available_action_space,
+                                           exploit_action=exploit_action, values=q_avail)
+
+
+class B200DeepQLearning(_B200DQNMixin, _RefDeepQLearning):
+    """Drop-in for `pearl...deep_q_learning.DeepQLearning`."""
+    _double = False
+
+
+class B200DoubleDQN(_B200DQNMixin, _RefDoubleDQN):
+    """Drop-in for `pearl...double_dqn.DoubleDQN`."""
+    _double = True

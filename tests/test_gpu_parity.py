@@ -1,0 +1,347 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI via the
+pearl_b200 plugins, against (a) golden fixtures recorded from the reference,
+(b) the CPU oracle on the same seeded inputs, (c) size-independent properties
+at BASELINE.json's full sizes.
+
+Tolerances: indices / gathered transitions bit-exact; Q-values, Bellman targets,
+losses, parameters and AdamW state within 1e-4 relative fp32 (north_star) — the
+assertions below use rtol=1e-4 with a small atol for values near zero, and
+print the achieved maxima.
+"""
+import glob
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+KAT = json.load(open(os.path.join(GOLDEN, "random_sample_kat.json")))["cases"]
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+RTOL = 1e-4
+
+
+def _imports():
+    import pearl_b200
+    from oracle import c_oracle
+    from oracle.pearl_oracle import OracleDQN
+    from oracle.synth import from_fixture, make_transitions
+    return pearl_b200, c_oracle, OracleDQN, from_fixture, make_transitions
+
+
+class _Space:  # minimal DiscreteActionSpace stand-in for the constructor / act()
+    def __init__(self, n):
+        self.n = n
+        self.actions = [torch.tensor([i]) for i in range(n)]
+
+    @property
+    def actions_batch(self):
+        return torch.stack(self.actions)
+
+
+def relerr(got, want, atol):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want) / (np.abs(want) + atol / RTOL)))
+
+
+def assert_close(got, want, what, atol=1e-6):
+    e = relerr(got, want, atol)
+    print(f"    {what}: max rel err {e:.3e}")
+    np.testing.assert_allclose(np.asarray(got), np.asarray(want), rtol=RTOL, atol=atol, err_msg=what)
+
+
+def filled_buffer(n, obs=1, n_act=2, capacity=None, rng="device"):
+    pearl_b200 = _imports()[0]
+    buf = pearl_b200.B200ReplayBuffer(capacity or n, rng=rng)
+    dev = buf.device
+    chunk = 1 << 18
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        buf.push_batch(torch.zeros((m, obs), device=dev), torch.zeros(m, dtype=torch.int32, device=dev),
+                       torch.arange(s, s + m, device=dev, dtype=torch.float32), torch.zeros((m, obs), device=dev),
+                       torch.zeros(m, dtype=torch.bool, device=dev), torch.zeros(m, dtype=torch.bool, device=dev),
+                       max_number_actions=n_act)
+    return buf
+
+
+# --------------------------------------------------------------------------- sampler
+@pytest.mark.parametrize("case", KAT, ids=lambda c: f"seed{c['seed']}_n{c['n']}_k{c['k']}")
+def test_sampler_matches_cpython_known_answers(case):
+    buf = filled_buffer(case["n"])
+    buf.seed(case["seed"])
+    st0 = buf.get_rng_state()
+    assert int(np.bitwise_xor.reduce(st0[:624])) == case["state_before_xor"]
+    logical, slot = buf.sample_indices(case["k"], rounds=case["reps"])
+    assert logical.cpu().tolist() == case["samples"]
+    assert torch.equal(logical, slot)  # ring not wrapped: slot == logical
+    st1 = buf.get_rng_state()
+    assert int(st1[624]) == case["state_after_index"]
+    assert int(np.bitwise_xor.reduce(st1[:624])) == case["state_after_xor"]
+
+
+def test_sampler_full_size_against_c_oracle_and_python_handoff():
+    """cfg2 buffer size (1e6, k=256), many rounds, vs the C restatement; and the
+    rng='python' mode continues / hands back the global `random` state."""
+    _, c_oracle, *_ = _imports()
+    n, k, rounds = 1_000_000, 256, 200
+    buf = filled_buffer(n, rng="python")
+    random.seed(2024)
+    mt = c_oracle.MT(state=np.asarray(random.getstate()[1], dtype=np.uint64).astype(np.uint32))
+    logical, _ = buf.sample_indices(k, rounds=rounds)
+    want = np.stack([mt.sample(n, k) for _ in range(rounds)])
+    got = logical.cpu().numpy()
+    assert np.array_equal(got, want)
+    assert all(len(set(r.tolist())) == k for r in got)
+    assert np.array_equal(np.asarray(random.getstate()[1], dtype=np.uint64).astype(np.uint32), mt.st)
+    # the next draw of the host interpreter continues the same stream
+    assert random.getrandbits(32) == mt.getrandbits32()
+
+
+def test_sample_too_large_raises_value_error():
+    buf = filled_buffer(10)
+    with pytest.raises(ValueError):
+        buf.sample(11)
+
+
+# --------------------------------------------------------------------------- ring + gather
+def test_ring_wraps_fifo_and_gather_is_bit_exact():
+    pearl_b200, _, _, _, make_transitions = _imports()
+    cap, n, obs, A = 37, 100, 7, 3
+    d = make_transitions(n, obs, A, seed=9)
+    buf = pearl_b200.B200ReplayBuffer(cap, rng="device")
+    # mixed single pushes (host), host batches and device batches
+    for i in range(5):
+        buf.push(torch.from_numpy(d["state"][i]), torch.tensor([int(d["action"][i])]), float(d["reward"][i]),
+                 bool(d["terminated"][i]), bool(d["truncated"][i]), curr_available_actions=_Space(A),
+                 next_state=torch.from_numpy(d["next_state"][i]), next_available_actions=_Space(A),
+                 max_number_actions=A)
+    t = lambda k, s, e, dev="cpu": torch.from_numpy(d[k][s:e]).to(dev)
+    buf.push_batch(t("state", 5, 60), t("action", 5, 60), t("reward", 5, 60), t("next_state", 5, 60),
+                   t("terminated", 5, 60), t("truncated", 5, 60))
+    buf.push_batch(t("state", 60, n, "cuda"), t("action", 60, n, "cuda"), t("reward", 60, n, "cuda"),
+                   t("next_state", 60, n, "cuda"), t("terminated", 60, n, "cuda"), t("truncated", 60, n, "cuda"))
+    assert len(buf) == cap
+    buf.seed(5)
+    b = buf.sample(cap)  # k == n: every stored element exactly once (test_trajectories_in_replay_buffer.py)
+    logical = np.arange(n - cap, n)
+    # identify rows through the state (unique with probability 1)
+    pos = {d["state"][j].tobytes(): j for j in logical}
+    rows = [pos[s.tobytes()] for s in b.state.cpu().numpy()]
+    assert sorted(rows) == logical.tolist()
+    rows = np.asarray(rows)
+    assert np.array_equal(b.next_state.cpu().numpy(), d["next_state"][rows])
+    assert np.array_equal(b.reward.cpu().numpy(), d["reward"][rows])
+    assert np.array_equal(b.action.cpu().numpy().reshape(-1), d["action"][rows])
+    assert np.array_equal(b.terminated.cpu().numpy(), d["terminated"][rows])
+    assert b.terminated.dtype == torch.bool and b.truncated.dtype == torch.bool
+    assert b.action.dtype == torch.int64 and b.action.shape == (cap, 1)
+    assert b.next_available_actions.shape == (cap, A, 1) and b.next_unavailable_actions_mask.shape == (cap, A)
+    assert not b.next_unavailable_actions_mask.any()
+    buf.clear()
+    assert len(buf) == 0
+
+
+# --------------------------------------------------------------------------- learner vs golden
+def build_from_fixture(name, rows_per_cta=0):
+    pearl_b200, _, _, from_fixture, _ = _imports()
+    fx = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = json.loads(bytes(fx["config"]).decode())
+    data = from_fixture(fx)
+    A = cfg["n_act"]
+    buf = pearl_b200.B200ReplayBuffer(cfg["capacity"], rng="python")
+    n = cfg["n_push"]
+    kw = {}
+    if cfg["dynamic"]:
+        kw = dict(next_available_ids=torch.from_numpy(data["next_avail_ids"].astype(np.uint8)),
+                  next_available_count=torch.from_numpy(data["next_avail_n"].astype(np.int32)))
+    buf.push_batch(torch.from_numpy(data["state"]), torch.from_numpy(data["action"]), torch.from_numpy(data["reward"]),
+                   torch.from_numpy(data["next_state"]), torch.from_numpy(data["terminated"]),
+                   torch.from_numpy(data["truncated"]), max_number_actions=A, **kw)
+    cls = pearl_b200.B200DoubleDQN if cfg["double"] else pearl_b200.B200DeepQLearning
+    learner = cls(state_dim=cfg["obs"], action_space=_Space(A), hidden_dims=cfg["hidden"],
+                  learning_rate=cfg["lr"], discount_factor=cfg["gamma"], training_rounds=cfg["rounds"],
+                  batch_size=cfg["batch"], target_update_freq=cfg["target_update_freq"],
+                  soft_update_tau=cfg["tau"],
+                  action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(A),
+                  rows_per_cta=rows_per_cta)
+    learner.to("cuda")
+    from oracle.pearl_oracle import load_flat
+    load_flat(learner._Q, fx["init_q"])
+    load_flat(learner._Q_target, fx["init_q_target"])
+    return fx, cfg, data, buf, learner
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_learn_matches_reference_golden(name):
+    """Same pushed transitions, same CPython random state, same initial weights as the
+    recorded reference run: indices bit-exact; q, y, loss, parameters, AdamW state 1e-4."""
+    fx, cfg, data, buf, learner = build_from_fixture(name)
+    random.setstate((3, tuple(int(x) for x in fx["mt_state_before"]), None))
+    total = cfg["rounds"] * cfg["learn_calls"]
+    # run in segments that end at the snapshot rounds (learn() semantics are unchanged:
+    # _training_steps and the RNG state carry over between calls)
+    cuts = sorted(set(cfg["snap_rounds"] + [total]))
+    done, idx, q, y, mae = 0, [], [], [], []
+    for c in cuts:
+        learner._training_rounds = c - done
+        rep = learner.learn(buf, trace=True)
+        idx.append(rep["idx"].cpu().numpy()); q.append(rep["q"].cpu().numpy()); y.append(rep["y"].cpu().numpy())
+        mae += rep["loss"]
+        done = c
+        if c in cfg["snap_rounds"]:
+            assert_close(learner.flat_parameters.cpu().numpy(), fx[f"q_after_{c}"], f"{name} params after {c}")
+            assert_close(learner.flat_target_parameters.cpu().numpy(), fx[f"qt_after_{c}"],
+                         f"{name} target params after {c}")
+    assert np.array_equal(np.concatenate(idx), fx["idx"]), "sampled indices differ from the reference"
+    after = np.asarray(random.getstate()[1], dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(after, fx["mt_state_after"]), "python random state not handed back correctly"
+    assert_close(np.concatenate(q), fx["q"], f"{name} q")
+    assert_close(np.concatenate(y), fx["y"], f"{name} y")
+    assert_close(np.asarray(mae), fx["mae"], f"{name} loss")
+    st = learner.adam_state()
+    assert st["step"] == total
+    assert_close(st["exp_avg"].cpu().numpy(), fx["exp_avg"], f"{name} exp_avg", atol=1e-7)
+    assert_close(st["exp_avg_sq"].cpu().numpy(), fx["exp_avg_sq"], f"{name} exp_avg_sq", atol=1e-9)
+    assert_close(st["max_exp_avg_sq"].cpu().numpy(), fx["max_exp_avg_sq"], f"{name} max_exp_avg_sq", atol=1e-9)
+    # state_dict keys of the reference module tree
+    keys = set(learner.state_dict().keys())
+    for net in ("_Q", "_Q_target"):
+        for i in range(3):
+            assert f"{net}._model.{i}.0.weight" in keys and f"{net}._model.{i}.0.bias" in keys
+    info = learner.launch_info()
+    assert info["launches"] == 2 and info["ctas"] >= 1
+
+
+@pytest.mark.parametrize("rows", [1, 2, 8, 16])
+def test_tiling_does_not_change_results_beyond_tolerance(rows):
+    fx, cfg, data, buf, learner = build_from_fixture("dqn_cfg2_pool", rows_per_cta=rows)
+    random.setstate((3, tuple(int(x) for x in fx["mt_state_before"]), None))
+    learner._training_rounds = 10
+    rep = learner.learn(buf, trace=True)
+    assert np.array_equal(rep["idx"].cpu().numpy(), fx["idx"][:10])
+    assert_close(rep["q"].cpu().numpy(), fx["q"][:10], f"rows={rows} q")
+    assert_close(learner.flat_parameters.cpu().numpy(), fx["q_after_10"], f"rows={rows} params")
+    assert learner.launch_info()["rows_per_cta"] == rows
+
+
+def test_learn_is_deterministic():
+    outs = []
+    for _ in range(2):
+        fx, cfg, data, buf, learner = build_from_fixture("ddqn_setbranch")
+        random.setstate((3, tuple(int(x) for x in fx["mt_state_before"]), None))
+        learner.learn(buf)
+        outs.append(learner.flat_parameters.clone())
+    assert torch.equal(outs[0], outs[1])
+
+
+# --------------------------------------------------------------------------- learn_batch / q_values vs oracle
+@pytest.mark.parametrize("double", [False, True])
+def test_learn_batch_and_q_values_match_oracle(double):
+    pearl_b200, _, OracleDQN, _, make_transitions = _imports()
+    obs, A, hidden, B = 12, 6, (24, 20), 40
+    d = make_transitions(B, obs, A, seed=77, dynamic=True)
+    torch.manual_seed(3)
+    cls = pearl_b200.B200DoubleDQN if double else pearl_b200.B200DeepQLearning
+    learner = cls(state_dim=obs, action_space=_Space(A), hidden_dims=list(hidden), training_rounds=1,
+                  batch_size=B, target_update_freq=3, soft_update_tau=0.3,
+                  action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(A)).to("cuda")
+    from oracle.pearl_oracle import flat
+    orc = OracleDQN(obs, A, hidden, batch_size=B, target_update_freq=3, tau=0.3, double=double,
+                    init_q=flat(learner._Q).cpu(), init_q_target=flat(learner._Q_target).cpu())
+    # perturb the target so that online != target
+    with torch.no_grad():
+        for p, po in zip(learner._Q_target.parameters(), orc.Qt.parameters()):
+            noise = torch.randn(p.shape) * 0.05
+            p.add_(noise.to(p.device)); po.add_(noise)
+    states = torch.from_numpy(d["state"])
+    qv = learner.q_values(states).cpu()
+    eye = torch.eye(A).unsqueeze(0).expand(B, A, A)
+    with torch.no_grad():
+        want = orc._q_values(orc.Q, states, eye)
+    assert_close(qv.numpy(), want.numpy(), "q_values")
+    # arbitrary (non-prefix) availability masks
+    g = torch.Generator().manual_seed(1)
+    mask = torch.rand((B, A), generator=g) < 0.4
+    mask[mask.all(1), 0] = False  # keep at least one action available
+    avail = torch.arange(A).float().view(1, A, 1).expand(B, A, 1).clone()
+    batch = pearl_b200.TransitionBatch(
+        state=states, action=torch.from_numpy(d["action"]).view(B, 1), reward=torch.from_numpy(d["reward"]),
+        next_state=torch.from_numpy(d["next_state"]), terminated=torch.from_numpy(d["terminated"]),
+        truncated=torch.from_numpy(d["truncated"]), next_available_actions=avail,
+        next_unavailable_actions_mask=mask)
+    for step in range(4):  # training_steps stays 0 in learn_batch (reference quirk): no target update
+        got = learner.learn_batch(batch)["loss"]
+        b = dict(state=states, action=orc._one_hot(batch.action), reward=batch.reward, terminated=batch.terminated,
+                 next_state=batch.next_state, next_available_actions=orc._one_hot(avail),
+                 next_unavailable_actions_mask=mask)
+        want_loss = orc.learn_batch(b)
+        assert abs(got - want_loss) <= RTOL * abs(want_loss) + 1e-6
+    assert_close(learner.flat_parameters.cpu().numpy(), flat(orc.Q).numpy(), "params after learn_batch x4")
+    assert_close(learner.flat_target_parameters.cpu().numpy(), flat(orc.Qt).numpy(), "target after learn_batch x4")
+
+
+def test_empty_buffer_learn_returns_empty_report():
+    pearl_b200 = _imports()[0]
+    buf = pearl_b200.B200ReplayBuffer(8)
+    learner = pearl_b200.B200DeepQLearning(
+        state_dim=4, action_space=_Space(2), hidden_dims=[8, 8],
+        action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(2)).to("cuda")
+    assert learner.learn(buf) == {}
+
+
+# --------------------------------------------------------------------------- full size (BASELINE cfg2)
+def test_full_size_cfg2_against_oracle_on_the_sampled_batches():
+    """obs=128, A=16, [64,64], B=256 on a 1e6-transition buffer: the learner's own sampled
+    indices (bit-exact vs the C oracle) select the batches the torch oracle replays."""
+    pearl_b200, c_oracle, OracleDQN, _, _ = _imports()
+    n, obs, A, B, rounds = 1_000_000, 128, 16, 256, 12
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    buf = pearl_b200.B200ReplayBuffer(n, rng="python")
+    host = {}
+    chunk = 250_000
+    for s in range(0, n, chunk):
+        st = torch.randn((chunk, obs), generator=g, device="cuda")
+        ns = torch.randn((chunk, obs), generator=g, device="cuda")
+        rw = torch.randn(chunk, generator=g, device="cuda")
+        tm = torch.rand(chunk, generator=g, device="cuda") < 0.02
+        ac = (torch.arange(s, s + chunk, device="cuda") % A).to(torch.int32)
+        buf.push_batch(st, ac, rw, ns, tm, torch.zeros_like(tm), max_number_actions=A)
+        host[s] = (st, ns, rw, tm, ac)
+    assert len(buf) == n
+    torch.manual_seed(1234)
+    learner = pearl_b200.B200DeepQLearning(
+        state_dim=obs, action_space=_Space(A), hidden_dims=[64, 64], training_rounds=rounds, batch_size=B,
+        target_update_freq=10, soft_update_tau=0.75,
+        action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(A)).to("cuda")
+    from oracle.pearl_oracle import flat
+    orc = OracleDQN(obs, A, (64, 64), batch_size=B, target_update_freq=10, tau=0.75,
+                    init_q=flat(learner._Q).cpu(), init_q_target=flat(learner._Q_target).cpu())
+    random.seed(1234)
+    mt = c_oracle.MT(state=np.asarray(random.getstate()[1], dtype=np.uint64).astype(np.uint32))
+    rep = learner.learn(buf, trace=True)
+    idx = rep["idx"].cpu().numpy()
+    assert np.array_equal(idx, np.stack([mt.sample(n, B) for _ in range(rounds)]))
+
+    full = [torch.cat([host[s][f] for s in sorted(host)]) for f in range(5)]
+    host.clear()
+
+    def rows(ix):
+        ix = torch.from_numpy(ix.astype(np.int64)).cuda()
+        return [f[ix].cpu() for f in full]
+
+    eye = torch.eye(A).unsqueeze(0).expand(B, A, A)
+    losses = []
+    for r in range(rounds):
+        st, ns, rw, tm, ac = rows(idx[r])
+        orc.training_steps += 1
+        b = dict(state=st, action=orc._one_hot(ac.long()), reward=rw, terminated=tm, next_state=ns,
+                 next_available_actions=eye, next_unavailable_actions_mask=torch.zeros((B, A), dtype=torch.bool))
+        losses.append(orc.learn_batch(b))
+    assert_close(np.asarray(rep["loss"]), np.asarray(losses), "cfg2 loss")
+    assert_close(learner.flat_parameters.cpu().numpy(), flat(orc.Q).numpy(), "cfg2 params after 12 rounds")
+    assert_close(learner.flat_target_parameters.cpu().numpy(), flat(orc.Qt).numpy(), "cfg2 target params")
