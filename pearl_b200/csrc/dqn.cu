@@ -25,6 +25,9 @@
 #include <new>
 
 #include "common.cuh"
+#include "sampler.cuh"
+
+int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *smem_bytes);
 
 namespace cg = cooperative_groups;
 using namespace prl;
@@ -35,7 +38,7 @@ constexpr int NT = 256;      // threads per CTA
 constexpr int NC = 64;       // output columns per staged weight panel
 constexpr int KCMAX = 128;   // K extent of a staged weight panel
 constexpr int MB = 64;       // rows per register-tiled row block
-constexpr int STAGE_FLOATS = NC * (KCMAX + 4);
+constexpr int STAGE_FLOATS = KCMAX * (NC + 4);  // >= NC * (KCMAX + 4): either panel orientation
 constexpr int RED_FLOATS = NT * 16;
 
 struct Dims {
@@ -97,6 +100,11 @@ struct LearnArgs {
     Plan plan;
     int B, R, rounds, mch, double_dqn, freq;
     int first_update;         // apply the soft target update before round 0
+    int G;                    // learner CTAs; CTA index G (if fused_sampler) produces the indices
+    int fused_sampler;
+    SamplerParams sp;         // out_slot == slots (+ optional out_logical)
+    uint32_t *mt_state;
+    long long *prof;          // optional [rounds][16] SM-clock stamps of CTA 0 (developer profiling)
     long long steps0;         // learner._training_steps before the call
     float decay, omb1, beta2, omb2, eps, gamma, tau, omtau, inv_b2;  // fp32 images of the scalars
 };
@@ -104,15 +112,26 @@ struct LearnArgs {
 // ---------------------------------------------------------------------------
 // out[m][n] = act(bias[n] + sum_k X[m][k] * Wop[n][k]),  m < M, n < N, k < K
 //   X   : shared, row stride ldx (multiple of 4, rows 16-byte aligned)
-//   Wop : global; !trans: W[n*ldw + k]   trans: W[k*ldw + n]
+//   Wop : global.  NN == false: Wop[n][k] = W[n*ldw + k]  (y = x W^T, forward)
+//                  NN == true : Wop[n][k] = W[k*ldw + n]  (y = x W,   backward wrt input)
 //   out : shared, row stride ldo
-// 64x64 output blocks, 4x4 register tiles; for blocks with few rows the idle
-// thread rows split K instead and the partial sums are combined through `red`.
+// The weight panel (<= 64 outputs x <= 128 k) is streamed L2 -> shared with
+// 16-byte cp.async (all chunks in flight at once; zero-filled tails), then
+// consumed by 4x4 register tiles.  Row blocks with few rows let the idle thread
+// rows split K; the partial sums are combined in fixed order through `red`.
 // ---------------------------------------------------------------------------
-__device__ void cta_linear(const float *X, int ldx, int M, const float *__restrict__ W, int ldw, bool trans,
-                           int N, int K, const float *__restrict__ bias, bool relu, float *out, int ldo,
-                           float *stage, float *red) {
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+
+template <bool NN>
+__device__ void cta_linear(const float *X, int ldx, int M, const float *__restrict__ W, int ldw, int N, int K,
+                           const float *__restrict__ bias, bool relu, float *out, int ldo, float *stage,
+                           float *red) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((ldw & 3) == 0);
     for (int n0 = 0; n0 < N; n0 += NC) {
         const int nc = min(NC, N - n0);
         for (int m0 = 0; m0 < M; m0 += MB) {
@@ -138,71 +157,118 @@ __device__ void cta_linear(const float *X, int ldx, int M, const float *__restri
             for (int k0 = 0; k0 < K; k0 += KCMAX) {
                 const int kc = min(KCMAX, K - k0);
                 const int kc4 = round_up(kc, 4);
-                const int lds = kc4 | 4;  // (lds/4) odd: conflict-free float4 rows
-                __syncthreads();          // previous panel fully consumed
-                if (!trans) {
-                    const int tr = tid / kc4, tc = tid - tr * kc4, rpp = NT / kc4;
-                    if (tr < rpp)
-                        for (int n = tr; n < NC; n += rpp) {
-                            float v = 0.f;
-                            if (n < nc && tc < kc) v = __ldcg(W + (size_t)(n0 + n) * ldw + k0 + tc);
-                            stage[n * lds + tc] = v;
-                        }
-                } else {
-                    const int tr = tid >> 6, tc = tid & 63;  // tc: n (contiguous in memory), tr: k
-                    for (int k = tr; k < kc4; k += NT / 64) {
-                        float v = 0.f;
-                        if (tc < nc && k < kc) v = __ldcg(W + (size_t)(k0 + k) * ldw + n0 + tc);
-                        stage[tc * lds + k] = v;
+                // panel geometry: NT rows = outputs, cols = k; NN rows = k, cols = outputs
+                const int prow = NN ? kc4 : NC, pcol = NN ? NC : kc4;
+                const int vrow = NN ? kc : nc, vcol = NN ? nc : kc;       // valid extent
+                const int lds = NN ? (NC + 4) : (kc4 | 4);                // (lds/4) odd
+                const float *src = NN ? (W + (size_t)k0 * ldw + n0) : (W + (size_t)n0 * ldw + k0);
+                __syncthreads();  // previous panel fully consumed
+                if (vec_ok) {
+                    const int c4 = pcol >> 2;
+                    for (int e = tid; e < prow * c4; e += NT) {
+                        const int r = e / c4, c = (e - r * c4) * 4;
+                        int nb = 0;
+                        if (r < vrow) nb = 4 * max(0, min(4, vcol - c));
+                        cp_async16_zfill(stage + r * lds + c, nb ? (src + (size_t)r * ldw + c) : W, nb);
                     }
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                } else {  // unaligned parameter block: scalar loads, 8 in flight per thread
+                    const int tr = tid / pcol, tc = tid - tr * pcol, rpp = NT / pcol;
+                    if (tr < rpp)
+                        for (int r = tr; r < prow; r += rpp * 8) {
+                            float v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const int rr = r + u * rpp;
+                                v[u] = (rr < vrow && tc < vcol) ? __ldcg(src + (size_t)rr * ldw + tc) : 0.f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const int rr = r + u * rpp;
+                                if (rr < prow) stage[rr * lds + tc] = v[u];
+                            }
+                        }
                 }
                 __syncthreads();
                 if (active) {
                     const int ksl = round_up((kc4 + KS - 1) / KS, 4);
                     const int kb = kz * ksl, ke = min(kc4, kb + ksl);
-                    for (int k = kb; k < ke; k += 4) {
-                        float4 a[4], b[4];
+                    if (!NN) {
+                        for (int k = kb; k < ke; k += 4) {
+                            float4 a[4], b[4];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(xr[i] + k0 + k);
+                            for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(xr[i] + k0 + k);
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            b[j] = *reinterpret_cast<const float4 *>(stage + (tx + 16 * j) * lds + k);
+                            for (int j = 0; j < 4; j++)
+                                b[j] = *reinterpret_cast<const float4 *>(stage + (tx + 16 * j) * lds + k);
 #pragma unroll
-                        for (int i = 0; i < 4; i++)
+                            for (int i = 0; i < 4; i++)
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
-                                acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
-                                acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
-                                acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+                                for (int j = 0; j < 4; j++) {
+                                    acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+                                    acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+                                    acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+                                    acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+                                }
+                        }
+                    } else {
+                        for (int k = kb; k < ke; k += 4) {
+                            float4 a[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const float4 *>(xr[i] + k0 + k);
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) {
+                                const float4 b = *reinterpret_cast<const float4 *>(stage + (k + kk) * lds + tx * 4);
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                                    acc[i][0] = fmaf(av, b.x, acc[i][0]);
+                                    acc[i][1] = fmaf(av, b.y, acc[i][1]);
+                                    acc[i][2] = fmaf(av, b.z, acc[i][2]);
+                                    acc[i][3] = fmaf(av, b.w, acc[i][3]);
+                                }
                             }
+                        }
                     }
                 }
             }
-            if (KS > 1) {  // combine the K slices (fixed order kz = 0,1,2,...)
+            if (KS > 1) {
+                // combine the K slices in fixed order kz = 0,1,2,...: every thread reduces and
+                // finishes a strided share of the block's outputs (not just the kz == 0 threads)
                 __syncthreads();
 #pragma unroll
                 for (int e = 0; e < 16; e++) red[(ty * 16 + e) * 16 + tx] = acc[e >> 2][e & 3];
                 __syncthreads();
-                if (kz == 0 && active)
-                    for (int z = 1; z < KS; z++)
-#pragma unroll
-                        for (int e = 0; e < 16; e++)
-                            acc[e >> 2][e & 3] += red[(((z << sh) + mt) * 16 + e) * 16 + tx];
-            }
-            if (kz == 0 && active) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int m = m0 + mt * 4 + i;
-                    if (m >= M) continue;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int n = n0 + tx + 16 * j;
-                        if (n >= N) continue;
-                        float v = acc[i][j];
+                const int n_out = mt_cnt * 256;  // (mt, e, tx)
+                for (int o = tid; o < n_out; o += NT) {
+                    const int otx = o & 15, oe = (o >> 4) & 15, omt = o >> 8;
+                    float v = 0.f;
+                    for (int z = 0; z < KS; z++) v += red[(((z << sh) + omt) * 16 + oe) * 16 + otx];
+                    const int m = m0 + omt * 4 + (oe >> 2);
+                    const int n = n0 + (NN ? otx * 4 + (oe & 3) : otx + 16 * (oe & 3));
+                    if (m < M && n < N) {
                         if (bias) v += __ldcg(bias + n);
                         if (relu) v = fmaxf(v, 0.f);
                         out[(size_t)m * ldo + n] = v;
+                    }
+                }
+            } else if (active) {
+                float bv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int n = n0 + (NN ? tx * 4 + j : tx + 16 * j);
+                    bv[j] = (bias && n < N) ? __ldcg(bias + n) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int m = m0 + mt * 4 + i;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int n = n0 + (NN ? tx * 4 + j : tx + 16 * j);
+                        float v = acc[i][j] + bv[j];
+                        if (relu) v = fmaxf(v, 0.f);
+                        if (m < M && n < N) out[(size_t)m * ldo + n] = v;
                     }
                 }
             }
@@ -226,10 +292,14 @@ __device__ void cta_outer(const float *dY, int ldy, const float *X, int ldx, int
             acc.z = fmaf(dy, x.z, acc.z); acc.w = fmaf(dy, x.w, acc.w);
         }
         float *o = out + (size_t)n * ldw + k;
-        o[0] = acc.x;
-        if (k + 1 < K) o[1] = acc.y;
-        if (k + 2 < K) o[2] = acc.z;
-        if (k + 3 < K) o[3] = acc.w;
+        if (k + 3 < K && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            *reinterpret_cast<float4 *>(o) = acc;
+        } else {
+            o[0] = acc.x;
+            if (k + 1 < K) o[1] = acc.y;
+            if (k + 2 < K) o[2] = acc.z;
+            if (k + 3 < K) o[3] = acc.w;
+        }
     }
 }
 
@@ -237,9 +307,15 @@ __device__ void cta_outer(const float *dY, int ldy, const float *X, int ldx, int
 __device__ void cta_head(const float *H, int ldh, int M, const float *__restrict__ w3, float b3, int H2,
                          float *q) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float wv[8];  // this lane's slice of w3, fetched from L2 once (covers H2 <= 256 without reloads)
+#pragma unroll
+    for (int u = 0; u < 8; u++) wv[u] = (lane + 32 * u < H2) ? __ldcg(w3 + lane + 32 * u) : 0.f;
     for (int m = warp; m < M; m += NT / 32) {
         float s = 0.f;
-        for (int j = lane; j < H2; j += 32) s = fmaf(__ldcg(w3 + j), H[(size_t)m * ldh + j], s);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (lane + 32 * u < H2) s = fmaf(wv[u], H[(size_t)m * ldh + lane + 32 * u], s);
+        for (int j = lane + 256; j < H2; j += 32) s = fmaf(__ldcg(w3 + j), H[(size_t)m * ldh + j], s);
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) q[m] = s + b3;
@@ -286,8 +362,7 @@ __device__ void all_actions_q(const float *__restrict__ net, const Dims &d, cons
             Hc[ra * d.H1p + j] = fmaxf(T1[r * d.H1p + j] + Wa[id * d.H1p + j], 0.f);
         }
         __syncthreads();
-        cta_linear(Hc, d.H1p, mc, net + d.oW2, d.H1, false, d.H2, d.H1, net + d.ob2, true, H2c, d.H2p, stage,
-                   red);
+        cta_linear<false>(Hc, d.H1p, mc, net + d.oW2, d.H1, d.H2, d.H1, net + d.ob2, true, H2c, d.H2p, stage, red);
         cta_head(H2c, d.H2p, mc, net + d.oW3, __ldcg(net + d.ob3), d.H2, qa + c0);
         __syncthreads();
     }
@@ -304,7 +379,7 @@ __device__ void prefetch_records(const LearnArgs &a, float *sm, int round, int R
     const int32_t *sl = a.slots + (size_t)round * a.B + r0;
     for (int e = threadIdx.x; e < Rv * W4; e += NT) {
         const int r = e / W4, c = e - r * W4;
-        cp_async16(dst + (size_t)r * W + c * 4, a.records + (size_t)sl[r] * W + c * 4);
+        cp_async16(dst + (size_t)r * W + c * 4, a.records + (size_t)__ldcg(sl + r) * W + c * 4);
     }
     cp_async_commit();
 }
@@ -312,14 +387,20 @@ __device__ void prefetch_records(const LearnArgs &a, float *sm, int round, int R
 // ---------------------------------------------------------------------------
 // phase A
 // ---------------------------------------------------------------------------
+#define PRL_STAMP(idx)                                                                  \
+    do {                                                                                \
+        if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[(size_t)round * 16 + (idx)] = clock64(); \
+    } while (0)
+
 __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
     const Dims &d = a.d;
     const Plan &pl = a.plan;
     const int tid = threadIdx.x, R = a.R, W = a.lay.record_words;
     const int r0 = blockIdx.x * R, Rv = min(R, a.B - r0);
+    PRL_STAMP(0);
     cp_async_wait<0>();
     __syncthreads();
-    if (round + 1 < a.rounds) prefetch_records(a, sm, round + 1, Rv, r0);
+    PRL_STAMP(1);
 
     const uint32_t *rec = reinterpret_cast<const uint32_t *>(sm + pl.rec) + (size_t)(round & 1) * R * W;
     const float *recf = reinterpret_cast<const float *>(rec);
@@ -341,21 +422,25 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
     stage_action_cols(w, d, WaO);
     stage_action_cols(wt, d, WaT);
     __syncthreads();
+    PRL_STAMP(2);
 
     // ---- online Q(s, a) (q_value_networks.py:152-174; the one-hot action selects a W1 column)
-    cta_linear(recf + a.lay.off_state, W, Rv, w + d.oW1, d.D, false, d.H1, d.obs, w + d.ob1, false, T1o, d.H1p,
-               stage, red);
+    cta_linear<false>(recf + a.lay.off_state, W, Rv, w + d.oW1, d.D, d.H1, d.obs, w + d.ob1, false, T1o, d.H1p,
+                      stage, red);
     for (int e = tid; e < Rv * d.H1; e += NT) {
         const int r = e / d.H1, j = e - r * d.H1;
         H1o[r * d.H1p + j] = fmaxf(T1o[r * d.H1p + j] + WaO[sc.act[r] * d.H1p + j], 0.f);
     }
     __syncthreads();
-    cta_linear(H1o, d.H1p, Rv, w + d.oW2, d.H1, false, d.H2, d.H1, w + d.ob2, true, H2o, d.H2p, stage, red);
+    PRL_STAMP(3);
+    cta_linear<false>(H1o, d.H1p, Rv, w + d.oW2, d.H1, d.H2, d.H1, w + d.ob2, true, H2o, d.H2p, stage, red);
     cta_head(H2o, d.H2p, Rv, w + d.oW3, __ldcg(w + d.ob3), d.H2, sc.q);
+    PRL_STAMP(4);
 
     // ---- bootstrap value of s' (deep_q_learning.py:130-167 / double_dqn.py:29-57)
-    cta_linear(recf + a.lay.off_next_state, W, Rv, wt + d.oW1, d.D, false, d.H1, d.obs, wt + d.ob1, false, T1t,
-               d.H1p, stage, red);
+    cta_linear<false>(recf + a.lay.off_next_state, W, Rv, wt + d.oW1, d.D, d.H1, d.obs, wt + d.ob1, false, T1t,
+                      d.H1p, stage, red);
+    PRL_STAMP(5);
     if (!a.double_dqn) {
         all_actions_q(wt, d, T1t, WaT, rec, W, a.lay, a.buf_flags, Rv, a.mch, sc.cnt, Hc, H2c, qa, stage, red);
         if (tid < Rv) {
@@ -364,8 +449,8 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
             sc.v[tid] = best;
         }
     } else {
-        cta_linear(recf + a.lay.off_next_state, W, Rv, w + d.oW1, d.D, false, d.H1, d.obs, w + d.ob1, false,
-                   T1d, d.H1p, stage, red);
+        cta_linear<false>(recf + a.lay.off_next_state, W, Rv, w + d.oW1, d.D, d.H1, d.obs, w + d.ob1, false, T1d,
+                          d.H1p, stage, red);
         all_actions_q(w, d, T1d, WaO, rec, W, a.lay, a.buf_flags, Rv, a.mch, sc.cnt, Hc, H2c, qa, stage, red);
         if (tid < Rv) {
             float best = qa[tid * d.A];
@@ -386,11 +471,12 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
             Hc[r * d.H1p + j] = fmaxf(T1t[r * d.H1p + j] + WaT[sc.idsel[r] * d.H1p + j], 0.f);
         }
         __syncthreads();
-        cta_linear(Hc, d.H1p, Rv, wt + d.oW2, d.H1, false, d.H2, d.H1, wt + d.ob2, true, H2c, d.H2p, stage, red);
+        cta_linear<false>(Hc, d.H1p, Rv, wt + d.oW2, d.H1, d.H2, d.H1, wt + d.ob2, true, H2c, d.H2p, stage, red);
         cta_head(H2c, d.H2p, Rv, wt + d.oW3, __ldcg(wt + d.ob3), d.H2, sc.v);
     }
     __syncthreads();
 
+    PRL_STAMP(6);
     // ---- Bellman target, MSE gradient (deep_td_learning.py:313-320)
     if (tid < Rv) {
         const float y = __fadd_rn(__fmul_rn(__fmul_rn(sc.v[tid], a.gamma), 1.f - sc.term[tid]), sc.rew[tid]);
@@ -402,19 +488,24 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
     }
     __syncthreads();
 
+    PRL_STAMP(7);
     // ---- backward through the online network
     for (int e = tid; e < Rv * d.H2; e += NT) {
         const int r = e / d.H2, j = e - r * d.H2;
         dZ2[r * d.H2p + j] = (H2o[r * d.H2p + j] > 0.f) ? sc.dq[r] * __ldcg(w + d.oW3 + j) : 0.f;
     }
     __syncthreads();
-    cta_linear(dZ2, d.H2p, Rv, w + d.oW2, d.H1, true, d.H1, d.H2, nullptr, false, dZ1, d.H1p, stage, red);
+    cta_linear<true>(dZ2, d.H2p, Rv, w + d.oW2, d.H1, d.H1, d.H2, nullptr, false, dZ1, d.H1p, stage, red);
     for (int e = tid; e < Rv * d.H1; e += NT) {
         const int r = e / d.H1, j = e - r * d.H1;
         if (!(H1o[r * d.H1p + j] > 0.f)) dZ1[r * d.H1p + j] = 0.f;
     }
     __syncthreads();
 
+    PRL_STAMP(8);
+    // next round's transitions: issued after the last weight panel (cp.async groups retire
+    // in order) so the HBM latency hides behind the outer products, phase B and the barriers
+    if (round + 1 < a.rounds) prefetch_records(a, sm, round + 1, Rv, r0);
     float *g = a.gpart + (size_t)blockIdx.x * d.Pp;
     cta_outer(dZ1, d.H1p, recf + a.lay.off_state, W, Rv, d.H1, d.obs, g + d.oW1, d.D);  // dW1[:, :obs]
     cta_outer(dZ2, d.H2p, H1o, d.H1p, Rv, d.H2, d.H1, g + d.oW2, d.H1);                 // dW2
@@ -445,6 +536,7 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
         g[d.ob3] = s;
         g[d.P] = e;
     }
+    PRL_STAMP(9);
 }
 
 // soft target update, neural_networks/common/utils.py:214-226
@@ -458,14 +550,29 @@ __device__ __forceinline__ float soft_update(float src, float tgt, float tau, fl
 // ---------------------------------------------------------------------------
 __device__ void phase_update(const LearnArgs &a, int round) {
     const Dims &d = a.d;
-    const int G = gridDim.x;
+    const int G = a.G;
     const float2 s = a.scal[round];
     const float step_size = s.x, bc2_sqrt = s.y;
     const long long t_next = a.steps0 + round + 2;  // training step of the next round
     const bool upd_next = (round + 1 < a.rounds) && ((t_next + 1) % a.freq == 0);
     for (int i = blockIdx.x * NT + threadIdx.x; i <= d.P; i += G * NT) {
-        float g = 0.f;
-        for (int c = 0; c < G; c++) g += __ldcg(a.gpart + (size_t)c * d.Pp + i);
+        float g = 0.f;  // sum of the G partials in CTA order; up to 32 loads in flight
+        int c = 0;
+        for (; c + 32 <= G; c += 32) {
+            float t[32];
+#pragma unroll
+            for (int u = 0; u < 32; u++) t[u] = __ldcg(a.gpart + (size_t)(c + u) * d.Pp + i);
+#pragma unroll
+            for (int u = 0; u < 32; u++) g += t[u];
+        }
+        for (; c + 8 <= G; c += 8) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = __ldcg(a.gpart + (size_t)(c + u) * d.Pp + i);
+#pragma unroll
+            for (int u = 0; u < 8; u++) g += t[u];
+        }
+        for (; c < G; c++) g += __ldcg(a.gpart + (size_t)c * d.Pp + i);
         if (i == d.P) {  // reported "loss": mean |q - y| (deep_td_learning.py:358-360)
             a.out_mae[round] = g / (float)a.B;
             continue;
@@ -486,14 +593,34 @@ __device__ void phase_update(const LearnArgs &a, int round) {
 __global__ void __launch_bounds__(NT, 1) k_dqn_learn(const LearnArgs a) {
     extern __shared__ __align__(16) float sm[];
     cg::grid_group grid = cg::this_grid();
+    if (a.fused_sampler && blockIdx.x == a.G) {
+        // ---- producer CTA: the MT19937-exact index stream, two rounds ahead of the learners,
+        // fully overlapped with their work; it only meets them at the grid barriers.
+        __shared__ SamplerState S;
+        sampler_init(S, a.mt_state, sm, a.sp);
+        sampler_advance(S, sm, a.sp, min(a.rounds, 2));
+        __threadfence();
+        grid.sync();
+        if (a.first_update) grid.sync();
+        for (int round = 0; round < a.rounds; round++) {
+            sampler_advance(S, sm, a.sp, min(a.rounds, round + 3));
+            __threadfence();
+            grid.sync();
+            grid.sync();
+        }
+        __syncthreads();
+        sampler_store(S, a.mt_state);
+        return;
+    }
     const int r0 = blockIdx.x * a.R, Rv = min(a.R, a.B - r0);
     for (int i = a.plan.zero_begin + threadIdx.x; i < a.plan.zero_end; i += NT) sm[i] = 0.f;
+    if (a.fused_sampler) grid.sync();  // indices of rounds 0 and 1 are published
     prefetch_records(a, sm, 0, Rv, r0);
     // forward() applies the soft update BEFORE the gradient step of a round with
     // (training_steps + 1) % freq == 0 (deep_td_learning.py:283-284); later rounds get
     // it from phase B of the previous round.
     if (a.first_update) {
-        for (int i = blockIdx.x * NT + threadIdx.x; i < a.d.P; i += gridDim.x * NT)
+        for (int i = blockIdx.x * NT + threadIdx.x; i < a.d.P; i += a.G * NT)
             a.wt[i] = soft_update(__ldcg(a.w + i), __ldcg(a.wt + i), a.tau, a.omtau);
         __threadfence();
         grid.sync();
@@ -502,9 +629,12 @@ __global__ void __launch_bounds__(NT, 1) k_dqn_learn(const LearnArgs a) {
         phase_rows(a, sm, round);
         __threadfence();
         grid.sync();
+        PRL_STAMP(10);
         phase_update(a, round);
+        PRL_STAMP(11);
         __threadfence();
         grid.sync();
+        PRL_STAMP(12);
     }
     cp_async_wait<0>();
 }
@@ -563,8 +693,8 @@ k_q_values(const float *__restrict__ net, Dims d, Plan pl, int R, int mch, int n
     if (tid < Rv) sc.cnt[tid] = d.A;
     stage_action_cols(net, d, sm + pl.WaO);
     __syncthreads();
-    cta_linear(S, W, Rv, net + d.oW1, d.D, false, d.H1, d.obs, net + d.ob1, false, sm + pl.T1t, d.H1p,
-               sm + pl.stage, sm + pl.red);
+    cta_linear<false>(S, W, Rv, net + d.oW1, d.D, d.H1, d.obs, net + d.ob1, false, sm + pl.T1t, d.H1p,
+                      sm + pl.stage, sm + pl.red);
     prl_buf_layout L = {};
     all_actions_q(net, d, sm + pl.T1t, sm + pl.WaO, nullptr, 0, L, 0, Rv, mch, sc.cnt, sm + pl.Hc, sm + pl.H2c,
                   sm + pl.qa, sm + pl.stage, sm + pl.red);
@@ -597,6 +727,7 @@ struct prl_dqn {
     // optional device timing of the persistent kernel (bench / roofline)
     int timing;
     cudaEvent_t t0, t1;
+    long long *prof;
 };
 
 static const int kMaxCtas = 148;
@@ -686,6 +817,7 @@ extern "C" int prl_dqn_create(prl_dqn **out, const prl_dqn_cfg *cfg, float *w, f
     }
     q->last_launches = q->last_ctas = q->last_rows = 0;
     q->timing = 0;
+    q->prof = nullptr;
     q->t0 = q->t1 = nullptr;
     *out = q;
     return PRL_OK;
@@ -711,6 +843,11 @@ extern "C" int prl_dqn_set_timing(prl_dqn *q, int enable) {
         PRL_CUDA(cudaEventCreate(&q->t1));
     }
     q->timing = enable != 0;
+    return PRL_OK;
+}
+extern "C" int prl_dqn_set_profile(prl_dqn *q, long long *stamps_dev) {
+    PRL_REQUIRE(q, "null handle");
+    q->prof = stamps_dev;
     return PRL_OK;
 }
 extern "C" int prl_dqn_last_kernel_ms(prl_dqn *q, float *ms) {
@@ -743,7 +880,7 @@ extern "C" int prl_dqn_last_launch_info(const prl_dqn *q, int32_t *launches, int
 static int choose_tiling(const prl_dqn *q, int B, int W, int *R_out, int *mch_out, Plan *plan_out) {
     const Dims &d = q->d;
     int R = q->cfg.rows_per_cta;
-    const int max_ctas = q->sm_count < kMaxCtas ? q->sm_count : kMaxCtas;
+    const int max_ctas = (q->sm_count < kMaxCtas ? q->sm_count : kMaxCtas) - 1;  // one SM for the index producer
     if (R <= 0) {
         R = 4;  // 64 target rows per CTA at A = 16: one full register-tiled block
         while ((B + R - 1) / R > max_ctas) R *= 2;
@@ -766,7 +903,8 @@ static int choose_tiling(const prl_dqn *q, int B, int W, int *R_out, int *mch_ou
 
 static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layout &lay, int buf_flags,
                         const int32_t *slots, int rounds, int B, int64_t steps0, int first_update, float *out_mae,
-                        float *out_q, float *out_y, cudaStream_t stream) {
+                        float *out_q, float *out_y, cudaStream_t stream, prl_buf *sample_from = nullptr,
+                        int32_t *out_logical = nullptr) {
     int R, mch;
     Plan pl;
     int rc = choose_tiling(q, B, lay.record_words, &R, &mch, &pl);
@@ -803,11 +941,26 @@ static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layou
     a.omtau = (float)(1.0 - c.tau);
     a.inv_b2 = 2.0f / (float)B;
     const int G = (B + R - 1) / R;
-    const size_t smem = (size_t)pl.total * 4;
+    size_t smem = (size_t)pl.total * 4;
+    a.G = G;
+    a.fused_sampler = 0;
+    a.mt_state = nullptr;
+    a.prof = q->prof;
+    if (sample_from) {  // the index stream is produced inside the kernel by CTA number G
+        size_t sbytes = 0;
+        rc = prl_sampler_params(sample_from, B, &a.sp, &sbytes);
+        if (rc) return rc;
+        a.sp.out_slot = const_cast<int32_t *>(slots);
+        a.sp.out_logical = out_logical;
+        a.mt_state = sample_from->mt_state;
+        a.fused_sampler = 1;
+        if (sbytes > smem) smem = sbytes;
+        PRL_REQUIRE(smem <= (size_t)q->max_smem, "sampler tables do not fit shared memory");
+    }
     PRL_CUDA(cudaFuncSetAttribute(k_dqn_learn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {(void *)&a};
     if (q->timing) PRL_CUDA(cudaEventRecord(q->t0, stream));
-    PRL_CUDA(cudaLaunchCooperativeKernel((void *)k_dqn_learn, dim3(G), dim3(NT), args, smem, stream));
+    PRL_CUDA(cudaLaunchCooperativeKernel((void *)k_dqn_learn, dim3(G + a.fused_sampler), dim3(NT), args, smem, stream));
     if (q->timing) PRL_CUDA(cudaEventRecord(q->t1, stream));
     q->adam_step += rounds;
     q->last_ctas = G;
@@ -827,12 +980,11 @@ extern "C" int prl_dqn_learn(prl_dqn *q, prl_buf *buf, int rounds, int batch, in
                 "buffer (obs %d, actions %d) does not match learner (obs %d, actions %d)", buf->desc.obs_dim,
                 buf->desc.n_actions, q->cfg.obs_dim, q->cfg.n_actions);
     cudaStream_t stream = (cudaStream_t)stream_;
-    int rc = prl_buf_sample_indices(buf, rounds, batch, out_logical ? out_logical : nullptr, q->slots, stream_);
+    int rc = launch_learn(q, buf->records, buf->lay, buf->desc.flags, q->slots, rounds, batch, training_steps0,
+                          (training_steps0 + 2) % q->cfg.target_update_freq == 0, out_mae, out_q, out_y, stream,
+                          buf, out_logical);
     if (rc) return rc;
-    rc = launch_learn(q, buf->records, buf->lay, buf->desc.flags, q->slots, rounds, batch, training_steps0,
-                      (training_steps0 + 2) % q->cfg.target_update_freq == 0, out_mae, out_q, out_y, stream);
-    if (rc) return rc;
-    q->last_launches = 2;  // sampler + persistent learner
+    q->last_launches = 1;  // one persistent kernel: index producer CTA + learner CTAs
     return PRL_OK;
 }
 

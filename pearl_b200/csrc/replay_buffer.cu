@@ -6,6 +6,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "sampler.cuh"
 
 namespace prl {
 thread_local char g_err[512] = "";
@@ -346,190 +347,16 @@ extern "C" int prl_rng_seed(prl_buf *b, const uint32_t *key, int key_len, void *
 }
 
 // --------------------------------------------------------------------------
-// K2: MT19937-exact sampler (CPython random.sample, both branches)
+// K2: MT19937-exact sampler, stand-alone kernel (device routines in sampler.cuh)
 // --------------------------------------------------------------------------
-namespace {
-
-constexpr int MT_N = 624, MT_M = 397;
-constexpr int kSamplerThreads = 256;
-
-__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    return y;
-}
-__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b) {
-    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-}
-
-// One MT19937 block regeneration ("twist") by the whole CTA: old -> nw.
-// new[i] depends on old[i], old[i+1] and on old[i+397] (i<227) or new[i-227].
-__device__ void mt_twist_cta(const uint32_t *old, uint32_t *nw) {
-    const int t = threadIdx.x;
-    if (t < MT_N - MT_M) nw[t] = old[t + MT_M] ^ mt_mix(old[t], old[t + 1]);
-    __syncthreads();
-    if (t < MT_N - MT_M) {
-        int i = t + (MT_N - MT_M);  // 227..453
-        nw[i] = nw[i - (MT_N - MT_M)] ^ mt_mix(old[i], old[i + 1]);
-    }
-    __syncthreads();
-    if (t < MT_N - 1 - 2 * (MT_N - MT_M)) {
-        int i = t + 2 * (MT_N - MT_M);  // 454..622
-        nw[i] = nw[i - (MT_N - MT_M)] ^ mt_mix(old[i], old[i + 1]);
-    }
-    if (t == kSamplerThreads - 1) nw[MT_N - 1] = nw[MT_M - 1] ^ mt_mix(old[MT_N - 1], nw[0]);
-    __syncthreads();
-}
-
-struct SamplerShared {
-    uint32_t mt[2][MT_N];
-    int cur;      // which mt[] holds the live block
-    int pos;      // next unread word, 0..624
-    int done;     // completed samples
-    int cnt;      // accepted draws in the current sample
-    uint32_t epoch;
-    int pool_ready;
-};
-
-__device__ __forceinline__ int bit_length(uint32_t n) { return 32 - __clz(n); }
-
-// logical index -> physical slot
-__device__ __forceinline__ int32_t slot_of(uint32_t j, int64_t head, int64_t capacity) {
-    int64_t s = head + (int64_t)j;
-    if (s >= capacity) s -= capacity;
-    return (int32_t)s;
-}
-
-}  // namespace
-
-// dynamic smem: set branch -> uint64 table[cap]; pool branch -> int32 pool[n]
 __global__ void __launch_bounds__(kSamplerThreads, 1)
-k_sample_indices(uint32_t *__restrict__ mt_state, uint32_t n, int k, int rounds, int use_pool,
-                 uint32_t table_cap, int64_t head, int64_t capacity,
-                 int32_t *__restrict__ out_logical, int32_t *__restrict__ out_slot) {
+k_sample_indices(uint32_t *__restrict__ mt_state, SamplerParams p, int rounds) {
     extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ SamplerShared S;
-    unsigned long long *table = reinterpret_cast<unsigned long long *>(dyn);
-    int32_t *pool = reinterpret_cast<int32_t *>(dyn);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    for (int i = tid; i < MT_N; i += kSamplerThreads) S.mt[0][i] = mt_state[i];
-    if (!use_pool)
-        for (uint32_t i = tid; i < table_cap; i += kSamplerThreads) table[i] = 0ull;
-    if (tid == 0) {
-        S.cur = 0;
-        S.pos = (int)mt_state[MT_N];
-        S.done = 0;
-        S.cnt = 0;
-        S.epoch = 1;
-        S.pool_ready = 0;
-    }
+    __shared__ SamplerState S;
+    sampler_init(S, mt_state, dyn, p);
+    sampler_advance(S, dyn, p, rounds);
     __syncthreads();
-    if (k == 0 || rounds == 0) return;  // random.sample(.., 0) draws nothing
-
-    const int shift = 32 - bit_length(n);  // set branch: getrandbits(n.bit_length())
-
-    while (true) {
-        if (use_pool && !S.pool_ready) {
-            for (uint32_t i = tid; i < n; i += kSamplerThreads) pool[i] = (int32_t)i;
-        }
-        if (S.pos >= MT_N) {  // uniform: S.pos only changes between barriers
-            mt_twist_cta(S.mt[S.cur], S.mt[S.cur ^ 1]);
-            if (tid == 0) { S.cur ^= 1; S.pos = 0; }
-        }
-        __syncthreads();
-        if (use_pool) {
-            // n <= setsize: partial Fisher-Yates on a pool copy, inherently
-            // sequential (Lib/random.py:435-442); only small buffers get here.
-            if (tid == 0) {
-                S.pool_ready = 1;
-                const uint32_t *mt = S.mt[S.cur];
-                int pos = S.pos, cnt = S.cnt, done = S.done;
-                while (pos < MT_N && done < rounds) {
-                    uint32_t m = n - (uint32_t)cnt;           // randbelow(n - i)
-                    uint32_t r = mt_temper(mt[pos++]) >> (32 - bit_length(m));
-                    if (r >= m) continue;
-                    int32_t v = pool[r];
-                    pool[r] = pool[m - 1];
-                    size_t o = (size_t)done * k + cnt;
-                    if (out_logical) out_logical[o] = v;
-                    if (out_slot) out_slot[o] = slot_of((uint32_t)v, head, capacity);
-                    if (++cnt == k) { cnt = 0; done++; S.pool_ready = 0; break; }
-                }
-                S.pos = pos; S.cnt = cnt; S.done = done;
-            }
-        } else if (warp == 0) {
-            // n > setsize: j = randbelow(n) until j not yet selected
-            // (Lib/random.py:443-451).  A word is consumed per draw whether it
-            // is accepted, out of range or a duplicate, so the accepted
-            // sequence is an order-preserving compaction of the word stream.
-            const uint32_t *mt = S.mt[S.cur];
-            int pos = S.pos, cnt = S.cnt, done = S.done;
-            uint32_t epoch = S.epoch;
-            const unsigned lt = (1u << lane) - 1u;
-            while (pos < MT_N && done < rounds) {
-                const int w = pos + lane;
-                const bool inb = w < MT_N;
-                const uint32_t r = inb ? (mt_temper(mt[w]) >> shift) : 0xffffffffu;
-                bool cand = inb && r < n;
-                uint32_t h = (r * 2654435761u) & (table_cap - 1);
-                if (cand) {  // already selected in an earlier chunk of this sample?
-                    while (true) {
-                        unsigned long long e = table[h];
-                        if ((uint32_t)(e >> 32) != epoch) break;
-                        if ((uint32_t)e == r) { cand = false; break; }
-                        h = (h + 1) & (table_cap - 1);
-                    }
-                }
-                const unsigned cm = __ballot_sync(0xffffffffu, cand);
-                bool first = false;
-                if (cand) {  // duplicates inside the chunk: the earliest word wins
-                    unsigned grp = __match_any_sync(cm, r);
-                    first = (grp & lt) == 0;
-                }
-                const unsigned am = __ballot_sync(0xffffffffu, first);
-                const int total = __popc(am), need = k - cnt;
-                int consumed;
-                unsigned take;
-                bool finished = false;
-                if (total >= need) {
-                    const int last = __fns(am, 0, need);  // lane of the need-th accepted word
-                    take = am & ((last == 31) ? 0xffffffffu : ((2u << last) - 1u));
-                    consumed = last + 1;
-                    finished = true;
-                } else {
-                    take = am;
-                    consumed = min(32, MT_N - pos);
-                }
-                if ((take >> lane) & 1u) {
-                    const int rank = __popc(take & lt);
-                    size_t o = (size_t)done * k + cnt + rank;
-                    if (out_logical) out_logical[o] = (int32_t)r;
-                    if (out_slot) out_slot[o] = slot_of(r, head, capacity);
-                    if (!finished) {  // remember it for the rest of this sample
-                        const unsigned long long mine = ((unsigned long long)epoch << 32) | r;
-                        while (true) {
-                            unsigned long long e = table[h];
-                            if ((uint32_t)(e >> 32) == epoch) { h = (h + 1) & (table_cap - 1); continue; }
-                            if (atomicCAS(&table[h], e, mine) == e) break;
-                        }
-                    }
-                }
-                __syncwarp();
-                pos += consumed;
-                if (finished) { done++; cnt = 0; epoch++; } else { cnt += __popc(take); }
-            }
-            if (lane == 0) { S.pos = pos; S.cnt = cnt; S.done = done; S.epoch = epoch; }
-        }
-        __syncthreads();
-        if (S.done >= rounds) break;
-    }
-    // hand the advanced state back (same layout as random.getstate()[1])
-    for (int i = tid; i < MT_N; i += kSamplerThreads) mt_state[i] = S.mt[S.cur][i];
-    if (tid == 0) mt_state[MT_N] = (uint32_t)S.pos;
+    sampler_store(S, mt_state);
 }
 
 static int64_t sample_setsize(int64_t k) {  // Lib/random.py:432-434
@@ -538,30 +365,43 @@ static int64_t sample_setsize(int64_t k) {  // Lib/random.py:432-434
     return s;
 }
 
+// sampler geometry for `k` draws from the buffer's current population (shared with
+// the fused learner kernels); returns the dynamic shared memory the sampler needs
+int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *smem_bytes) {
+    const int64_t n = b->len;
+    if (k > n)
+        return fail(PRL_EINVAL, "Can't get a batch of size %d from a replay buffer with only %lld elements", k,
+                    (long long)n);
+    sp->n = (uint32_t)n; sp->k = k;
+    sp->use_pool = n <= sample_setsize(k);
+    sp->table_cap = 0;
+    if (sp->use_pool) {
+        *smem_bytes = (size_t)n * 4;
+    } else {
+        uint32_t cap = 64;
+        while (cap < (uint32_t)(2 * k)) cap <<= 1;
+        sp->table_cap = cap;
+        *smem_bytes = (size_t)cap * 8;
+    }
+    if (*smem_bytes > 200 * 1024) return fail(PRL_EUNSUPPORTED, "sample size %d too large for the on-chip sampler", k);
+    sp->head = prl_buf_head(b); sp->capacity = b->desc.capacity;
+    sp->out_logical = nullptr; sp->out_slot = nullptr;
+    return PRL_OK;
+}
+
 extern "C" int prl_buf_sample_indices(prl_buf *b, int rounds, int k, int32_t *out_logical,
                                       int32_t *out_slot, void *stream_) {
     PRL_REQUIRE(b, "null buffer");
     PRL_REQUIRE(rounds >= 0 && k >= 0, "negative rounds / k");
-    if (k > b->len)
-        return fail(PRL_EINVAL, "Can't get a batch of size %d from a replay buffer with only %lld elements",
-                    k, (long long)b->len);
+    SamplerParams sp;
+    size_t smem = 0;
+    int rc = prl_sampler_params(b, k, &sp, &smem);
+    if (rc) return rc;
     if (rounds == 0 || k == 0) return PRL_OK;
-    const int64_t n = b->len;
-    const int use_pool = n <= sample_setsize(k);
-    uint32_t cap = 0;
-    size_t smem;
-    if (use_pool) {
-        smem = (size_t)n * 4;
-    } else {
-        cap = 64;
-        while (cap < (uint32_t)(2 * k)) cap <<= 1;
-        smem = (size_t)cap * 8;
-    }
-    if (smem > 200 * 1024) return fail(PRL_EUNSUPPORTED, "sample size %d too large for the on-chip sampler", k);
+    sp.out_logical = out_logical;
+    sp.out_slot = out_slot;
     PRL_CUDA(cudaFuncSetAttribute(k_sample_indices, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_sample_indices<<<1, kSamplerThreads, smem, (cudaStream_t)stream_>>>(
-        b->mt_state, (uint32_t)n, k, rounds, use_pool, cap, prl_buf_head(b), b->desc.capacity, out_logical,
-        out_slot);
+    k_sample_indices<<<1, kSamplerThreads, smem, (cudaStream_t)stream_>>>(b->mt_state, sp, rounds);
     PRL_CUDA(cudaGetLastError());
     return PRL_OK;
 }

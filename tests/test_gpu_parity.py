@@ -214,10 +214,10 @@ def test_learn_matches_reference_golden(name):
         for i in range(3):
             assert f"{net}._model.{i}.0.weight" in keys and f"{net}._model.{i}.0.bias" in keys
     info = learner.launch_info()
-    assert info["launches"] == 2 and info["ctas"] >= 1
+    assert info["launches"] == 1 and info["ctas"] >= 1
 
 
-@pytest.mark.parametrize("rows", [1, 2, 8, 16])
+@pytest.mark.parametrize("rows", [2, 8, 16, 32])
 def test_tiling_does_not_change_results_beyond_tolerance(rows):
     fx, cfg, data, buf, learner = build_from_fixture("dqn_cfg2_pool", rows_per_cta=rows)
     random.setstate((3, tuple(int(x) for x in fx["mt_state_before"]), None))
