@@ -228,6 +228,30 @@ int prl_dqn_q_values(prl_dqn *dqn, int n, const float *state, int target, float 
 int prl_dqn_last_launch_info(const prl_dqn *dqn, int32_t *launches, int32_t *ctas,
                              int32_t *rows_per_cta);
 
+/* ---- multi-GPU data-parallel learner -------------------------------------
+ * One process per GPU (torch.distributed provides the rendezvous only).  Each rank owns a replay
+ * shard and samples its own batch; inside the persistent learner kernel the per-rank gradient
+ * (P floats) is exchanged between phase A and the AdamW step by ONE-SHOT PUSH over NVLink peer
+ * memory: every rank stores its reduced gradient into every peer's inbox, raises a per-CTA flag
+ * with a system-scope atomic, waits for the W flags of its own CTA index, then sums the W
+ * inboxes in rank order and divides by W.  All ranks therefore apply bit-identical updates
+ * (the mean gradient of the W*B sampled transitions).  The reference has no counterpart: no RL
+ * learner in Pearl is distributed; this is the "all-reduce on the gradient
+ * only" of the north star, fused into the step kernel instead of a separate NCCL launch.
+ *
+ * The communicator's buffers are library-allocated (cudaMalloc) so that they can be shared with
+ * CUDA IPC: exchange the 128-byte blob of prl_comm_local_handles between all ranks (any byte
+ * all-gather), then prl_comm_open_peers with the W blobs in rank order. */
+typedef struct prl_comm prl_comm;
+#define PRL_COMM_HANDLE_BYTES 128
+int prl_comm_create(prl_comm **out, int rank, int world, int64_t max_param_count);
+int prl_comm_local_handles(prl_comm *comm, uint8_t out_blob[PRL_COMM_HANDLE_BYTES]);
+int prl_comm_open_peers(prl_comm *comm, const uint8_t *blobs /* [world][PRL_COMM_HANDLE_BYTES] */);
+int prl_comm_destroy(prl_comm *comm);
+/* attach (or detach with NULL) a communicator to a learner; every rank must then call
+ * prl_dqn_learn with the same `rounds` */
+int prl_dqn_set_comm(prl_dqn *dqn, prl_comm *comm);
+
 /* Device timing of the persistent learner kernel alone (CUDA events recorded on
  * the launch stream around the kernel); used by bench.py for the roofline line.
  * prl_dqn_last_kernel_ms synchronises on the end event. */

@@ -67,6 +67,11 @@ _SIGNATURES = {
     "prl_dqn_learn": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P]),
     "prl_dqn_learn_batch": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
     "prl_dqn_q_values": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
+    "prl_comm_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int64]),
+    "prl_comm_local_handles": (C.c_int, [_P, _P]),
+    "prl_comm_open_peers": (C.c_int, [_P, _P]),
+    "prl_comm_destroy": (C.c_int, [_P]),
+    "prl_dqn_set_comm": (C.c_int, [_P, _P]),
     "prl_dqn_set_timing": (C.c_int, [_P, C.c_int]),
     "prl_dqn_set_profile": (C.c_int, [_P, _P]),
     "prl_dqn_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),

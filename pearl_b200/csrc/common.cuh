@@ -66,3 +66,16 @@ struct prl_buf {
     int stage_next;
     int device;
 };
+
+// multi-GPU communicator (see include/pearl_b200.h)
+struct prl_comm {
+    int rank, world;
+    int64_t slot_floats;       // floats per (parity, rank) inbox slot
+    float *inbox;              // local: [2][world][slot_floats]
+    unsigned int *flags;       // local: [kCommFlags] monotonically increasing arrival counters
+    float *peer_inbox[16];     // peer_inbox[p] = rank p's inbox as mapped here (self: local)
+    unsigned int *peer_flags[16];
+    unsigned long long exchanges;  // exchanges completed so far (identical on all ranks)
+    bool opened;
+};
+static const int kCommFlags = 256;

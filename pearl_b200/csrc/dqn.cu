@@ -104,6 +104,15 @@ struct LearnArgs {
     int fused_sampler;
     SamplerParams sp;         // out_slot == slots (+ optional out_logical)
     uint32_t *mt_state;
+    // data-parallel exchange (world == 1: unused)
+    int rank, world;
+    float *peer_inbox[16];
+    unsigned int *peer_flags[16];
+    float *inbox;             // local inbox [2][world][comm_slot]
+    unsigned int *flags;      // local arrival counters, one per learner CTA
+    long long comm_slot;      // floats per inbox slot
+    unsigned long long exch0; // exchanges completed before this launch
+    float inv_world;
     long long *prof;          // optional [rounds][16] SM-clock stamps of CTA 0 (developer profiling)
     long long steps0;         // learner._training_steps before the call
     float decay, omb1, beta2, omb2, eps, gamma, tau, omtau, inv_b2;  // fp32 images of the scalars
@@ -127,7 +136,7 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gme
 }
 
 template <bool NN>
-__device__ void cta_linear(const float *X, int ldx, int M, const float *__restrict__ W, int ldw, int N, int K,
+__device__ __noinline__ void cta_linear(const float *X, int ldx, int M, const float *__restrict__ W, int ldw, int N, int K,
                            const float *__restrict__ bias, bool relu, float *out, int ldo, float *stage,
                            float *red) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -279,7 +288,7 @@ __device__ void cta_linear(const float *X, int ldx, int M, const float *__restri
 
 // out[n*ldw + k] = sum_{m<M} dY[m][n] * X[m][k]  (n < N, k < K): the CTA's partial
 // weight gradient, written to global in the parameter layout.
-__device__ void cta_outer(const float *dY, int ldy, const float *X, int ldx, int M, int N, int K,
+__device__ __noinline__ void cta_outer(const float *dY, int ldy, const float *X, int ldx, int M, int N, int K,
                           float *__restrict__ out, int ldw) {
     const int K4 = (K + 3) >> 2;
     for (int item = threadIdx.x; item < N * K4; item += NT) {
@@ -304,7 +313,7 @@ __device__ void cta_outer(const float *dY, int ldy, const float *X, int ldx, int
 }
 
 // q[m] = b3 + sum_j w3[j] * H[m][j]   (one warp per row, fixed shuffle tree)
-__device__ void cta_head(const float *H, int ldh, int M, const float *__restrict__ w3, float b3, int H2,
+__device__ __noinline__ void cta_head(const float *H, int ldh, int M, const float *__restrict__ w3, float b3, int H2,
                          float *q) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float wv[8];  // this lane's slice of w3, fetched from L2 once (covers H2 <= 256 without reloads)
@@ -323,7 +332,7 @@ __device__ void cta_head(const float *H, int ldh, int M, const float *__restrict
 }
 
 // action columns of W1 transposed into shared: WaT[a][j] = W1[j][obs + a]
-__device__ void stage_action_cols(const float *__restrict__ w, const Dims &d, float *Wa) {
+__device__ __noinline__ void stage_action_cols(const float *__restrict__ w, const Dims &d, float *Wa) {
     for (int e = threadIdx.x; e < d.A * d.H1; e += NT) {
         const int j = e / d.A, a = e - j * d.A;
         Wa[a * d.H1p + j] = __ldcg(w + d.oW1 + (size_t)j * d.D + d.obs + a);
@@ -346,7 +355,7 @@ __device__ inline RowScal row_scal(float *base, int R) {
 
 // Q(s', a) for every (row, available-action slot): qa[r*A + a]; -inf where masked.
 // T1 = layer-1 state product (+bias) of the net being evaluated, Wa its action columns.
-__device__ void all_actions_q(const float *__restrict__ net, const Dims &d, const float *T1, const float *Wa,
+__device__ __noinline__ void all_actions_q(const float *__restrict__ net, const Dims &d, const float *T1, const float *Wa,
                               const uint32_t *rec, int W, const prl_buf_layout &L, int buf_flags, int Rv,
                               int mch, const int *cnt, float *Hc, float *H2c, float *qa, float *stage,
                               float *red) {
@@ -506,9 +515,11 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
     // next round's transitions: issued after the last weight panel (cp.async groups retire
     // in order) so the HBM latency hides behind the outer products, phase B and the barriers
     if (round + 1 < a.rounds) prefetch_records(a, sm, round + 1, Rv, r0);
+    PRL_STAMP(13);
     float *g = a.gpart + (size_t)blockIdx.x * d.Pp;
     cta_outer(dZ1, d.H1p, recf + a.lay.off_state, W, Rv, d.H1, d.obs, g + d.oW1, d.D);  // dW1[:, :obs]
     cta_outer(dZ2, d.H2p, H1o, d.H1p, Rv, d.H2, d.H1, g + d.oW2, d.H1);                 // dW2
+    PRL_STAMP(14);
     for (int e = tid; e < d.H1 * d.A; e += NT) {                                        // dW1[:, obs+a]
         const int j = e / d.A, k = e - j * d.A;
         float s = 0.f;
@@ -516,6 +527,7 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
             if (sc.act[r] == k) s += dZ1[r * d.H1p + j];
         g[d.oW1 + (size_t)j * d.D + d.obs + k] = s;
     }
+    PRL_STAMP(15);
     for (int j = tid; j < d.H1; j += NT) {
         float s = 0.f;
         for (int r = 0; r < Rv; r++) s += dZ1[r * d.H1p + j];
@@ -548,6 +560,36 @@ __device__ __forceinline__ float soft_update(float src, float tgt, float tau, fl
 // phase B: gradient reduction + AdamW(amsgrad) (torch/optim/adam.py:395-547,
 // non-capturable single-tensor path) + look-ahead soft target update
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// sum of the G partials of parameter i in CTA order; up to 32 loads in flight
+__device__ __forceinline__ float reduce_partials(const LearnArgs &a, int i) {
+    const Dims &d = a.d;
+    const int G = a.G;
+    float g = 0.f;
+    int c = 0;
+    for (; c + 32 <= G; c += 32) {
+        float t[32];
+#pragma unroll
+        for (int u = 0; u < 32; u++) t[u] = __ldcg(a.gpart + (size_t)(c + u) * d.Pp + i);
+#pragma unroll
+        for (int u = 0; u < 32; u++) g += t[u];
+    }
+    for (; c + 8 <= G; c += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = __ldcg(a.gpart + (size_t)(c + u) * d.Pp + i);
+#pragma unroll
+        for (int u = 0; u < 8; u++) g += t[u];
+    }
+    for (; c < G; c++) g += __ldcg(a.gpart + (size_t)c * d.Pp + i);
+    return g;
+}
+
 __device__ void phase_update(const LearnArgs &a, int round) {
     const Dims &d = a.d;
     const int G = a.G;
@@ -555,25 +597,35 @@ __device__ void phase_update(const LearnArgs &a, int round) {
     const float step_size = s.x, bc2_sqrt = s.y;
     const long long t_next = a.steps0 + round + 2;  // training step of the next round
     const bool upd_next = (round + 1 < a.rounds) && ((t_next + 1) % a.freq == 0);
+    const int parity = (int)((a.exch0 + (unsigned long long)round) & 1ull);
+    if (a.world > 1) {
+        // ---- fused gradient exchange: push this rank's reduced gradient slice into every
+        // peer's inbox over NVLink, flag, wait for the W arrivals of this CTA index.
+        for (int i = blockIdx.x * NT + threadIdx.x; i < d.P; i += G * NT) {
+            const float g = reduce_partials(a, i);
+            const size_t off = ((size_t)parity * a.world + a.rank) * a.comm_slot + i;
+            for (int p = 0; p < a.world; p++) a.peer_inbox[p][off] = g;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int p = 0; p < a.world; p++) atomicAdd_system(a.peer_flags[p] + blockIdx.x, 1u);
+            const unsigned int target = (unsigned int)((a.exch0 + (unsigned long long)round + 1ull) * a.world);
+            while ((int)(ld_acquire_sys(a.flags + blockIdx.x) - target) < 0) {}
+        }
+        __syncthreads();
+    }
     for (int i = blockIdx.x * NT + threadIdx.x; i <= d.P; i += G * NT) {
-        float g = 0.f;  // sum of the G partials in CTA order; up to 32 loads in flight
-        int c = 0;
-        for (; c + 32 <= G; c += 32) {
-            float t[32];
-#pragma unroll
-            for (int u = 0; u < 32; u++) t[u] = __ldcg(a.gpart + (size_t)(c + u) * d.Pp + i);
-#pragma unroll
-            for (int u = 0; u < 32; u++) g += t[u];
+        float g;
+        if (a.world > 1 && i < d.P) {
+            g = 0.f;  // rank order: identical on every rank
+            for (int q = 0; q < a.world; q++)
+                g += __ldcv(a.inbox + ((size_t)parity * a.world + q) * a.comm_slot + i);
+            g *= a.inv_world;
+        } else {
+            g = reduce_partials(a, i);
         }
-        for (; c + 8 <= G; c += 8) {
-            float t[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) t[u] = __ldcg(a.gpart + (size_t)(c + u) * d.Pp + i);
-#pragma unroll
-            for (int u = 0; u < 8; u++) g += t[u];
-        }
-        for (; c < G; c++) g += __ldcg(a.gpart + (size_t)c * d.Pp + i);
-        if (i == d.P) {  // reported "loss": mean |q - y| (deep_td_learning.py:358-360)
+        if (i == d.P) {  // reported "loss": mean |q - y| (deep_td_learning.py:358-360), local batch
             a.out_mae[round] = g / (float)a.B;
             continue;
         }
@@ -728,6 +780,7 @@ struct prl_dqn {
     int timing;
     cudaEvent_t t0, t1;
     long long *prof;
+    prl_comm *comm;
 };
 
 static const int kMaxCtas = 148;
@@ -818,6 +871,7 @@ extern "C" int prl_dqn_create(prl_dqn **out, const prl_dqn_cfg *cfg, float *w, f
     q->last_launches = q->last_ctas = q->last_rows = 0;
     q->timing = 0;
     q->prof = nullptr;
+    q->comm = nullptr;
     q->t0 = q->t1 = nullptr;
     *out = q;
     return PRL_OK;
@@ -833,6 +887,72 @@ extern "C" int prl_dqn_destroy(prl_dqn *q) {
         }
     if (q->t0) { cudaEventDestroy(q->t0); cudaEventDestroy(q->t1); }
     delete q;
+    return PRL_OK;
+}
+
+extern "C" int prl_dqn_set_comm(prl_dqn *q, prl_comm *comm) {
+    PRL_REQUIRE(q, "null handle");
+    q->comm = comm;
+    return PRL_OK;
+}
+
+extern "C" int prl_comm_create(prl_comm **out, int rank, int world, int64_t max_param_count) {
+    PRL_REQUIRE(out && world >= 1 && world <= 16 && rank >= 0 && rank < world, "bad rank/world");
+    PRL_REQUIRE(max_param_count > 0, "bad parameter count");
+    prl_comm *c = new (std::nothrow) prl_comm();
+    if (!c) return fail(PRL_ENOMEM, "out of host memory");
+    c->rank = rank; c->world = world;
+    c->slot_floats = (max_param_count + 63) / 64 * 64;
+    c->exchanges = 0;
+    c->opened = world == 1;
+    for (int p = 0; p < 16; p++) { c->peer_inbox[p] = nullptr; c->peer_flags[p] = nullptr; }
+    const size_t inbox_bytes = (size_t)2 * world * c->slot_floats * 4;
+    cudaError_t e = cudaMalloc((void **)&c->inbox, inbox_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->flags, kCommFlags * 4);
+    if (e == cudaSuccess) e = cudaMemset(c->inbox, 0, inbox_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->flags, 0, kCommFlags * 4);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete c; return fail(PRL_ECUDA, "prl_comm_create: %s", cudaGetErrorString(e)); }
+    c->peer_inbox[rank] = c->inbox;
+    c->peer_flags[rank] = c->flags;
+    *out = c;
+    return PRL_OK;
+}
+
+extern "C" int prl_comm_local_handles(prl_comm *c, uint8_t *blob) {
+    PRL_REQUIRE(c && blob, "null argument");
+    static_assert(2 * sizeof(cudaIpcMemHandle_t) <= PRL_COMM_HANDLE_BYTES, "blob too small");
+    cudaIpcMemHandle_t h[2];
+    PRL_CUDA(cudaIpcGetMemHandle(&h[0], c->inbox));
+    PRL_CUDA(cudaIpcGetMemHandle(&h[1], c->flags));
+    memset(blob, 0, PRL_COMM_HANDLE_BYTES);
+    memcpy(blob, h, sizeof(h));
+    return PRL_OK;
+}
+
+extern "C" int prl_comm_open_peers(prl_comm *c, const uint8_t *blobs) {
+    PRL_REQUIRE(c && blobs, "null argument");
+    for (int p = 0; p < c->world; p++) {
+        if (p == c->rank) continue;
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, blobs + (size_t)p * PRL_COMM_HANDLE_BYTES, sizeof(h));
+        PRL_CUDA(cudaIpcOpenMemHandle((void **)&c->peer_inbox[p], h[0], cudaIpcMemLazyEnablePeerAccess));
+        PRL_CUDA(cudaIpcOpenMemHandle((void **)&c->peer_flags[p], h[1], cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->opened = true;
+    return PRL_OK;
+}
+
+extern "C" int prl_comm_destroy(prl_comm *c) {
+    if (!c) return PRL_OK;
+    for (int p = 0; p < c->world; p++) {
+        if (p == c->rank) continue;
+        if (c->peer_inbox[p]) cudaIpcCloseMemHandle(c->peer_inbox[p]);
+        if (c->peer_flags[p]) cudaIpcCloseMemHandle(c->peer_flags[p]);
+    }
+    cudaFree(c->inbox);
+    cudaFree(c->flags);
+    delete c;
     return PRL_OK;
 }
 
@@ -946,6 +1066,18 @@ static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layou
     a.fused_sampler = 0;
     a.mt_state = nullptr;
     a.prof = q->prof;
+    a.rank = 0; a.world = 1; a.inbox = nullptr; a.flags = nullptr; a.comm_slot = 0; a.exch0 = 0; a.inv_world = 1.f;
+    for (int p = 0; p < 16; p++) { a.peer_inbox[p] = nullptr; a.peer_flags[p] = nullptr; }
+    if (q->comm && sample_from) {  // data-parallel learn(): exchange inside the kernel
+        prl_comm *c = q->comm;
+        PRL_REQUIRE(c->opened, "communicator peers were not opened");
+        PRL_REQUIRE(c->slot_floats >= q->d.P, "communicator slots are smaller than the parameter vector");
+        PRL_REQUIRE(G <= kCommFlags, "too many learner CTAs for the communicator");
+        a.rank = c->rank; a.world = c->world; a.inbox = c->inbox; a.flags = c->flags;
+        a.comm_slot = c->slot_floats; a.exch0 = c->exchanges; a.inv_world = 1.0f / (float)c->world;
+        for (int p = 0; p < c->world; p++) { a.peer_inbox[p] = c->peer_inbox[p]; a.peer_flags[p] = c->peer_flags[p]; }
+        c->exchanges += (unsigned long long)rounds;
+    }
     if (sample_from) {  // the index stream is produced inside the kernel by CTA number G
         size_t sbytes = 0;
         rc = prl_sampler_params(sample_from, B, &a.sp, &sbytes);

@@ -36,3 +36,7 @@ mhz = tot / (ms * 1e3 / rounds)
 print(f"kernel {ms*1e3/rounds:.2f} us/round, {tot:.0f} clk/round -> {mhz:.0f} MHz; info {L.launch_info()}")
 for n, v in zip(names, d):
     print(f"  {n:28s} {v:9.0f} clk  {v/mhz:7.2f} us")
+sub = [("  .. prefetch issue", s[:, 13] - s[:, 8]), ("  .. cta_outer x2", s[:, 14] - s[:, 13]), ("  .. dW1 action cols", s[:, 15] - s[:, 14]),
+       ("  .. biases/w3/mae", s[:, 9] - s[:, 15])]
+for n, v in sub:
+    print(f"  {n:28s} {v.mean():9.0f} clk")
