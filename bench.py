@@ -210,6 +210,10 @@ def run_b200(args) -> None:
     buf = make_buffer("device")
     buf.seed(1234 + rank)
     learner = make_learner()
+    comm = None
+    if world > 1 and args.multi == "dp":
+        comm = pearl_b200.B200Communicator(learner.flat_parameters.numel(), dev)
+        learner.set_communicator(comm)
     learner.set_kernel_timing(True)
     for _ in range(max(args.warmup, 3)):
         learner.learn(buf)
@@ -282,7 +286,11 @@ def run_b200(args) -> None:
                        "training_rounds_per_step": rounds, "hidden": list(HIDDEN), "replay_capacity_per_gpu": shard,
                        "replay_bytes_per_gpu": shard * buf.record_bytes, "l2": "inputs larger than L2 (no flush needed)",
                        "persistent_kernel_ctas": info["ctas"], "rows_per_cta": info["rows_per_cta"],
-                       "multi_gpu": "independent learner + buffer shard per GPU, no data-path collective" if world > 1 else "single GPU",
+                       "multi_gpu": ("single GPU" if world == 1 else
+                                     "data-parallel: per-GPU replay shard + batch of 256, mean gradient exchanged inside the "
+                                     "persistent kernel over NVLink peer memory every round (global batch 256*N); value counts "
+                                     "batch-256 gradient computations" if args.multi == "dp" else
+                                     "independent learner + buffer shard per GPU, no data-path collective"),
                        "loss_last": last_loss},
             "e2e": {"value": e2e_value, "unit": "gradient-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": f"push_batch({n_new} transitions from pinned host) + learn() incl. CPython RNG hand-off and loss report"},
@@ -304,6 +312,9 @@ def run_b200(args) -> None:
                                     "sample": f"3 learn() calls x {args.ref_rounds} rounds on a {args.ref_capacity}-transition deque "
                                               f"({r['seconds']:.1f} s)"}
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        dist.barrier()
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -320,6 +331,8 @@ def main() -> None:
     ap.add_argument("--ref-rounds", type=int, default=200)
     ap.add_argument("--ref-capacity", type=int, default=20_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--multi", default="dp", choices=["dp", "replicas"],
+                    help="N>1: data-parallel learner with in-kernel gradient exchange, or independent replicas")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

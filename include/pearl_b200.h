@@ -232,9 +232,10 @@ int prl_dqn_last_launch_info(const prl_dqn *dqn, int32_t *launches, int32_t *cta
  * One process per GPU (torch.distributed provides the rendezvous only).  Each rank owns a replay
  * shard and samples its own batch; inside the persistent learner kernel the per-rank gradient
  * (P floats) is exchanged between phase A and the AdamW step by ONE-SHOT PUSH over NVLink peer
- * memory: every rank stores its reduced gradient into every peer's inbox, raises a per-CTA flag
- * with a system-scope atomic, waits for the W flags of its own CTA index, then sums the W
- * inboxes in rank order and divides by W.  All ranks therefore apply bit-identical updates
+ * memory: every rank stores (gradient value, round sequence number) as one 8-byte word into every
+ * peer's inbox (double-buffered by round parity); the owner of parameter i polls the W sequence
+ * numbers of element i, sums the W values in rank order and divides by W — one-way NVLink latency,
+ * no fence / flag round trip, no host involvement.  All ranks therefore apply bit-identical updates
  * (the mean gradient of the W*B sampled transitions).  The reference has no counterpart: no RL
  * learner in Pearl is distributed; this is the "all-reduce on the gradient
  * only" of the north star, fused into the step kernel instead of a separate NCCL launch.

@@ -71,7 +71,7 @@ struct prl_buf {
 struct prl_comm {
     int rank, world;
     int64_t slot_floats;       // floats per (parity, rank) inbox slot
-    float *inbox;              // local: [2][world][slot_floats]
+    float *inbox;              // local: [2 parities][world][slot_floats] of (value f32, sequence u32)
     unsigned int *flags;       // local: [kCommFlags] monotonically increasing arrival counters
     float *peer_inbox[16];     // peer_inbox[p] = rank p's inbox as mapped here (self: local)
     unsigned int *peer_flags[16];

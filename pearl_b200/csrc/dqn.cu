@@ -560,10 +560,14 @@ __device__ __forceinline__ float soft_update(float src, float tgt, float tau, fl
 // phase B: gradient reduction + AdamW(amsgrad) (torch/optim/adam.py:395-547,
 // non-capturable single-tensor path) + look-ahead soft target update
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_volatile_v2(float *p, float val, unsigned int tag) {
+    asm volatile("st.volatile.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(val)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v2(const float *p, float &val, unsigned int &tag) {
+    unsigned int a, b;
+    asm volatile("ld.volatile.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+    val = __uint_as_float(a);
+    tag = b;
 }
 
 // sum of the G partials of parameter i in CTA order; up to 32 loads in flight
@@ -598,30 +602,29 @@ __device__ void phase_update(const LearnArgs &a, int round) {
     const long long t_next = a.steps0 + round + 2;  // training step of the next round
     const bool upd_next = (round + 1 < a.rounds) && ((t_next + 1) % a.freq == 0);
     const int parity = (int)((a.exch0 + (unsigned long long)round) & 1ull);
+    const unsigned int seq = (unsigned int)(a.exch0 + (unsigned long long)round + 1ull);
     if (a.world > 1) {
-        // ---- fused gradient exchange: push this rank's reduced gradient slice into every
-        // peer's inbox over NVLink, flag, wait for the W arrivals of this CTA index.
+        // ---- fused gradient exchange (NVLink peer memory, one-way latency only): every rank
+        // pushes (value, round sequence number) as ONE 8-byte store into every peer's inbox;
+        // readers poll the sequence half of each element, so there is no fence / flag round trip.
         for (int i = blockIdx.x * NT + threadIdx.x; i < d.P; i += G * NT) {
             const float g = reduce_partials(a, i);
             const size_t off = ((size_t)parity * a.world + a.rank) * a.comm_slot + i;
-            for (int p = 0; p < a.world; p++) a.peer_inbox[p][off] = g;
+            for (int p = 0; p < a.world; p++) st_volatile_v2(a.peer_inbox[p] + 2 * off, g, seq);
         }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int p = 0; p < a.world; p++) atomicAdd_system(a.peer_flags[p] + blockIdx.x, 1u);
-            const unsigned int target = (unsigned int)((a.exch0 + (unsigned long long)round + 1ull) * a.world);
-            while ((int)(ld_acquire_sys(a.flags + blockIdx.x) - target) < 0) {}
-        }
-        __syncthreads();
     }
     for (int i = blockIdx.x * NT + threadIdx.x; i <= d.P; i += G * NT) {
         float g;
         if (a.world > 1 && i < d.P) {
-            g = 0.f;  // rank order: identical on every rank
-            for (int q = 0; q < a.world; q++)
-                g += __ldcv(a.inbox + ((size_t)parity * a.world + q) * a.comm_slot + i);
-            g *= a.inv_world;
+            float sum = 0.f;  // rank order: identical on every rank
+            for (int q = 0; q < a.world; q++) {
+                const float *src = a.inbox + 2 * (((size_t)parity * a.world + q) * a.comm_slot + i);
+                float val;
+                unsigned int tag;
+                do { ld_volatile_v2(src, val, tag); } while (tag != seq);
+                sum += val;
+            }
+            g = sum * a.inv_world;
         } else {
             g = reduce_partials(a, i);
         }
@@ -906,7 +909,7 @@ extern "C" int prl_comm_create(prl_comm **out, int rank, int world, int64_t max_
     c->exchanges = 0;
     c->opened = world == 1;
     for (int p = 0; p < 16; p++) { c->peer_inbox[p] = nullptr; c->peer_flags[p] = nullptr; }
-    const size_t inbox_bytes = (size_t)2 * world * c->slot_floats * 4;
+    const size_t inbox_bytes = (size_t)2 * world * c->slot_floats * 8;  // (value, sequence) pairs
     cudaError_t e = cudaMalloc((void **)&c->inbox, inbox_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->flags, kCommFlags * 4);
     if (e == cudaSuccess) e = cudaMemset(c->inbox, 0, inbox_bytes);

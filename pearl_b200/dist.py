@@ -1,0 +1,67 @@
+"""Multi-GPU data-parallel learner plumbing (one process per GPU).
+
+`torch.distributed` is used only for the rendezvous (rank/world, a byte
+all-gather of CUDA IPC handles).  The gradient exchange itself happens inside
+the persistent learner kernel over NVLink peer memory (include/pearl_b200.h,
+prl_comm_*): the reference has no distributed RL learner, this
+is the north star's "all-reduce on the gradient only".
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+HANDLE_BYTES = 128
+
+
+def all_gather_bytes(blob: bytes, group=None, device: Optional[torch.device] = None) -> List[bytes]:
+    """All-gather one fixed-size byte string per rank (works with nccl and gloo)."""
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = device if (backend == "nccl" and device is not None) else (
+        torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+    mine = torch.tensor(list(blob), dtype=torch.uint8, device=dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [bytes(t.cpu().tolist()) for t in out]
+
+
+def shard_owner(global_write_index: int, world: int) -> tuple:
+    """Interleaved ownership of a globally numbered transition stream:
+    transition g lives on rank g mod W at local position g div W, which keeps FIFO
+    eviction and age-uniform sampling balanced across shards."""
+    return global_write_index % world, global_write_index // world
+
+
+class B200Communicator:
+    """NVLink peer-memory communicator for B200DeepQLearning / B200DoubleDQN."""
+
+    def __init__(self, param_count: int, device: torch.device, group=None) -> None:
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
+        self._lib = _lib.init(self.device.index)
+        self._handle = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.prl_comm_create(C.byref(self._handle), self.rank, self.world, int(param_count)))
+            blob = (C.c_uint8 * HANDLE_BYTES)()
+            _lib.check(self._lib.prl_comm_local_handles(self._handle, blob))
+            blobs = all_gather_bytes(bytes(blob), group, self.device)
+            joined = (C.c_uint8 * (HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(blobs))
+            _lib.check(self._lib.prl_comm_open_peers(self._handle, joined))
+        dist.barrier(group)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._handle
+
+    def close(self) -> None:
+        if self._handle.value:
+            self._lib.prl_comm_destroy(self._handle)
+            self._handle = C.c_void_p(0)

@@ -152,6 +152,8 @@ class _B200DQNMixin:
             _lib.check(self._libh.prl_dqn_create(C.byref(handle), C.byref(cfg), _lib.ptr(w), _lib.ptr(wt),
                                                  _lib.ptr(m), _lib.ptr(v), _lib.ptr(vmax), step, _lib.ptr(ws)))
         self._handle, self._cfg = handle, cfg
+        if getattr(self, "_comm", None) is not None:
+            _lib.check(self._libh.prl_dqn_set_comm(self._handle, self._comm.handle))
         self._flat = dict(w=w, wt=wt, m=m, v=v, vmax=vmax, ws=ws)
         self._bound_ptr = params[0].data_ptr()
         self._device = device
@@ -181,6 +183,15 @@ class _B200DQNMixin:
         a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
         self._libh.prl_dqn_last_launch_info(self._handle, C.byref(a), C.byref(b), C.byref(c))
         return dict(launches=a.value, ctas=b.value, rows_per_cta=c.value)
+
+    def set_communicator(self, comm) -> None:
+        """Data-parallel learning over `comm` (pearl_b200.dist.B200Communicator): every rank's
+        `learn(B200ReplayBuffer)` then applies the mean gradient of all ranks' batches, exchanged
+        inside the kernel.  All ranks must call learn() with the same number of rounds and start
+        from identical parameters."""
+        self._bind(1)
+        self._comm = comm
+        _lib.check(self._libh.prl_dqn_set_comm(self._handle, comm.handle if comm is not None else None))
 
     def set_kernel_timing(self, enable: bool = True) -> None:
         self._bind(1)
