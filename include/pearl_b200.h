@@ -262,6 +262,12 @@ int prl_dqn_set_timing(prl_dqn *dqn, int enable);
 int prl_dqn_set_profile(prl_dqn *dqn, long long *stamps_dev);
 int prl_dqn_last_kernel_ms(prl_dqn *dqn, float *ms);
 
+/* Self-test of the tcgen05 / TMEM building block used by the learner kernels: one CTA computes
+ * D[128][n] = A[128][k] * B[n][k]^T (device fp32 row-major arrays) with plain TF32 (passes = 1) or
+ * the 3xTF32 split the learner uses for fp32 parity (passes = 3).  Test infrastructure hook. */
+int prl_test_umma_gemm(const float *a_dev, const float *b_dev, float *d_dev, int n, int k, int passes,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

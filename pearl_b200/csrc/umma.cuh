@@ -1,0 +1,144 @@
+// umma.cuh — thin inline-PTX layer over Blackwell's 5th-generation tensor cores
+// (tcgen05.mma with TMEM accumulators) for the dense contractions of the learner.
+//
+// fp32 parity needs more than one TF32 pass: every fp32 operand x is split
+//   x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi)
+// and a product is accumulated as hi*hi + hi*lo + lo*hi in the fp32 TMEM
+// accumulator ("3xTF32"): relative error ~2^-21 per product instead of 2^-11.
+//
+// Operand tiles live in shared memory in the canonical K-major NO-SWIZZLE
+// ("interleaved") UMMA layout, written directly by SIMT code:
+//   16-byte chunk c = k/4 of row r sits at  (r/8)*SBO + c*LBO + (r%8)*16
+//   (8 rows x 16 B = one 128-byte core matrix; LBO = 128 B so the core matrices
+//    of one 8-row group are contiguous along K; SBO = (K/4)*128 B)
+// One tcgen05.mma.kind::tf32 consumes K = 8 (two chunks); the next K step
+// advances the descriptor start address by 2*LBO.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- operand layout -------------------------------------------------------
+constexpr int LBO = 128;  // bytes between the two 16-byte K chunks of one MMA / consecutive core matrices
+__host__ __device__ constexpr int tile_sbo(int K) { return (K / 4) * 128; }           // bytes per 8-row group
+__host__ __device__ constexpr int tile_bytes(int rows, int K) { return (rows / 8) * tile_sbo(K); }
+// float index of element (r, k) inside a tile of K columns
+__device__ __forceinline__ int tile_index(int r, int k, int K) {
+    return (r >> 3) * (tile_sbo(K) >> 2) + (k >> 2) * 32 + (r & 7) * 4 + (k & 3);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - hi);
+}
+
+// ---- descriptors ------------------------------------------------------------
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64) = 0 (no swizzle)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((LBO >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, M x N x 8
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// 3xTF32 product of one [M x K] A tile pair and one [N x K] B tile pair into a TMEM accumulator.
+// Issued by ONE thread.  a_hi/a_lo/b_hi/b_lo: shared addresses of the tiles.
+__device__ __forceinline__ void gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                            uint32_t b_lo, int M, int N, int K, bool accumulate_first) {
+    const uint32_t idesc = make_idesc_tf32(M, N);
+    const int sbo = tile_sbo(K);
+    bool acc = accumulate_first;
+    for (int k = 0; k < K; k += 8) {
+        const uint32_t o = (uint32_t)(k >> 2) * LBO;
+        const uint64_t ah = make_desc(a_hi + o, sbo), al = make_desc(a_lo + o, sbo);
+        const uint64_t bh = make_desc(b_hi + o, sbo), bl = make_desc(b_lo + o, sbo);
+        mma_tf32(tmem_d, al, bh, idesc, acc);   // small terms first
+        mma_tf32(tmem_d, ah, bl, idesc, true);
+        mma_tf32(tmem_d, ah, bh, idesc, true);
+        acc = true;
+    }
+}
+
+// ---- TMEM management ----------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the allocating warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_thread_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_thread_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the tensor core (async proxy)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- mbarrier (completion of committed MMAs) -------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {  // arrives on `bar` when all prior MMAs of this thread finish
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// ---- accumulator read-back: this warp's 32 lanes (rows) x 32 consecutive fp32 columns -------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace umma

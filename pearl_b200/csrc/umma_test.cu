@@ -1,0 +1,88 @@
+// umma_test.cu — self-test of the tcgen05 building block (umma.cuh): one CTA computes
+// D[128 x N] = A[128 x K] * B[N x K]^T with `passes` = 1 (plain TF32) or 3 (3xTF32).
+// Exposed through the C ABI so tests/ can check it against an fp64 product on the GPU box.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+using namespace prl;
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+k_umma_test(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D, int N, int K,
+            int passes) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int a_floats = umma::tile_bytes(128, K) / 4, b_floats = umma::tile_bytes(N, K) / 4;
+    float *a_hi = smem, *a_lo = a_hi + a_floats, *b_hi = a_lo + a_floats, *b_lo = b_hi + b_floats;
+    for (int e = tid; e < 128 * K; e += 128) {
+        const int r = e / K, k = e - r * K;
+        float hi, lo;
+        umma::split_tf32(A[e], hi, lo);
+        if (passes == 1) { hi = A[e]; lo = 0.f; }
+        a_hi[umma::tile_index(r, k, K)] = hi;
+        a_lo[umma::tile_index(r, k, K)] = lo;
+    }
+    for (int e = tid; e < N * K; e += 128) {
+        const int r = e / K, k = e - r * K;
+        float hi, lo;
+        umma::split_tf32(B[e], hi, lo);
+        if (passes == 1) { hi = B[e]; lo = 0.f; }
+        b_hi[umma::tile_index(r, k, K)] = hi;
+        b_lo[umma::tile_index(r, k, K)] = lo;
+    }
+    if (warp == 0) umma::tmem_alloc(&tmem_base, 64 > N ? 64 : N);  // power of two >= 32 columns
+    if (tid == 0) umma::mbar_init(&bar, 1);
+    umma::fence_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tm = tmem_base;
+    if (tid == 0) {
+        if (passes == 3) {
+            umma::gemm_3xtf32(tm, umma::smem_u32(a_hi), umma::smem_u32(a_lo), umma::smem_u32(b_hi),
+                              umma::smem_u32(b_lo), 128, N, K, false);
+        } else {
+            const uint32_t idesc = umma::make_idesc_tf32(128, N);
+            const int sbo = umma::tile_sbo(K);
+            for (int k = 0; k < K; k += 8) {
+                const uint32_t o = (uint32_t)(k >> 2) * umma::LBO;
+                umma::mma_tf32(tm, umma::make_desc(umma::smem_u32(a_hi) + o, sbo),
+                               umma::make_desc(umma::smem_u32(b_hi) + o, sbo), idesc, k > 0);
+            }
+        }
+        umma::mma_commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_thread_sync();
+    // warp w owns TMEM lanes (= rows) 32w .. 32w+31
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        umma::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int c = 0; c < 32; c++)
+            if (c0 + c < N) D[(size_t)(warp * 32 + lane) * N + c0 + c] = v[c];
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tm, 64 > N ? 64 : N);
+}
+
+}  // namespace
+
+extern "C" int prl_test_umma_gemm(const float *a_dev, const float *b_dev, float *d_dev, int n, int k, int passes,
+                                  void *stream) {
+    PRL_REQUIRE(a_dev && b_dev && d_dev, "null argument");
+    PRL_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && (n & (n - 1)) == 0, "N must be a power of two in [16,256]");
+    PRL_REQUIRE(k >= 8 && k % 8 == 0 && k <= 256, "K must be a multiple of 8 in [8,256]");
+    PRL_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
+    const size_t smem = (size_t)2 * (umma::tile_bytes(128, k) + umma::tile_bytes(n, k));
+    PRL_REQUIRE(smem <= 200 * 1024, "tile does not fit shared memory");
+    PRL_CUDA(cudaFuncSetAttribute(k_umma_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_test<<<1, 128, smem, (cudaStream_t)stream>>>(a_dev, b_dev, d_dev, n, k, passes);
+    PRL_CUDA(cudaGetLastError());
+    return PRL_OK;
+}
