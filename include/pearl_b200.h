@@ -267,6 +267,11 @@ int prl_dqn_last_kernel_ms(prl_dqn *dqn, float *ms);
  * the 3xTF32 split the learner uses for fp32 parity (passes = 3).  Test infrastructure hook. */
 int prl_test_umma_gemm(const float *a_dev, const float *b_dev, float *d_dev, int n, int k, int passes,
                        void *stream);
+/* General self-test: D[m][n] = A[m][k] * B[n][k]^T with m in {64,128} and a free operand chunk pitch
+ * `lbo` (128 dense / 144 transposed-write friendly, see csrc/umma.cuh).  draw_dev receives the raw
+ * accumulator: 128 TMEM lanes x n columns (for m = 64, row i is lane 32*(i/16) + i%16). */
+int prl_test_umma_gemm2(const float *a_dev, const float *b_dev, float *draw_dev, int m, int n, int k, int lbo,
+                        void *stream);
 
 #ifdef __cplusplus
 }

@@ -55,7 +55,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int sbo_bytes)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-
 // D[tmem] (+)= A[smem] * B[smem]^T, M x N x 8
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          bool accumulate) {
@@ -65,6 +64,51 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
+}
+
+// generic descriptor: explicit LBO / SBO (bytes)
+__device__ __forceinline__ uint64_t make_desc2(uint32_t smem_addr, int lbo_bytes, int sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// K-major operand tile with a free chunk pitch.  Element (r, k) of a tile with K columns lives at byte
+//   (r/8)*sbo + (k/4)*lbo + (r%8)*16 + (k%4)*4,   sbo = (K/4)*lbo.
+// lbo = 128: dense (rows written by their owner thread as 16-byte chunks);
+// lbo = 144: "transposed-write friendly": when 32 lanes write the SAME row r and consecutive k
+//            (a thread that owns batch row k scatters its values into column k of the tile), the
+//            addresses (k/4)*144 + (k%4)*4 hit 32 distinct banks.
+// MN-major tf32 operands are NOT usable with the no-swizzle layout (measured: garbage), so the backward
+// pass builds explicitly transposed tiles instead.
+struct Tile {
+    uint32_t addr;  // shared-memory byte address
+    int lbo, sbo;   // bytes
+    __device__ __forceinline__ uint64_t desc(int kstep) const { return make_desc2(addr + (uint32_t)kstep * 2 * lbo, lbo, sbo); }
+    __device__ __forceinline__ Tile rows_from(int r) const { return Tile{addr + (uint32_t)(r >> 3) * sbo, lbo, sbo}; }  // r % 8 == 0
+    __device__ __forceinline__ Tile shifted(uint32_t bytes) const { return Tile{addr + bytes, lbo, sbo}; }
+};
+__host__ __device__ constexpr int tile_bytes2(int rows, int K, int lbo) { return (rows / 8) * (K / 4) * lbo; }
+__device__ __forceinline__ int tile_index2(int r, int k, int K, int lbo) {
+    return (r >> 3) * ((K >> 2) * (lbo >> 2)) + (k >> 2) * (lbo >> 2) + (r & 7) * 4 + (k & 3);
+}
+__device__ __forceinline__ Tile make_tile(const void *p, int K, int lbo) { return Tile{smem_u32(p), lbo, (K >> 2) * lbo}; }
+
+// 3xTF32: D[M x N] (+)= A[M x K] * B[N x K]^T; issued by ONE thread.  *_exact: the operand is exactly
+// representable in TF32 (0/1 indicators), its lo tile is not needed.
+__device__ __forceinline__ void gemm3(uint32_t tmem_d, Tile a_hi, Tile a_lo, Tile b_hi, Tile b_lo, int M, int N, int K,
+                                      bool accumulate_first, bool a_exact = false, bool b_exact = false) {
+    const uint32_t idesc = make_idesc_tf32(M, N);
+    bool acc = accumulate_first;
+    for (int ks = 0; ks < (K >> 3); ks++) {
+        if (!a_exact) { mma_tf32(tmem_d, a_lo.desc(ks), b_hi.desc(ks), idesc, acc); acc = true; }
+        if (!b_exact) { mma_tf32(tmem_d, a_hi.desc(ks), b_lo.desc(ks), idesc, acc); acc = true; }
+        mma_tf32(tmem_d, a_hi.desc(ks), b_hi.desc(ks), idesc, acc);
+        acc = true;
+    }
 }
 
 // 3xTF32 product of one [M x K] A tile pair and one [N x K] B tile pair into a TMEM accumulator.
