@@ -253,6 +253,21 @@ int prl_comm_destroy(prl_comm *comm);
  * prl_dqn_learn with the same `rounds` */
 int prl_dqn_set_comm(prl_dqn *dqn, prl_comm *comm);
 
+/* ---- tensor-core learner, one SM per learner (aggregate mode) -----------------------------
+ * PolicyLearner.learn() for `count` INDEPENDENT learners (seeds / agents; the reference runs those
+ * as separate OS processes, utils/scripts/benchmark.py:80-116) in one launch: CTA i trains learner
+ * dqns[i] on buffer bufs[i] for `rounds` gradient steps with every dense contraction on tcgen05
+ * (3xTF32, fp32 accumulation in TMEM).  Same arithmetic contract and outputs as prl_dqn_learn, per
+ * learner; out_mae (required) / out_q / out_y / out_logical are arrays of `count` device pointers
+ * (the optional arrays and their entries may be NULL).  Shape class: hidden [64,64], obs % 8 == 0
+ * and <= 128, n_actions in {1,2,4,8,16}, DeepQLearning (not DoubleDQN), batch 128 or 256, all
+ * learners with one configuration and one record layout; otherwise PRL_EUNSUPPORTED (use
+ * prl_dqn_learn).  prl_dqn_tc_supported answers that question for one learner. */
+int prl_dqn_tc_supported(const prl_dqn *dqn, int batch);
+int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, int count, int rounds, int batch,
+                        const int64_t *training_steps0, float *const *out_mae_dev, float *const *out_q_dev,
+                        float *const *out_y_dev, int32_t *const *out_logical_dev, void *stream);
+
 /* Device timing of the persistent learner kernel alone (CUDA events recorded on
  * the launch stream around the kernel); used by bench.py for the roofline line.
  * prl_dqn_last_kernel_ms synchronises on the end event. */

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "sampler.cuh"
+#include "dqn_common.cuh"
 
 int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *smem_bytes);
 
@@ -40,21 +41,6 @@ constexpr int KCMAX = 128;   // K extent of a staged weight panel
 constexpr int MB = 64;       // rows per register-tiled row block
 constexpr int STAGE_FLOATS = KCMAX * (NC + 4);  // >= NC * (KCMAX + 4): either panel orientation
 constexpr int RED_FLOATS = NT * 16;
-
-struct Dims {
-    int obs, A, H1, H2, D, H1p, H2p, P, Pp;
-    int oW1, ob1, oW2, ob2, oW3, ob3;
-};
-
-__host__ __device__ inline Dims make_dims(int obs, int A, int H1, int H2) {
-    Dims d;
-    d.obs = obs; d.A = A; d.H1 = H1; d.H2 = H2; d.D = obs + A;
-    d.H1p = round_up(H1, 4); d.H2p = round_up(H2, 4);
-    d.oW1 = 0; d.ob1 = d.oW1 + H1 * d.D; d.oW2 = d.ob1 + H1; d.ob2 = d.oW2 + H2 * H1;
-    d.oW3 = d.ob2 + H2; d.ob3 = d.oW3 + H2; d.P = d.ob3 + 1;
-    d.Pp = round_up(d.P + 1, 4);  // +1: the CTA's sum |q-y| rides along
-    return d;
-}
 
 // shared-memory plan, offsets in floats (all multiples of 4)
 struct Plan {
@@ -551,11 +537,6 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
     PRL_STAMP(9);
 }
 
-// soft target update, neural_networks/common/utils.py:214-226
-__device__ __forceinline__ float soft_update(float src, float tgt, float tau, float omtau) {
-    return __fadd_rn(__fmul_rn(tau, src), __fmul_rn(omtau, tgt));
-}
-
 // ---------------------------------------------------------------------------
 // phase B: gradient reduction + AdamW(amsgrad) (torch/optim/adam.py:395-547,
 // non-capturable single-tensor path) + look-ahead soft target update
@@ -632,15 +613,8 @@ __device__ void phase_update(const LearnArgs &a, int round) {
             a.out_mae[round] = g / (float)a.B;
             continue;
         }
-        float p = __fmul_rn(__ldcg(a.w + i), a.decay);                 // param.mul_(1 - lr*wd)
-        float m = __ldcg(a.m + i);
-        m = fmaf(a.omb1, g - m, m);                                    // exp_avg.lerp_(grad, 1-beta1)
-        float v = __fmul_rn(__ldcg(a.v + i), a.beta2);
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(a.omb2, g), g));          // .mul_(b2).addcmul_(g,g,1-b2)
-        const float vm = fmaxf(__ldcg(a.vmax + i), v);                 // amsgrad
-        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vm), bc2_sqrt), a.eps);
-        p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-step_size, m), denom));  // addcdiv_(m, denom, -step_size)
-        a.w[i] = p; a.m[i] = m; a.v[i] = v; a.vmax[i] = vm;
+        AdamScalars hs{a.decay, a.omb1, a.beta2, a.omb2, a.eps, step_size, bc2_sqrt};
+        const float p = adamw_step(a.w + i, a.m + i, a.v + i, a.vmax + i, g, hs);
         if (upd_next) a.wt[i] = soft_update(p, __ldcg(a.wt + i), a.tau, a.omtau);
     }
 }
@@ -761,31 +735,6 @@ k_q_values(const float *__restrict__ net, Dims d, Plan pl, int R, int mch, int n
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-struct prl_dqn {
-    prl_dqn_cfg cfg;
-    Dims d;
-    float *w, *wt, *m, *v, *vmax;
-    int64_t adam_step;
-    // workspace carve-up (device)
-    float *gpart;
-    int32_t *slots, *logical;
-    float2 *scal_dev;
-    uint32_t *tmp_rec;
-    int32_t *tmp_slots;
-    prl_buf_layout tmp_lay;
-    // pinned per-round optimizer scalars, double buffered
-    float2 *scal_host[2];
-    cudaEvent_t scal_done[2];
-    int scal_next;
-    int sm_count, max_smem;
-    int last_launches, last_ctas, last_rows;
-    // optional device timing of the persistent kernel (bench / roofline)
-    int timing;
-    cudaEvent_t t0, t1;
-    long long *prof;
-    prl_comm *comm;
-};
-
 static const int kMaxCtas = 148;
 
 static int64_t align_up64(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -816,7 +765,7 @@ extern "C" int64_t prl_dqn_param_count(const prl_dqn_cfg *c) {
     return make_dims(c->obs_dim, c->n_actions, c->hidden1, c->hidden2).P;
 }
 
-struct WsPlan { int64_t gpart, slots, logical, scal, tmp_rec, tmp_slots, total; };
+struct WsPlan { int64_t gpart, slots, logical, scal, tmp_rec, tmp_slots, multi, total; };
 static WsPlan ws_plan(const prl_dqn_cfg *c) {
     Dims d = make_dims(c->obs_dim, c->n_actions, c->hidden1, c->hidden2);
     WsPlan w;
@@ -827,6 +776,7 @@ static WsPlan ws_plan(const prl_dqn_cfg *c) {
     w.scal = o; o = align_up64(o + (int64_t)c->max_rounds * 8, 256);
     w.tmp_rec = o; o = align_up64(o + tmp_layout(c).storage_bytes, 256);
     w.tmp_slots = o; o = align_up64(o + (int64_t)c->max_batch * 4, 256);
+    w.multi = o; o = align_up64(o + 64 * 1024, 256);
     w.total = o;
     return w;
 }
@@ -856,6 +806,7 @@ extern "C" int prl_dqn_create(prl_dqn **out, const prl_dqn_cfg *cfg, float *w, f
     q->scal_dev = (float2 *)(base + ws.scal);
     q->tmp_rec = (uint32_t *)(base + ws.tmp_rec);
     q->tmp_slots = (int32_t *)(base + ws.tmp_slots);
+    q->multi_dev = (void *)(base + ws.multi);
     q->tmp_lay = tmp_layout(cfg);
     q->scal_next = 0;
     q->scal_host[0] = q->scal_host[1] = nullptr;
@@ -1024,16 +975,9 @@ static int choose_tiling(const prl_dqn *q, int B, int W, int *R_out, int *mch_ou
     return PRL_OK;
 }
 
-static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layout &lay, int buf_flags,
-                        const int32_t *slots, int rounds, int B, int64_t steps0, int first_update, float *out_mae,
-                        float *out_q, float *out_y, cudaStream_t stream, prl_buf *sample_from = nullptr,
-                        int32_t *out_logical = nullptr) {
-    int R, mch;
-    Plan pl;
-    int rc = choose_tiling(q, B, lay.record_words, &R, &mch, &pl);
-    if (rc) return rc;
+// per-round optimizer scalars exactly as torch evaluates them (Python floats -> fp32)
+int prl_dqn_stage_scalars(prl_dqn *q, int rounds, cudaStream_t stream) {
     const prl_dqn_cfg &c = q->cfg;
-    // per-round optimizer scalars exactly as torch evaluates them (Python floats)
     const int sb = q->scal_next;
     q->scal_next ^= 1;
     PRL_CUDA(cudaEventSynchronize(q->scal_done[sb]));
@@ -1044,6 +988,20 @@ static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layou
     }
     PRL_CUDA(cudaMemcpyAsync(q->scal_dev, q->scal_host[sb], (size_t)rounds * 8, cudaMemcpyHostToDevice, stream));
     PRL_CUDA(cudaEventRecord(q->scal_done[sb], stream));
+    return PRL_OK;
+}
+
+static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layout &lay, int buf_flags,
+                        const int32_t *slots, int rounds, int B, int64_t steps0, int first_update, float *out_mae,
+                        float *out_q, float *out_y, cudaStream_t stream, prl_buf *sample_from = nullptr,
+                        int32_t *out_logical = nullptr) {
+    int R, mch;
+    Plan pl;
+    int rc = choose_tiling(q, B, lay.record_words, &R, &mch, &pl);
+    if (rc) return rc;
+    const prl_dqn_cfg &c = q->cfg;
+    rc = prl_dqn_stage_scalars(q, rounds, stream);
+    if (rc) return rc;
 
     LearnArgs a;
     a.records = records; a.lay = lay; a.buf_flags = buf_flags; a.slots = slots;

@@ -1,0 +1,630 @@
+// dqn_tc.cu — tensor-core DQN learner: ONE SM (one CTA) runs one complete learner, every dense
+// contraction of the step on tcgen05 (3xTF32 UMMA, fp32 accumulators in TMEM), so that a launch
+// with L CTAs trains L independent learners (seeds / agents) concurrently — the aggregate mode that
+// fills a B200 — and a single learner needs one SM instead of 65.
+//
+// Same semantics as the cooperative SIMT kernel in dqn.cu (DeepQLearning.learn: sample -> Q(s,a) ->
+// max_a' Q_target(s',a') -> MSE -> backward -> AdamW(amsgrad) -> scheduled soft target update; reference
+// call sites in include/pearl_b200.h).  Supported shape class: two hidden layers of 64, obs % 8 == 0,
+// obs <= 128, n_actions in {1,2,4,8,16}, batch in {128, 256}; everything else stays on the SIMT kernel.
+//
+// Per gradient step (256 threads, thread (m = tid % 128, h = tid / 128) owns batch row m of the
+// current 128-row tile = TMEM lane m, and column half h):
+//   phase T  target net: T1 = S' W1s^T per row tile (K chunks of 64 staged through smem); then one
+//            128 x 64 x 64 product per (row tile, action slot): A tile row m = relu(T1[m] + W1a[:,a] + b1)
+//            built from registers, two thread groups ping-pong (own A buffer + own accumulator) so the
+//            tensor pipe always has the other group's tile; running max over action slots in registers.
+//   phase O  online net forward (same tiles), loss gradient, dZ2, dH1 = dZ2 W2 (B operand = W2^T tile),
+//            and the weight gradients as tensor-core products over the batch dimension:
+//            dW2 = dZ2^T H1, dW1s = dZ1^T S, and [db | dW1a] = dZ^T E with E = [1 | onehot(action)];
+//            their operands are explicitly transposed tiles written with a 144-byte chunk pitch
+//            (bank-conflict-free column scatter).  Accumulators for all of these live in TMEM.
+//   AdamW    gradients read straight from TMEM (M = 64 lane map), parameters / moments in L2.
+#include <math.h>
+#include <stdarg.h>
+
+#include <new>
+
+#include "dqn_common.cuh"
+#include "sampler.cuh"
+#include "umma.cuh"
+
+using namespace prl;
+
+int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *smem_bytes);
+
+namespace {
+
+constexpr int NTH = 256;
+constexpr int HID = 64;
+constexpr int MAX_B = 256;
+// shared memory regions (bytes)
+constexpr int REG1 = 0, REG2 = 65536, REG3 = 131072, MISC_OFF = 196608;
+constexpr int HALF = 32768;          // hi tile at region base, lo tile at base + HALF
+// transposed-tile arena (regions 1+2) for the weight-gradient products, 64 batch rows per pass
+constexpr int TL = 144;              // chunk pitch of transposed tiles
+constexpr int AR_A_HI = 0, AR_A_LO = 18432, AR_B_HI = 36864, AR_B_LO = 73728, AR_E = 110592;
+// TMEM columns
+constexpr int TM_T1 = 0, TM_ACC0 = 128, TM_ACC1 = 192, TM_DW2 = 256, TM_DW1 = 320, TM_DE2 = 448, TM_DE1 = 480;
+
+struct TcLearner {            // one per CTA, in global memory
+    const uint32_t *records;
+    const int32_t *slots;     // [rounds][B]
+    float *w, *wt, *m, *v, *vmax;
+    const float2 *scal;       // [rounds]
+    float *out_mae, *out_q, *out_y;
+    long long steps0;
+    int buf_flags;
+    int pad_;
+};
+
+struct TcArgs {
+    const TcLearner *learners;
+    prl_buf_layout lay;
+    Dims d;
+    int B, rounds, freq;
+    float decay, omb1, beta2, omb2, eps, gamma, tau, omtau, inv_b2;
+};
+
+struct Misc {
+    float watb[16][HID];     // W1[:, obs + a] + b1 of the network being evaluated
+    float b2[HID], w3[HID];
+    float b3, pad0[3];
+    float y[MAX_B];
+    float vpart[128][2];
+    float vmax2[2][128];
+    int act[MAX_B], cnt[MAX_B], slot[MAX_B];
+    float rew[MAX_B], term[MAX_B];
+    float redw[8][32];
+    float redmae[8], reddb3[8];
+    unsigned long long bar[6];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory"); }
+
+__device__ __forceinline__ void st_split4(float *hi_base, float *lo_base, int idx, float4 v) {
+    float4 h, l;
+    umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+    umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<float4 *>(hi_base + idx) = h;
+    *reinterpret_cast<float4 *>(lo_base + idx) = l;
+}
+
+// weights of one network -> UMMA B-operand tiles + the small fp32 vectors
+__device__ void load_weights(const float *__restrict__ net, const Dims &d, char *smem, Misc &mi, bool with_w2t) {
+    const int tid = threadIdx.x;
+    float *w1hi = reinterpret_cast<float *>(smem + REG1), *w1lo = reinterpret_cast<float *>(smem + REG1 + HALF);
+    for (int e = tid; e < HID * d.obs; e += NTH) {           // W1[:, :obs]  -> tile [64 n][obs k]
+        const int n = e / d.obs, k = e - n * d.obs;
+        float hi, lo;
+        umma::split_tf32(__ldcg(net + d.oW1 + (size_t)n * d.D + k), hi, lo);
+        const int idx = umma::tile_index(n, k, d.obs);
+        w1hi[idx] = hi; w1lo[idx] = lo;
+    }
+    float *w2hi = reinterpret_cast<float *>(smem + REG3), *w2lo = w2hi + 4096;
+    float *w2thi = w2hi + 8192, *w2tlo = w2hi + 12288;
+    for (int e = tid; e < HID * HID; e += NTH) {             // W2 -> tile [64 j][64 k]; W2^T -> tile [64 k][64 j]
+        const int j = e >> 6, k = e & 63;
+        float hi, lo;
+        umma::split_tf32(__ldcg(net + d.oW2 + e), hi, lo);
+        const int idx = umma::tile_index(j, k, HID);
+        w2hi[idx] = hi; w2lo[idx] = lo;
+        if (with_w2t) {
+            const int it = umma::tile_index(k, j, HID);
+            w2thi[it] = hi; w2tlo[it] = lo;
+        }
+    }
+    for (int e = tid; e < d.A * HID; e += NTH) {
+        const int j = e / d.A, a = e - j * d.A;
+        mi.watb[a][j] = __ldcg(net + d.oW1 + (size_t)j * d.D + d.obs + a) + __ldcg(net + d.ob1 + j);
+    }
+    if (tid < HID) { mi.b2[tid] = __ldcg(net + d.ob2 + tid); mi.w3[tid] = __ldcg(net + d.oW3 + tid); }
+    if (tid == 0) mi.b3 = __ldcg(net + d.ob3);
+}
+
+// 128 rows x 64 columns [kc*64, kc*64+64) of state / next_state -> A tile (hi/lo) in region 2
+__device__ void build_rows_chunk(const TcArgs &a, const TcLearner &L, const Misc &mi, char *smem, int field_off, int tile,
+                                 int kc) {
+    const int m = threadIdx.x & 127, h = threadIdx.x >> 7;
+    float *hi = reinterpret_cast<float *>(smem + REG2), *lo = reinterpret_cast<float *>(smem + REG2 + HALF);
+    const int k0 = kc * 64 + h * 32;
+    const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[tile * 128 + m] * a.lay.record_words) +
+                       field_off + k0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + 4 * i < a.d.obs) v = __ldg(reinterpret_cast<const float4 *>(src + 4 * i));
+        st_split4(hi, lo, umma::tile_index(m, h * 32 + 4 * i, 64), v);
+    }
+}
+
+// T1[tile] = X[tile rows] W1s^T for every row tile, X = state (online) or next_state (target)
+__device__ void layer1_all_tiles(const TcArgs &a, const TcLearner &L, Misc &mi, char *smem, int field_off, uint32_t tm,
+                                 uint32_t &par0) {
+    const int ntiles = a.B >> 7;
+    const umma::Tile A_hi = umma::make_tile(smem + REG2, 64, 128), A_lo = umma::make_tile(smem + REG2 + HALF, 64, 128);
+    const umma::Tile B_hi = umma::make_tile(smem + REG1, a.d.obs, 128), B_lo = umma::make_tile(smem + REG1 + HALF, a.d.obs, 128);
+    for (int t = 0; t < ntiles; t++)
+        for (int kc = 0; kc * 64 < a.d.obs; kc++) {
+            build_rows_chunk(a, L, mi, smem, field_off, t, kc);
+            umma::fence_async_smem();
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                umma::fence_after_thread_sync();
+                const int keff = min(64, a.d.obs - kc * 64);
+                umma::gemm3(tm + TM_T1 + t * 64, A_hi, A_lo, B_hi.shifted(kc * 2048), B_lo.shifted(kc * 2048), 128, HID, keff,
+                            kc > 0);
+                umma::mma_commit(reinterpret_cast<uint64_t *>(&mi.bar[0]));
+            }
+            umma::mbar_wait(reinterpret_cast<uint64_t *>(&mi.bar[0]), par0);
+            par0 ^= 1;
+            umma::fence_after_thread_sync();
+        }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
+    extern __shared__ __align__(1024) char smem[];
+    Misc &mi = *reinterpret_cast<Misc *>(smem + MISC_OFF);
+    const TcLearner L = a.learners[blockIdx.x];
+    const Dims &d = a.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = tid & 127, h = tid >> 7;
+    const int ntiles = a.B >> 7;
+    const int W = a.lay.record_words;
+
+    if (warp == 0) umma::tmem_alloc(&mi.tmem_base, 512);
+    if (tid == 0)
+        for (int i = 0; i < 6; i++) umma::mbar_init(reinterpret_cast<uint64_t *>(&mi.bar[i]), 1);
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tm = mi.tmem_base;
+    const uint32_t tlane = tm + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
+    uint32_t par0 = 0, parg = 0, par3 = 0, par4 = 0, par5 = 0;        // mbarrier phase parities
+    uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
+
+    for (int round = 0; round < a.rounds; round++) {
+        // ---- per-round row scalars + L2 prefetch of the NEXT round's transitions
+        if (tid < a.B) {
+            const int slot = L.slots[(size_t)round * a.B + tid];
+            const uint32_t *r = L.records + (size_t)slot * W;
+            mi.slot[tid] = slot;
+            mi.act[tid] = (int)r[a.lay.off_action];
+            mi.rew[tid] = __uint_as_float(r[a.lay.off_reward]);
+            const uint32_t fl = r[a.lay.off_flags];
+            mi.term[tid] = (fl & 1u) ? 1.f : 0.f;
+            mi.cnt[tid] = (int)((fl >> 8) & 0xffffu);
+            if (round + 1 < a.rounds) {
+                const char *nx = reinterpret_cast<const char *>(L.records + (size_t)L.slots[(size_t)(round + 1) * a.B + tid] * W);
+                for (int o = 0; o < W * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+            }
+        }
+        // ---- scheduled soft target update happens BEFORE this round's gradient step
+        //      (deep_td_learning.py:283-284: (training_steps + 1) % freq == 0)
+        if ((L.steps0 + round + 2) % a.freq == 0)
+            for (int i = tid; i < d.P; i += NTH) L.wt[i] = soft_update(__ldcg(L.w + i), __ldcg(L.wt + i), a.tau, a.omtau);
+        __syncthreads();
+
+        // ================= phase T: y = max_a' Q_target(s', a') * gamma * (1 - term) + r =================
+        load_weights(L.wt, d, smem, mi, false);
+        __syncthreads();
+        layer1_all_tiles(a, L, mi, smem, a.lay.off_next_state, tm, par0);
+        {
+            // group g = h: own A buffer (g=0: region 2, g=1: region 1 — W1s is no longer needed), own accumulator
+            float *ahi = reinterpret_cast<float *>(smem + (h ? REG1 : REG2)), *alo = ahi + HALF / 4;
+            const umma::Tile A_hi = umma::make_tile(ahi, 64, 128), A_lo = umma::make_tile(alo, 64, 128);
+            const umma::Tile B_hi = umma::make_tile(smem + REG3, 64, 128), B_lo = umma::make_tile(smem + REG3 + 16384, 64, 128);
+            const uint32_t acc_col = h ? TM_ACC1 : TM_ACC0;
+            __syncthreads();  // every thread is past layer 1: region 1 may be overwritten
+            for (int t = 0; t < ntiles; t++) {
+                const int row = t * 128 + m;
+                float t1[64];
+                umma::tmem_ld32(tlane + TM_T1 + t * 64, t1);
+                umma::tmem_ld32(tlane + TM_T1 + t * 64 + 32, t1 + 32);
+                const int cnt = mi.cnt[row];
+                const uint8_t *ids = reinterpret_cast<const uint8_t *>(L.records + (size_t)mi.slot[row] * W + a.lay.off_avail);
+                float best = -INFINITY;
+                for (int act = h; act < d.A; act += 2) {
+                    int id = act;
+                    if ((L.buf_flags & PRL_BUF_DYNAMIC_ACTIONS) && act < cnt) id = ids[act];
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; c4++) {
+                        const float4 wv = *reinterpret_cast<const float4 *>(&mi.watb[id][4 * c4]);
+                        float4 v;
+                        v.x = fmaxf(t1[4 * c4 + 0] + wv.x, 0.f); v.y = fmaxf(t1[4 * c4 + 1] + wv.y, 0.f);
+                        v.z = fmaxf(t1[4 * c4 + 2] + wv.z, 0.f); v.w = fmaxf(t1[4 * c4 + 3] + wv.w, 0.f);
+                        st_split4(ahi, alo, umma::tile_index(m, 4 * c4, 64), v);
+                    }
+                    umma::fence_async_smem();
+                    umma::fence_before_thread_sync();
+                    group_sync(h);
+                    if (m == 0) {
+                        umma::fence_after_thread_sync();
+                        umma::gemm3(tm + acc_col, A_hi, A_lo, B_hi, B_lo, 128, HID, HID, false);
+                        umma::mma_commit(&bar[1 + h]);
+                    }
+                    umma::mbar_wait(&bar[1 + h], parg);
+                    parg ^= 1;
+                    umma::fence_after_thread_sync();
+                    float acc[64];
+                    umma::tmem_ld32(tlane + acc_col, acc);
+                    umma::tmem_ld32(tlane + acc_col + 32, acc + 32);
+                    float q = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 64; c++) q = fmaf(mi.w3[c], fmaxf(acc[c] + mi.b2[c], 0.f), q);
+                    q += mi.b3;
+                    if (act >= cnt) q = -INFINITY;   // next_state_action_values[mask] = -inf
+                    best = fmaxf(best, q);
+                }
+                mi.vmax2[h][m] = best;
+                umma::fence_before_thread_sync();
+                __syncthreads();
+                if (h == 0) {
+                    const float v = fmaxf(mi.vmax2[0][m], mi.vmax2[1][m]);
+                    mi.y[row] = __fadd_rn(__fmul_rn(__fmul_rn(v, a.gamma), 1.f - mi.term[row]), mi.rew[row]);
+                }
+                __syncthreads();
+            }
+        }
+
+        // ================= phase O: online forward, loss, backward =================
+        load_weights(L.w, d, smem, mi, true);
+        __syncthreads();
+        layer1_all_tiles(a, L, mi, smem, a.lay.off_state, tm, par0);
+        float dw3_acc = 0.f, mae_acc = 0.f, db3_acc = 0.f;
+        const umma::Tile W2_hi = umma::make_tile(smem + REG3, 64, 128), W2_lo = umma::make_tile(smem + REG3 + 16384, 64, 128);
+        const umma::Tile W2T_hi = umma::make_tile(smem + REG3 + 32768, 64, 128), W2T_lo = umma::make_tile(smem + REG3 + 49152, 64, 128);
+        float *r2hi = reinterpret_cast<float *>(smem + REG2), *r2lo = r2hi + HALF / 4;
+        const umma::Tile R2_hi = umma::make_tile(r2hi, 64, 128), R2_lo = umma::make_tile(r2lo, 64, 128);
+        for (int t = 0; t < ntiles; t++) {
+            const int row = t * 128 + m, c0 = h * 32;
+            float h1[32];
+            umma::tmem_ld32(tlane + TM_T1 + t * 64 + c0, h1);
+            {
+                const int ai = mi.act[row];
+#pragma unroll
+                for (int c = 0; c < 32; c++) h1[c] = fmaxf(h1[c] + mi.watb[ai][c0 + c], 0.f);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; c4++)
+                    st_split4(r2hi, r2lo, umma::tile_index(m, c0 + 4 * c4, 64),
+                              make_float4(h1[4 * c4], h1[4 * c4 + 1], h1[4 * c4 + 2], h1[4 * c4 + 3]));
+            }
+            umma::fence_async_smem();
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_thread_sync();
+                umma::gemm3(tm + TM_ACC0, R2_hi, R2_lo, W2_hi, W2_lo, 128, HID, HID, false);
+                umma::mma_commit(&bar[4]);
+            }
+            umma::mbar_wait(&bar[4], par4);
+            par4 ^= 1;
+            umma::fence_after_thread_sync();
+            float z[32];   // h2, then dz2
+            umma::tmem_ld32(tlane + TM_ACC0 + c0, z);
+            float part = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c++) { z[c] = fmaxf(z[c] + mi.b2[c0 + c], 0.f); part = fmaf(mi.w3[c0 + c], z[c], part); }
+            mi.vpart[m][h] = part;
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            const float q = mi.vpart[m][0] + mi.vpart[m][1] + mi.b3;
+            const float y = mi.y[row];
+            const float dq = (q - y) * a.inv_b2;
+            if (h == 0) {
+                if (L.out_q) L.out_q[(size_t)round * a.B + row] = q;
+                if (L.out_y) L.out_y[(size_t)round * a.B + row] = y;
+                mae_acc += fabsf(q - y);
+                db3_acc += dq;
+            }
+            // dW3[c0 + c] += sum_rows dq * h2 : reduce over this warp's 32 rows, lane c keeps column c
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const float s = warp_sum(dq * z[c]);
+                if (lane == c) dw3_acc += s;
+            }
+#pragma unroll
+            for (int c = 0; c < 32; c++) z[c] = (z[c] > 0.f) ? dq * mi.w3[c0 + c] : 0.f;   // dZ2
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++)
+                st_split4(r2hi, r2lo, umma::tile_index(m, c0 + 4 * c4, 64),
+                          make_float4(z[4 * c4], z[4 * c4 + 1], z[4 * c4 + 2], z[4 * c4 + 3]));
+            umma::fence_async_smem();
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_thread_sync();
+                umma::gemm3(tm + TM_ACC1, R2_hi, R2_lo, W2T_hi, W2T_lo, 128, HID, HID, false);   // dH1 = dZ2 W2
+                umma::mma_commit(&bar[5]);
+            }
+            umma::mbar_wait(&bar[5], par5);
+            par5 ^= 1;
+            umma::fence_after_thread_sync();
+            float dz1[32];
+            umma::tmem_ld32(tlane + TM_ACC1 + c0, dz1);
+#pragma unroll
+            for (int c = 0; c < 32; c++) dz1[c] = (h1[c] > 0.f) ? dz1[c] : 0.f;
+
+            // ---- weight gradients: contractions over the batch rows, 64 rows per pass
+            float *arena = reinterpret_cast<float *>(smem);
+            const umma::Tile TA_hi = umma::make_tile(smem + AR_A_HI, 64, TL), TA_lo = umma::make_tile(smem + AR_A_LO, 64, TL);
+            const umma::Tile TB_hi = umma::make_tile(smem + AR_B_HI, 64, TL), TB_lo = umma::make_tile(smem + AR_B_LO, 64, TL);
+            const umma::Tile TE = umma::make_tile(smem + AR_E, 64, TL);
+            for (int hf = 0; hf < 2; hf++) {
+                const bool mine = (m >> 6) == hf;
+                const int rr = m & 63;
+                const bool first = (t == 0 && hf == 0);
+                umma::fence_before_thread_sync();
+                __syncthreads();   // previous products have been waited for: the arena is free
+                if (mine) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int idx = umma::tile_index2(c0 + c, rr, 64, TL);
+                        float hi, lo;
+                        umma::split_tf32(z[c], hi, lo);            // dZ2^T
+                        arena[AR_A_HI / 4 + idx] = hi; arena[AR_A_LO / 4 + idx] = lo;
+                        umma::split_tf32(h1[c], hi, lo);           // H1^T
+                        arena[AR_B_HI / 4 + idx] = hi; arena[AR_B_LO / 4 + idx] = lo;
+                    }
+                    const int ai = mi.act[row];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {                 // E^T: [1 | onehot(action)]
+                        const int er = h * 16 + e;
+                        arena[AR_E / 4 + umma::tile_index2(er, rr, 64, TL)] = (er == 0 || er == ai + 1) ? 1.f : 0.f;
+                    }
+                }
+                umma::fence_async_smem();
+                umma::fence_before_thread_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    umma::fence_after_thread_sync();
+                    umma::gemm3(tm + TM_DW2, TA_hi, TA_lo, TB_hi, TB_lo, 64, HID, 64, !first);
+                    umma::gemm3(tm + TM_DE2, TA_hi, TA_lo, TE, TE, 64, 32, 64, !first, false, true);
+                    umma::mma_commit(&bar[3]);
+                }
+                umma::mbar_wait(&bar[3], par3);
+                par3 ^= 1;
+                umma::fence_after_thread_sync();
+                umma::fence_before_thread_sync();
+                __syncthreads();
+                if (mine) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int idx = umma::tile_index2(c0 + c, rr, 64, TL);
+                        float hi, lo;
+                        umma::split_tf32(dz1[c], hi, lo);          // dZ1^T
+                        arena[AR_A_HI / 4 + idx] = hi; arena[AR_A_LO / 4 + idx] = lo;
+                    }
+                    // S^T: this thread scatters half of its row's state vector into column rr
+                    const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[row] * W) + a.lay.off_state;
+                    const int kh = (d.obs + 1) >> 1, kb = h * kh & ~3, ke = h ? d.obs : (kh & ~3);
+                    for (int k = kb; k < ke; k += 4) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(src + k));
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            float hi, lo;
+                            umma::split_tf32(vv[u], hi, lo);
+                            const int idx = umma::tile_index2(k + u, rr, 64, TL);
+                            arena[AR_B_HI / 4 + idx] = hi; arena[AR_B_LO / 4 + idx] = lo;
+                        }
+                    }
+                }
+                umma::fence_async_smem();
+                umma::fence_before_thread_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    umma::fence_after_thread_sync();
+                    umma::gemm3(tm + TM_DW1, TA_hi, TA_lo, TB_hi, TB_lo, 64, d.obs, 64, !first);
+                    umma::gemm3(tm + TM_DE1, TA_hi, TA_lo, TE, TE, 64, 32, 64, !first, false, true);
+                    umma::mma_commit(&bar[3]);
+                }
+                umma::mbar_wait(&bar[3], par3);
+                par3 ^= 1;
+                umma::fence_after_thread_sync();
+            }
+        }
+
+        // ================= AdamW (gradients straight from TMEM; M = 64 rows live in lanes 32q + (0..15)) ==========
+        mi.redw[warp][lane] = dw3_acc;
+        if (lane == 0) { mi.redmae[warp] = 0.f; mi.reddb3[warp] = 0.f; }
+        {
+            const float ms = warp_sum(mae_acc), ds = warp_sum(db3_acc);
+            if (lane == 0) { mi.redmae[warp] = ms; mi.reddb3[warp] = ds; }
+        }
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        umma::fence_after_thread_sync();
+        {
+            const float2 sc = L.scal[round];
+            const AdamScalars hs{a.decay, a.omb1, a.beta2, a.omb2, a.eps, sc.x, sc.y};
+            const int j = (warp & 3) * 16 + (lane & 15);   // output unit handled by this lane (lanes >= 16 idle)
+            const bool live = lane < 16;
+            float g[32];
+            // W2[j][h*32 .. +32)
+            umma::tmem_ld32(tlane + TM_DW2 + h * 32, g);
+            if (live)
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const int i = d.oW2 + j * HID + h * 32 + c;
+                    adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[c], hs);
+                }
+            // W1[j][k], state columns: half h covers [h*64, h*64+64)
+            for (int cc = 0; cc < 2; cc++) {
+                const int kbase = h * 64 + cc * 32;
+                if (kbase < d.obs) {   // warp-uniform
+                    umma::tmem_ld32(tlane + TM_DW1 + kbase, g);
+                    if (live)
+#pragma unroll
+                        for (int c = 0; c < 32; c++)
+                            if (kbase + c < d.obs) {
+                                const int i = d.oW1 + j * d.D + kbase + c;
+                                adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[c], hs);
+                            }
+                }
+            }
+            // biases and the action columns of W1 from the E products
+            umma::tmem_ld32(tlane + (h ? TM_DE1 : TM_DE2), g);
+            if (live) {
+                if (h == 0) {
+                    const int i = d.ob2 + j;
+                    adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[0], hs);
+                } else {
+                    int i = d.ob1 + j;
+                    adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[0], hs);
+                    for (int k = 0; k < d.A; k++) {
+                        i = d.oW1 + j * d.D + d.obs + k;
+                        adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[1 + k], hs);
+                    }
+                }
+            }
+            if (tid < HID) {   // W3: sum the four row-quarter partials of this column in fixed order
+                const int hh = tid >> 5, c = tid & 31;
+                const float gw = ((mi.redw[hh * 4 + 0][c] + mi.redw[hh * 4 + 1][c]) + mi.redw[hh * 4 + 2][c]) + mi.redw[hh * 4 + 3][c];
+                const int i = d.oW3 + tid;
+                adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, gw, hs);
+            }
+            if (tid == HID) {
+                const float gb = ((mi.reddb3[0] + mi.reddb3[1]) + mi.reddb3[2]) + mi.reddb3[3];
+                const int i = d.ob3;
+                adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, gb, hs);
+                const float e = ((mi.redmae[0] + mi.redmae[1]) + mi.redmae[2]) + mi.redmae[3];
+                L.out_mae[round] = e / (float)a.B;   // reported "loss": mean |q - y|
+            }
+        }
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        umma::fence_after_thread_sync();
+    }
+    if (warp == 0) umma::tmem_dealloc(tm, 512);
+}
+
+// all learners' index streams in one launch: CTA i draws `rounds` samples for learner i
+struct MultiSampler {
+    uint32_t *mt_state;
+    SamplerParams sp;
+};
+__global__ void __launch_bounds__(kSamplerThreads, 1) k_sample_indices_multi(const MultiSampler *items, int rounds) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ SamplerState S;
+    const MultiSampler it = items[blockIdx.x];
+    sampler_init(S, it.mt_state, dyn, it.sp);
+    sampler_advance(S, dyn, it.sp, rounds);
+    __syncthreads();
+    sampler_store(S, it.mt_state);
+}
+
+}  // namespace
+
+static bool tc_eligible(const prl_dqn_cfg &c, int batch) {
+    const bool a_ok = c.n_actions == 1 || c.n_actions == 2 || c.n_actions == 4 || c.n_actions == 8 || c.n_actions == 16;
+    return c.hidden1 == HID && c.hidden2 == HID && c.obs_dim % 8 == 0 && c.obs_dim >= 8 && c.obs_dim <= 128 && a_ok &&
+           !c.double_dqn && (batch == 128 || batch == 256);
+}
+
+extern "C" int prl_dqn_tc_supported(const prl_dqn *q, int batch) { return q && tc_eligible(q->cfg, batch) ? 1 : 0; }
+
+extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, int count, int rounds, int batch,
+                                   const int64_t *training_steps0, float *const *out_mae, float *const *out_q,
+                                   float *const *out_y, int32_t *const *out_logical, void *stream_) {
+    PRL_REQUIRE(dqns && bufs && training_steps0 && out_mae && count > 0, "null / empty argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    prl_dqn *q0 = dqns[0];
+    const prl_dqn_cfg &c = q0->cfg;
+    if (!tc_eligible(c, batch))
+        return fail(PRL_EUNSUPPORTED,
+                    "tensor-core learner needs hidden [64,64], obs %% 8 == 0 <= 128, actions in {1,2,4,8,16}, DQN, batch 128/256");
+    PRL_REQUIRE(rounds > 0 && rounds <= c.max_rounds && batch <= c.max_batch, "rounds / batch outside the configured maxima");
+    PRL_REQUIRE((size_t)count * (sizeof(TcLearner) + sizeof(MultiSampler)) <= 64 * 1024, "too many learners in one group");
+    PRL_REQUIRE(count <= q0->sm_count, "more learners than SMs in one launch");
+    // per-learner descriptors are staged in pinned memory of learner 0 and copied to its workspace
+    static thread_local TcLearner *h_learn = nullptr;
+    static thread_local MultiSampler *h_samp = nullptr;
+    static thread_local cudaEvent_t h_done = nullptr;
+    if (!h_learn) {
+        PRL_CUDA(cudaHostAlloc((void **)&h_learn, 32 * 1024, cudaHostAllocDefault));
+        PRL_CUDA(cudaHostAlloc((void **)&h_samp, 32 * 1024, cudaHostAllocDefault));
+        PRL_CUDA(cudaEventCreateWithFlags(&h_done, cudaEventDisableTiming));
+    }
+    PRL_CUDA(cudaEventSynchronize(h_done));
+    size_t samp_smem = 0;
+    for (int i = 0; i < count; i++) {
+        prl_dqn *q = dqns[i];
+        prl_buf *b = bufs[i];
+        PRL_REQUIRE(q && b, "null learner / buffer");
+        const prl_dqn_cfg &ci = q->cfg;
+        PRL_REQUIRE(ci.obs_dim == c.obs_dim && ci.n_actions == c.n_actions && ci.hidden1 == c.hidden1 &&
+                        ci.hidden2 == c.hidden2 && ci.double_dqn == c.double_dqn &&
+                        ci.target_update_freq == c.target_update_freq && ci.lr == c.lr && ci.beta1 == c.beta1 &&
+                        ci.beta2 == c.beta2 && ci.eps == c.eps && ci.weight_decay == c.weight_decay &&
+                        ci.gamma == c.gamma && ci.tau == c.tau && rounds <= ci.max_rounds && batch <= ci.max_batch,
+                    "all learners of a group must share one configuration");
+        PRL_REQUIRE((b->desc.flags & PRL_BUF_DISCRETE) && b->desc.obs_dim == c.obs_dim && b->desc.n_actions == c.n_actions,
+                    "buffer %d does not match the learner", i);
+        PRL_REQUIRE(b->lay.record_words == bufs[0]->lay.record_words && b->lay.off_avail == bufs[0]->lay.off_avail,
+                    "buffers must share one record layout");
+        int rc = prl_dqn_stage_scalars(q, rounds, stream);
+        if (rc) return rc;
+        size_t sbytes = 0;
+        rc = prl_sampler_params(b, batch, &h_samp[i].sp, &sbytes);
+        if (rc) return rc;
+        if (sbytes > samp_smem) samp_smem = sbytes;
+        h_samp[i].mt_state = b->mt_state;
+        h_samp[i].sp.out_slot = q->slots;
+        h_samp[i].sp.out_logical = out_logical ? out_logical[i] : nullptr;
+        TcLearner &L = h_learn[i];
+        L.records = b->records; L.slots = q->slots;
+        L.w = q->w; L.wt = q->wt; L.m = q->m; L.v = q->v; L.vmax = q->vmax;
+        L.scal = q->scal_dev;
+        L.out_mae = out_mae[i]; L.out_q = out_q ? out_q[i] : nullptr; L.out_y = out_y ? out_y[i] : nullptr;
+        L.steps0 = training_steps0[i];
+        L.buf_flags = b->desc.flags;
+        L.pad_ = 0;
+    }
+    TcLearner *d_learn = reinterpret_cast<TcLearner *>(q0->multi_dev);
+    MultiSampler *d_samp = reinterpret_cast<MultiSampler *>(reinterpret_cast<char *>(q0->multi_dev) + 32 * 1024);
+    PRL_CUDA(cudaMemcpyAsync(d_learn, h_learn, (size_t)count * sizeof(TcLearner), cudaMemcpyHostToDevice, stream));
+    PRL_CUDA(cudaMemcpyAsync(d_samp, h_samp, (size_t)count * sizeof(MultiSampler), cudaMemcpyHostToDevice, stream));
+    PRL_CUDA(cudaEventRecord(h_done, stream));
+
+    PRL_CUDA(cudaFuncSetAttribute(k_sample_indices_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_sample_indices_multi<<<count, kSamplerThreads, samp_smem, stream>>>(d_samp, rounds);
+    PRL_CUDA(cudaGetLastError());
+
+    TcArgs a;
+    a.learners = d_learn;
+    a.lay = bufs[0]->lay;
+    a.d = q0->d;
+    a.B = batch; a.rounds = rounds; a.freq = c.target_update_freq;
+    a.decay = (float)(1.0 - c.lr * c.weight_decay);
+    a.omb1 = (float)(1.0 - c.beta1);
+    a.beta2 = (float)c.beta2;
+    a.omb2 = (float)(1.0 - c.beta2);
+    a.eps = (float)c.eps;
+    a.gamma = (float)c.gamma;
+    a.tau = (float)c.tau;
+    a.omtau = (float)(1.0 - c.tau);
+    a.inv_b2 = 2.0f / (float)batch;
+    const size_t smem = MISC_OFF + sizeof(Misc);
+    PRL_REQUIRE(smem <= (size_t)q0->max_smem, "tensor-core learner needs %zu B of shared memory", smem);
+    PRL_CUDA(cudaFuncSetAttribute(k_dqn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (q0->timing) PRL_CUDA(cudaEventRecord(q0->t0, stream));
+    k_dqn_tc<<<count, NTH, smem, stream>>>(a);
+    PRL_CUDA(cudaGetLastError());
+    if (q0->timing) PRL_CUDA(cudaEventRecord(q0->t1, stream));
+    for (int i = 0; i < count; i++) {
+        dqns[i]->adam_step += rounds;
+        dqns[i]->last_launches = 2;
+        dqns[i]->last_ctas = 1;
+        dqns[i]->last_rows = batch;
+    }
+    return PRL_OK;
+}

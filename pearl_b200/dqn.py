@@ -44,8 +44,13 @@ class _B200DQNMixin:
     _double = False
 
     def __init__(self, *args: Any, max_rounds_per_call: int = 4096, rows_per_cta: int = 0,
-                 **kwargs: Any) -> None:
+                 engine: str = "auto", **kwargs: Any) -> None:
+        """`engine`: "simt" = cooperative multi-SM fp32 kernel (lowest single-learner latency),
+        "tc" = tensor-core one-SM-per-learner kernel (what B200LearnerGroup uses), "auto" = simt."""
         super().__init__(*args, **kwargs)
+        if engine not in ("auto", "simt", "tc"):
+            raise ValueError("engine must be 'auto', 'simt' or 'tc'")
+        self._engine = engine
         if getattr(self, "_is_conservative", False):
             raise NotImplementedError("conservative (CQL) updates are outside the fused path")
         arm = self.action_representation_module
@@ -235,12 +240,21 @@ class _B200DQNMixin:
             stream = _stream_ptr(dev)
             replay_buffer._rng_push()
             done = 0
+            use_tc = self._engine == "tc"
+            if use_tc and not self._libh.prl_dqn_tc_supported(self._handle, bs):
+                raise NotImplementedError("engine='tc' does not support this network / batch shape")
             while done < rounds:
                 r = min(self._max_rounds, rounds - done)
                 off = lambda t, w=1: C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr() + 4 * done * w)
-                _lib.check(self._libh.prl_dqn_learn(self._handle, replay_buffer.handle, r, bs,
-                                                    int(self._training_steps), off(mae), off(q, bs), off(y, bs),
-                                                    off(idx, bs), stream))
+                if use_tc:
+                    one = lambda p: (C.c_void_p * 1)(p)
+                    _lib.check(self._libh.prl_dqn_learn_multi(
+                        one(self._handle), one(replay_buffer.handle), 1, r, bs, (C.c_int64 * 1)(int(self._training_steps)),
+                        one(off(mae)), one(off(q, bs)), one(off(y, bs)), one(off(idx, bs)), stream))
+                else:
+                    _lib.check(self._libh.prl_dqn_learn(self._handle, replay_buffer.handle, r, bs,
+                                                        int(self._training_steps), off(mae), off(q, bs), off(y, bs),
+                                                        off(idx, bs), stream))
                 self._training_steps += r
                 done += r
             replay_buffer._rng_pull()
@@ -318,6 +332,62 @@ class _B200DQNMixin:
             return exploit_action
         return self.exploration_module.act(subjective_state=subjective_state, action_space=available_action_space,
                                            exploit_action=exploit_action, values=q_avail)
+
+
+class B200LearnerGroup:
+    """`count` independent learners (seeds / agents) trained by ONE launch of the tensor-core kernel,
+    one SM per learner: `group.learn()` == `[l.learn(b) for l, b in zip(learners, buffers)]`, but the
+    learners run concurrently (the reference runs such replicas as separate processes,
+    utils/scripts/benchmark.py:80-116).  All learners must share one configuration."""
+
+    def __init__(self, learners, buffers) -> None:
+        if len(learners) != len(buffers) or not learners:
+            raise ValueError("need one replay buffer per learner")
+        self.learners, self.buffers = list(learners), list(buffers)
+
+    def learn(self) -> list:
+        n = len(self.learners)
+        l0 = self.learners[0]
+        rounds = int(l0._training_rounds)
+        sizes = [len(b) for b in self.buffers]
+        bs = [s if (l._batch_size == -1 or s < l._batch_size) else l._batch_size for l, s in zip(self.learners, sizes)]
+        if min(sizes) == 0 or len(set(bs)) != 1:
+            raise ValueError("all buffers of a group must be non-empty and give the same batch size")
+        bs = bs[0]
+        for l in self.learners:
+            l._bind(bs)
+        dev = l0._device
+        lib = l0._libh
+        if not lib.prl_dqn_tc_supported(l0._handle, bs):
+            raise NotImplementedError("the tensor-core group kernel does not support this network / batch shape")
+        mae = torch.empty((n, rounds), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = _stream_ptr(dev)
+            for b in self.buffers:
+                b._rng_push()
+            done = 0
+            while done < rounds:
+                r = min(l0._max_rounds, rounds - done)
+                arr = lambda xs: (C.c_void_p * n)(*xs)
+                _lib.check(lib.prl_dqn_learn_multi(
+                    arr([l._handle.value for l in self.learners]), arr([b.handle.value for b in self.buffers]), n, r, bs,
+                    (C.c_int64 * n)(*[int(l._training_steps) for l in self.learners]),
+                    arr([mae[i].data_ptr() + 4 * done for i in range(n)]), None, None, None, stream))
+                for l in self.learners:
+                    l._training_steps += r
+                done += r
+            for b in self.buffers:
+                b._rng_pull()
+        host = mae.cpu()
+        for l in self.learners:
+            l._sync_step_tensors()
+        return [{"loss": host[i].tolist()} for i in range(n)]
+
+    def set_kernel_timing(self, enable: bool = True) -> None:
+        self.learners[0].set_kernel_timing(enable)
+
+    def last_kernel_ms(self) -> float:
+        return self.learners[0].last_kernel_ms()
 
 
 class B200DeepQLearning(_B200DQNMixin, _RefDeepQLearning):

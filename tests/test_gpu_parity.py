@@ -345,3 +345,70 @@ def test_full_size_cfg2_against_oracle_on_the_sampled_batches():
     assert_close(np.asarray(rep["loss"]), np.asarray(losses), "cfg2 loss")
     assert_close(learner.flat_parameters.cpu().numpy(), flat(orc.Q).numpy(), "cfg2 params after 12 rounds")
     assert_close(learner.flat_target_parameters.cpu().numpy(), flat(orc.Qt).numpy(), "cfg2 target params")
+
+
+# --------------------------------------------------------------------------- tensor-core engine
+def test_tc_engine_matches_reference_golden_cfg2():
+    """The one-SM tcgen05 learner (3xTF32) on the cfg2-shaped fixture: same indices, q, y, loss,
+    parameters, target parameters and AdamW state as the recorded reference run, 1e-4."""
+    name = "dqn_cfg2_pool"
+    fx, cfg, data, buf, learner = build_from_fixture(name)
+    learner._engine = "tc"
+    random.setstate((3, tuple(int(x) for x in fx["mt_state_before"]), None))
+    cuts = sorted(set(cfg["snap_rounds"] + [cfg["rounds"]]))
+    done, idx, q, y, mae = 0, [], [], [], []
+    for c in cuts:
+        learner._training_rounds = c - done
+        rep = learner.learn(buf, trace=True)
+        idx.append(rep["idx"].cpu().numpy()); q.append(rep["q"].cpu().numpy()); y.append(rep["y"].cpu().numpy())
+        mae += rep["loss"]
+        done = c
+        if c in cfg["snap_rounds"]:
+            assert_close(learner.flat_parameters.cpu().numpy(), fx[f"q_after_{c}"], f"tc params after {c}")
+            assert_close(learner.flat_target_parameters.cpu().numpy(), fx[f"qt_after_{c}"], f"tc target after {c}")
+    assert np.array_equal(np.concatenate(idx), fx["idx"])
+    assert_close(np.concatenate(q), fx["q"], "tc q")
+    assert_close(np.concatenate(y), fx["y"], "tc y")
+    assert_close(np.asarray(mae), fx["mae"], "tc loss")
+    st = learner.adam_state()
+    assert_close(st["exp_avg"].cpu().numpy(), fx["exp_avg"], "tc exp_avg", atol=1e-7)
+    assert_close(st["exp_avg_sq"].cpu().numpy(), fx["exp_avg_sq"], "tc exp_avg_sq", atol=1e-9)
+    assert_close(st["max_exp_avg_sq"].cpu().numpy(), fx["max_exp_avg_sq"], "tc max_exp_avg_sq", atol=1e-9)
+
+
+def test_learner_group_equals_individual_simt_learners():
+    """B200LearnerGroup (one launch, one SM per learner, tensor cores) vs the same learners trained one
+    by one with the fp32 SIMT kernel: identical index streams, parameters within 1e-4; dynamic action
+    sets and obs < 128 included."""
+    pearl_b200, _, _, _, make_transitions = _imports()
+    obs, A, B, n, rounds, L = 40, 8, 128, 2000, 25, 5
+    groups = {}
+    for engine in ("simt", "tc"):
+        learners, bufs = [], []
+        for i in range(L):
+            d = make_transitions(n, obs, A, seed=300 + i, dynamic=(i % 2 == 1))
+            buf = pearl_b200.B200ReplayBuffer(n, rng="device", dynamic_action_space=True)
+            kw = {}
+            if i % 2 == 1:
+                kw = dict(next_available_ids=torch.from_numpy(d["next_avail_ids"].astype(np.uint8)),
+                          next_available_count=torch.from_numpy(d["next_avail_n"].astype(np.int32)))
+            buf.push_batch(*(torch.from_numpy(d[k]) for k in ("state", "action", "reward", "next_state", "terminated", "truncated")),
+                           max_number_actions=A, **kw)
+            buf.seed(900 + i)
+            torch.manual_seed(40 + i)
+            learners.append(pearl_b200.B200DeepQLearning(
+                state_dim=obs, action_space=_Space(A), hidden_dims=[64, 64], training_rounds=rounds, batch_size=B,
+                target_update_freq=4, soft_update_tau=0.5,
+                action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(A), engine=engine).to("cuda"))
+            bufs.append(buf)
+        if engine == "tc":
+            reps = pearl_b200.B200LearnerGroup(learners, bufs).learn()
+        else:
+            reps = [l.learn(b) for l, b in zip(learners, bufs)]
+        groups[engine] = (learners, bufs, reps)
+    for i in range(L):
+        ls, lt = groups["simt"][0][i], groups["tc"][0][i]
+        assert np.array_equal(groups["simt"][1][i].get_rng_state(), groups["tc"][1][i].get_rng_state())
+        assert_close(np.asarray(groups["tc"][2][i]["loss"]), np.asarray(groups["simt"][2][i]["loss"]), f"group loss {i}")
+        assert_close(lt.flat_parameters.cpu().numpy(), ls.flat_parameters.cpu().numpy(), f"group params {i}")
+        assert_close(lt.flat_target_parameters.cpu().numpy(), ls.flat_target_parameters.cpu().numpy(), f"group target {i}")
