@@ -64,7 +64,13 @@ struct TcArgs {
     Dims d;
     int B, rounds, freq;
     float decay, omb1, beta2, omb2, eps, gamma, tau, omtau, inv_b2;
+    long long *prof;   // optional [rounds][16] SM-clock stamps of CTA 0
 };
+
+#define TC_STAMP(idx)                                                                          \
+    do {                                                                                       \
+        if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[(size_t)round * 16 + (idx)] = clock64(); \
+    } while (0)
 
 struct Misc {
     float watb[16][HID];     // W1[:, obs + a] + b1 of the network being evaluated
@@ -91,36 +97,169 @@ __device__ __forceinline__ void st_split4(float *hi_base, float *lo_base, int id
     *reinterpret_cast<float4 *>(lo_base + idx) = l;
 }
 
-// weights of one network -> UMMA B-operand tiles + the small fp32 vectors
+// weights of one network -> UMMA B-operand tiles + the small fp32 vectors.  All global loads of a
+// thread are issued before the first dependent use (one L2 round trip, not one per element).
 __device__ void load_weights(const float *__restrict__ net, const Dims &d, char *smem, Misc &mi, bool with_w2t) {
     const int tid = threadIdx.x;
     float *w1hi = reinterpret_cast<float *>(smem + REG1), *w1lo = reinterpret_cast<float *>(smem + REG1 + HALF);
-    for (int e = tid; e < HID * d.obs; e += NTH) {           // W1[:, :obs]  -> tile [64 n][obs k]
-        const int n = e / d.obs, k = e - n * d.obs;
-        float hi, lo;
-        umma::split_tf32(__ldcg(net + d.oW1 + (size_t)n * d.D + k), hi, lo);
-        const int idx = umma::tile_index(n, k, d.obs);
-        w1hi[idx] = hi; w1lo[idx] = lo;
-    }
     float *w2hi = reinterpret_cast<float *>(smem + REG3), *w2lo = w2hi + 4096;
     float *w2thi = w2hi + 8192, *w2tlo = w2hi + 12288;
-    for (int e = tid; e < HID * HID; e += NTH) {             // W2 -> tile [64 j][64 k]; W2^T -> tile [64 k][64 j]
-        const int j = e >> 6, k = e & 63;
-        float hi, lo;
-        umma::split_tf32(__ldcg(net + d.oW2 + e), hi, lo);
-        const int idx = umma::tile_index(j, k, HID);
-        w2hi[idx] = hi; w2lo[idx] = lo;
-        if (with_w2t) {
-            const int it = umma::tile_index(k, j, HID);
-            w2thi[it] = hi; w2tlo[it] = lo;
+    const bool vec = ((d.D & 3) == 0) && ((reinterpret_cast<uintptr_t>(net) & 15) == 0);
+    if (vec) {
+        // A warp covers 8 tile rows x 4 chunks (lane = row%8 + 8*chunk): its 16-byte shared stores fall in
+        // 8 distinct bank groups per quarter-warp, and each row's 4 chunks are 64 contiguous global bytes.
+        const int lane = tid & 31, warp = tid >> 5, rl = lane & 7, cl = lane >> 3;
+        const int cgroups = (d.obs + 15) >> 4;                    // groups of 4 chunks along K (last may be partial)
+        const int items = (HID / 8) * cgroups;                    // W1[:, :obs] -> tile [64 n][obs k]
+        for (int it0 = warp; it0 < items; it0 += 8 * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int it = it0 + u * 8;
+                if (it < items) {
+                    const int n = (it / cgroups) * 8 + rl, k = ((it % cgroups) * 4 + cl) * 4;
+                    if (k < d.obs) v[u] = __ldcg(reinterpret_cast<const float4 *>(net + d.oW1 + (size_t)n * d.D + k));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int it = it0 + u * 8;
+                if (it < items) {
+                    const int n = (it / cgroups) * 8 + rl, k = ((it % cgroups) * 4 + cl) * 4;
+                    if (k < d.obs) st_split4(w1hi, w1lo, umma::tile_index(n, k, d.obs), v[u]);
+                }
+            }
+        }
+        float4 v2[4];                                             // W2: (64/8) x (16/4) = 32 warp items, 4 per warp
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int it = warp + u * 8, j = (it >> 2) * 8 + rl, k = ((it & 3) * 4 + cl) * 4;
+            v2[u] = __ldcg(reinterpret_cast<const float4 *>(net + d.oW2 + j * HID + k));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int it = warp + u * 8, j = (it >> 2) * 8 + rl, k = ((it & 3) * 4 + cl) * 4;
+            float4 hi, lo;
+            umma::split_tf32(v2[u].x, hi.x, lo.x); umma::split_tf32(v2[u].y, hi.y, lo.y);
+            umma::split_tf32(v2[u].z, hi.z, lo.z); umma::split_tf32(v2[u].w, hi.w, lo.w);
+            const int idx = umma::tile_index(j, k, HID);
+            *reinterpret_cast<float4 *>(w2hi + idx) = hi;
+            *reinterpret_cast<float4 *>(w2lo + idx) = lo;
+            if (with_w2t) {                                       // W2^T -> tile [64 k][64 j]
+                const float hh[4] = {hi.x, hi.y, hi.z, hi.w}, ll[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int it2 = umma::tile_index(k + c, j, HID);
+                    w2thi[it2] = hh[c]; w2tlo[it2] = ll[c];
+                }
+            }
+        }
+    } else {
+        for (int e0 = tid; e0 < HID * d.obs; e0 += NTH * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int e = e0 + u * NTH;
+                if (e < HID * d.obs) { const int n = e / d.obs, k = e - n * d.obs; v[u] = __ldcg(net + d.oW1 + (size_t)n * d.D + k); }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int e = e0 + u * NTH;
+                if (e < HID * d.obs) {
+                    const int n = e / d.obs, k = e - n * d.obs;
+                    float hi, lo;
+                    umma::split_tf32(v[u], hi, lo);
+                    const int idx = umma::tile_index(n, k, d.obs);
+                    w1hi[idx] = hi; w1lo[idx] = lo;
+                }
+            }
+        }
+        for (int e0 = tid; e0 < HID * HID; e0 += NTH * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldcg(net + d.oW2 + e0 + u * NTH);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int e = e0 + u * NTH, j = e >> 6, k = e & 63;
+                float hi, lo;
+                umma::split_tf32(v[u], hi, lo);
+                const int idx = umma::tile_index(j, k, HID);
+                w2hi[idx] = hi; w2lo[idx] = lo;
+                if (with_w2t) { const int it = umma::tile_index(k, j, HID); w2thi[it] = hi; w2tlo[it] = lo; }
+            }
         }
     }
-    for (int e = tid; e < d.A * HID; e += NTH) {
-        const int j = e / d.A, a = e - j * d.A;
-        mi.watb[a][j] = __ldcg(net + d.oW1 + (size_t)j * d.D + d.obs + a) + __ldcg(net + d.ob1 + j);
+    {
+        float wa[4], bb[4];                                       // A * 64 <= 1024 elements: <= 4 per thread
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = tid + u * NTH;
+            if (e < d.A * HID) {
+                const int j = e / d.A, a = e - j * d.A;
+                wa[u] = __ldcg(net + d.oW1 + (size_t)j * d.D + d.obs + a);
+                bb[u] = __ldcg(net + d.ob1 + j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = tid + u * NTH;
+            if (e < d.A * HID) { const int j = e / d.A, a = e - j * d.A; mi.watb[a][j] = wa[u] + bb[u]; }
+        }
     }
     if (tid < HID) { mi.b2[tid] = __ldcg(net + d.ob2 + tid); mi.w3[tid] = __ldcg(net + d.oW3 + tid); }
     if (tid == 0) mi.b3 = __ldcg(net + d.ob3);
+}
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+struct AdamScalarsTc : AdamScalars { float inv_bc2_sqrt; };
+
+// AdamW on `count` (multiple of 16 or smaller tail) consecutive parameters starting at index i0 with
+// gradients g[]: all loads of a 16-parameter batch first, then the arithmetic, then the stores.
+__device__ __forceinline__ void adamw_run(const TcLearner &L, int i0, int count, const float *g, const AdamScalarsTc &hs) {
+    const bool vec = (i0 & 3) == 0;
+    for (int b0 = 0; b0 < count; b0 += 16) {
+        if (vec && b0 + 16 <= count) {
+            float4 w4[4], m4[4], v4[4], x4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                w4[u] = __ldcg(reinterpret_cast<const float4 *>(L.w + i0 + b0) + u);
+                m4[u] = __ldcg(reinterpret_cast<const float4 *>(L.m + i0 + b0) + u);
+                v4[u] = __ldcg(reinterpret_cast<const float4 *>(L.v + i0 + b0) + u);
+                x4[u] = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i0 + b0) + u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float *wp = reinterpret_cast<float *>(&w4[u]), *mp = reinterpret_cast<float *>(&m4[u]);
+                float *vp = reinterpret_cast<float *>(&v4[u]), *xp = reinterpret_cast<float *>(&x4[u]);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float gg = g[b0 + 4 * u + c];
+                    float p = __fmul_rn(wp[c], hs.decay);
+                    float mm = fmaf(hs.omb1, gg - mp[c], mp[c]);
+                    float vv = __fadd_rn(__fmul_rn(vp[c], hs.beta2), __fmul_rn(__fmul_rn(hs.omb2, gg), gg));
+                    const float vm = fmaxf(xp[c], vv);
+                    // one SM updates all 13.5k parameters: MUFU sqrt / divide (<= 2 ulp) instead of
+                    // the IEEE software sequences; well inside the 1e-4 parity budget
+                    const float denom = __fadd_rn(__fmul_rn(fast_sqrt(vm), hs.inv_bc2_sqrt), hs.eps);
+                    p = __fadd_rn(p, __fdividef(__fmul_rn(-hs.step_size, mm), denom));
+                    wp[c] = p; mp[c] = mm; vp[c] = vv; xp[c] = vm;
+                }
+                reinterpret_cast<float4 *>(L.w + i0 + b0)[u] = w4[u];
+                reinterpret_cast<float4 *>(L.m + i0 + b0)[u] = m4[u];
+                reinterpret_cast<float4 *>(L.v + i0 + b0)[u] = v4[u];
+                reinterpret_cast<float4 *>(L.vmax + i0 + b0)[u] = x4[u];
+            }
+        } else {
+            for (int c = b0; c < count && c < b0 + 16; c++) {
+                const int i = i0 + c;
+                adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[c], hs);
+            }
+        }
+    }
 }
 
 // 128 rows x 64 columns [kc*64, kc*64+64) of state / next_state -> A tile (hi/lo) in region 2
@@ -164,6 +303,22 @@ __device__ void layer1_all_tiles(const TcArgs &a, const TcLearner &L, Misc &mi, 
         }
 }
 
+// v[c] = this lane's (row's) value of column c; returns, in lane c, the sum of column c over the warp's
+// 32 rows: reduce-scatter butterfly, 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float *v, int lane) {
+#pragma unroll
+    for (int n = 16; n >= 1; n >>= 1) {
+        const bool up = (lane & n) != 0;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            const float send = up ? v[i] : v[i + n];
+            const float keep = up ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return v[0];
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -192,6 +347,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
 
     for (int round = 0; round < a.rounds; round++) {
+        TC_STAMP(0);
         // ---- per-round row scalars + L2 prefetch of the NEXT round's transitions
         if (tid < a.B) {
             const int slot = L.slots[(size_t)round * a.B + tid];
@@ -214,9 +370,12 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         __syncthreads();
 
         // ================= phase T: y = max_a' Q_target(s', a') * gamma * (1 - term) + r =================
+        TC_STAMP(1);
         load_weights(L.wt, d, smem, mi, false);
         __syncthreads();
+        TC_STAMP(2);
         layer1_all_tiles(a, L, mi, smem, a.lay.off_next_state, tm, par0);
+        TC_STAMP(3);
         {
             // group g = h: own A buffer (g=0: region 2, g=1: region 1 — W1s is no longer needed), own accumulator
             float *ahi = reinterpret_cast<float *>(smem + (h ? REG1 : REG2)), *alo = ahi + HALF / 4;
@@ -259,7 +418,14 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     umma::tmem_ld32(tlane + acc_col + 32, acc + 32);
                     float q = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 64; c++) q = fmaf(mi.w3[c], fmaxf(acc[c] + mi.b2[c], 0.f), q);
+                    for (int c4 = 0; c4 < 16; c4++) {
+                        const float4 w3v = *reinterpret_cast<const float4 *>(&mi.w3[4 * c4]);
+                        const float4 b2v = *reinterpret_cast<const float4 *>(&mi.b2[4 * c4]);
+                        q = fmaf(w3v.x, fmaxf(acc[4 * c4 + 0] + b2v.x, 0.f), q);
+                        q = fmaf(w3v.y, fmaxf(acc[4 * c4 + 1] + b2v.y, 0.f), q);
+                        q = fmaf(w3v.z, fmaxf(acc[4 * c4 + 2] + b2v.z, 0.f), q);
+                        q = fmaf(w3v.w, fmaxf(acc[4 * c4 + 3] + b2v.w, 0.f), q);
+                    }
                     q += mi.b3;
                     if (act >= cnt) q = -INFINITY;   // next_state_action_values[mask] = -inf
                     best = fmaxf(best, q);
@@ -276,9 +442,12 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         }
 
         // ================= phase O: online forward, loss, backward =================
+        TC_STAMP(4);
         load_weights(L.w, d, smem, mi, true);
         __syncthreads();
+        TC_STAMP(5);
         layer1_all_tiles(a, L, mi, smem, a.lay.off_state, tm, par0);
+        TC_STAMP(6);
         float dw3_acc = 0.f, mae_acc = 0.f, db3_acc = 0.f;
         const umma::Tile W2_hi = umma::make_tile(smem + REG3, 64, 128), W2_lo = umma::make_tile(smem + REG3 + 16384, 64, 128);
         const umma::Tile W2T_hi = umma::make_tile(smem + REG3 + 32768, 64, 128), W2T_lo = umma::make_tile(smem + REG3 + 49152, 64, 128);
@@ -326,10 +495,11 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 db3_acc += dq;
             }
             // dW3[c0 + c] += sum_rows dq * h2 : reduce over this warp's 32 rows, lane c keeps column c
+            {
+                float cs[32];
 #pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const float s = warp_sum(dq * z[c]);
-                if (lane == c) dw3_acc += s;
+                for (int c = 0; c < 32; c++) cs[c] = dq * z[c];
+                dw3_acc += warp_colsum32(cs, lane);   // lane c receives the sum of column c over the 32 rows
             }
 #pragma unroll
             for (int c = 0; c < 32; c++) z[c] = (z[c] > 0.f) ? dq * mi.w3[c0 + c] : 0.f;   // dZ2
@@ -350,6 +520,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             umma::fence_after_thread_sync();
             float dz1[32];
             umma::tmem_ld32(tlane + TM_ACC1 + c0, dz1);
+            if (t == 0) TC_STAMP(7);
 #pragma unroll
             for (int c = 0; c < 32; c++) dz1[c] = (h1[c] > 0.f) ? dz1[c] : 0.f;
 
@@ -433,6 +604,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             }
         }
 
+        TC_STAMP(8);
         // ================= AdamW (gradients straight from TMEM; M = 64 rows live in lanes 32q + (0..15)) ==========
         mi.redw[warp][lane] = dw3_acc;
         if (lane == 0) { mi.redmae[warp] = 0.f; mi.reddb3[warp] = 0.f; }
@@ -445,30 +617,21 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         umma::fence_after_thread_sync();
         {
             const float2 sc = L.scal[round];
-            const AdamScalars hs{a.decay, a.omb1, a.beta2, a.omb2, a.eps, sc.x, sc.y};
+            AdamScalarsTc hs;
+            hs.decay = a.decay; hs.omb1 = a.omb1; hs.beta2 = a.beta2; hs.omb2 = a.omb2; hs.eps = a.eps;
+            hs.step_size = sc.x; hs.bc2_sqrt = sc.y; hs.inv_bc2_sqrt = 1.0f / sc.y;
             const int j = (warp & 3) * 16 + (lane & 15);   // output unit handled by this lane (lanes >= 16 idle)
             const bool live = lane < 16;
             float g[32];
             // W2[j][h*32 .. +32)
             umma::tmem_ld32(tlane + TM_DW2 + h * 32, g);
-            if (live)
-#pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const int i = d.oW2 + j * HID + h * 32 + c;
-                    adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[c], hs);
-                }
+            if (live) adamw_run(L, d.oW2 + j * HID + h * 32, 32, g, hs);
             // W1[j][k], state columns: half h covers [h*64, h*64+64)
             for (int cc = 0; cc < 2; cc++) {
                 const int kbase = h * 64 + cc * 32;
                 if (kbase < d.obs) {   // warp-uniform
                     umma::tmem_ld32(tlane + TM_DW1 + kbase, g);
-                    if (live)
-#pragma unroll
-                        for (int c = 0; c < 32; c++)
-                            if (kbase + c < d.obs) {
-                                const int i = d.oW1 + j * d.D + kbase + c;
-                                adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[c], hs);
-                            }
+                    if (live) adamw_run(L, d.oW1 + j * d.D + kbase, min(32, d.obs - kbase), g, hs);
                 }
             }
             // biases and the action columns of W1 from the E products
@@ -478,12 +641,9 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     const int i = d.ob2 + j;
                     adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[0], hs);
                 } else {
-                    int i = d.ob1 + j;
+                    const int i = d.ob1 + j;
                     adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[0], hs);
-                    for (int k = 0; k < d.A; k++) {
-                        i = d.oW1 + j * d.D + d.obs + k;
-                        adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[1 + k], hs);
-                    }
+                    adamw_run(L, d.oW1 + j * d.D + d.obs, d.A, g + 1, hs);
                 }
             }
             if (tid < HID) {   // W3: sum the four row-quarter partials of this column in fixed order
@@ -503,6 +663,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         umma::fence_before_thread_sync();
         __syncthreads();
         umma::fence_after_thread_sync();
+        TC_STAMP(9);
     }
     if (warp == 0) umma::tmem_dealloc(tm, 512);
 }
@@ -613,6 +774,7 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
     a.tau = (float)c.tau;
     a.omtau = (float)(1.0 - c.tau);
     a.inv_b2 = 2.0f / (float)batch;
+    a.prof = q0->prof;
     const size_t smem = MISC_OFF + sizeof(Misc);
     PRL_REQUIRE(smem <= (size_t)q0->max_smem, "tensor-core learner needs %zu B of shared memory", smem);
     PRL_CUDA(cudaFuncSetAttribute(k_dqn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -98,16 +98,20 @@ __device__ __forceinline__ int tile_index2(int r, int k, int K, int lbo) {
 __device__ __forceinline__ Tile make_tile(const void *p, int K, int lbo) { return Tile{smem_u32(p), lbo, (K >> 2) * lbo}; }
 
 // 3xTF32: D[M x N] (+)= A[M x K] * B[N x K]^T; issued by ONE thread.  *_exact: the operand is exactly
-// representable in TF32 (0/1 indicators), its lo tile is not needed.
+// representable in TF32 (0/1 indicators), its lo tile is not needed.  Descriptors are built once; a K
+// step of 8 only adds (2*lbo)>>4 to the 14-bit start-address field.
 __device__ __forceinline__ void gemm3(uint32_t tmem_d, Tile a_hi, Tile a_lo, Tile b_hi, Tile b_lo, int M, int N, int K,
                                       bool accumulate_first, bool a_exact = false, bool b_exact = false) {
     const uint32_t idesc = make_idesc_tf32(M, N);
+    uint64_t ah = a_hi.desc(0), al = a_lo.desc(0), bh = b_hi.desc(0), bl = b_lo.desc(0);
+    const uint64_t da = (uint64_t)((2 * a_hi.lbo) >> 4), db = (uint64_t)((2 * b_hi.lbo) >> 4);
     bool acc = accumulate_first;
     for (int ks = 0; ks < (K >> 3); ks++) {
-        if (!a_exact) { mma_tf32(tmem_d, a_lo.desc(ks), b_hi.desc(ks), idesc, acc); acc = true; }
-        if (!b_exact) { mma_tf32(tmem_d, a_hi.desc(ks), b_lo.desc(ks), idesc, acc); acc = true; }
-        mma_tf32(tmem_d, a_hi.desc(ks), b_hi.desc(ks), idesc, acc);
+        if (!a_exact) { mma_tf32(tmem_d, al, bh, idesc, acc); acc = true; }
+        if (!b_exact) { mma_tf32(tmem_d, ah, bl, idesc, acc); acc = true; }
+        mma_tf32(tmem_d, ah, bh, idesc, acc);
         acc = true;
+        ah += da; al += da; bh += db; bl += db;
     }
 }
 
