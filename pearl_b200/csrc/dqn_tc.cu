@@ -217,51 +217,19 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 }
 struct AdamScalarsTc : AdamScalars { float inv_bc2_sqrt; };
 
-// AdamW on `count` (multiple of 16 or smaller tail) consecutive parameters starting at index i0 with
-// gradients g[]: all loads of a 16-parameter batch first, then the arithmetic, then the stores.
-__device__ __forceinline__ void adamw_run(const TcLearner &L, int i0, int count, const float *g, const AdamScalarsTc &hs) {
-    const bool vec = (i0 & 3) == 0;
-    for (int b0 = 0; b0 < count; b0 += 16) {
-        if (vec && b0 + 16 <= count) {
-            float4 w4[4], m4[4], v4[4], x4[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                w4[u] = __ldcg(reinterpret_cast<const float4 *>(L.w + i0 + b0) + u);
-                m4[u] = __ldcg(reinterpret_cast<const float4 *>(L.m + i0 + b0) + u);
-                v4[u] = __ldcg(reinterpret_cast<const float4 *>(L.v + i0 + b0) + u);
-                x4[u] = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i0 + b0) + u);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                float *wp = reinterpret_cast<float *>(&w4[u]), *mp = reinterpret_cast<float *>(&m4[u]);
-                float *vp = reinterpret_cast<float *>(&v4[u]), *xp = reinterpret_cast<float *>(&x4[u]);
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const float gg = g[b0 + 4 * u + c];
-                    float p = __fmul_rn(wp[c], hs.decay);
-                    float mm = fmaf(hs.omb1, gg - mp[c], mp[c]);
-                    float vv = __fadd_rn(__fmul_rn(vp[c], hs.beta2), __fmul_rn(__fmul_rn(hs.omb2, gg), gg));
-                    const float vm = fmaxf(xp[c], vv);
-                    // one SM updates all 13.5k parameters: MUFU sqrt / divide (<= 2 ulp) instead of
-                    // the IEEE software sequences; well inside the 1e-4 parity budget
-                    const float denom = __fadd_rn(__fmul_rn(fast_sqrt(vm), hs.inv_bc2_sqrt), hs.eps);
-                    p = __fadd_rn(p, __fdividef(__fmul_rn(-hs.step_size, mm), denom));
-                    wp[c] = p; mp[c] = mm; vp[c] = vv; xp[c] = vm;
-                }
-                reinterpret_cast<float4 *>(L.w + i0 + b0)[u] = w4[u];
-                reinterpret_cast<float4 *>(L.m + i0 + b0)[u] = m4[u];
-                reinterpret_cast<float4 *>(L.v + i0 + b0)[u] = v4[u];
-                reinterpret_cast<float4 *>(L.vmax + i0 + b0)[u] = x4[u];
-            }
-        } else {
-            for (int c = b0; c < count && c < b0 + 16; c++) {
-                const int i = i0 + c;
-                adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[c], hs);
-            }
-        }
-    }
+// AdamW on parameters [i0, i0 + valid) with gradients g[OFF .. OFF + COUNT): COUNT is a compile-time
+// multiple of 16 so that g stays in registers; `valid` <= COUNT masks the tail.  Per 16-parameter batch:
+// all loads first (one L2 round trip), then arithmetic, then stores.
+__device__ __forceinline__ float adam_math(float w, float &m, float &v, float &x, float g, const AdamScalarsTc &hs) {
+    float p = __fmul_rn(w, hs.decay);
+    m = fmaf(hs.omb1, g - m, m);
+    v = __fadd_rn(__fmul_rn(v, hs.beta2), __fmul_rn(__fmul_rn(hs.omb2, g), g));
+    x = fmaxf(x, v);
+    // one SM updates all 13.5k parameters: MUFU sqrt / divide (<= 2 ulp) instead of the IEEE
+    // software sequences; well inside the 1e-4 parity budget
+    const float denom = __fadd_rn(__fmul_rn(fast_sqrt(x), hs.inv_bc2_sqrt), hs.eps);
+    return __fadd_rn(p, __fdividef(__fmul_rn(-hs.step_size, m), denom));
 }
-
 // 128 rows x 64 columns [kc*64, kc*64+64) of state / next_state -> A tile (hi/lo) in region 2
 __device__ void build_rows_chunk(const TcArgs &a, const TcLearner &L, const Misc &mi, char *smem, int field_off, int tile,
                                  int kc) {
@@ -616,48 +584,105 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         __syncthreads();
         umma::fence_after_thread_sync();
         {
-            const float2 sc = L.scal[round];
-            AdamScalarsTc hs;
-            hs.decay = a.decay; hs.omb1 = a.omb1; hs.beta2 = a.beta2; hs.omb2 = a.omb2; hs.eps = a.eps;
-            hs.step_size = sc.x; hs.bc2_sqrt = sc.y; hs.inv_bc2_sqrt = 1.0f / sc.y;
-            const int j = (warp & 3) * 16 + (lane & 15);   // output unit handled by this lane (lanes >= 16 idle)
+            // 1) gradients TMEM -> shared staging (arena is free: every product has been waited for).  Row
+            //    pitches are odd, so the 16 live lanes of a warp (rows 16q .. 16q+15) hit distinct banks.
+            float *gs_w2 = reinterpret_cast<float *>(smem);            // [64][65]
+            const int pitch1 = d.D | 1;
+            float *gs_w1 = gs_w2 + 64 * 65;                            // [64][pitch1]   (state cols, then action cols)
+            float *gs_b1 = gs_w1 + 64 * pitch1, *gs_b2 = gs_b1 + 64;
+            const int j = (warp & 3) * 16 + (lane & 15);               // M = 64 lane map: lanes >= 16 hold nothing
             const bool live = lane < 16;
             float g[32];
-            // W2[j][h*32 .. +32)
             umma::tmem_ld32(tlane + TM_DW2 + h * 32, g);
-            if (live) adamw_run(L, d.oW2 + j * HID + h * 32, 32, g, hs);
-            // W1[j][k], state columns: half h covers [h*64, h*64+64)
+            if (live)
+#pragma unroll
+                for (int c = 0; c < 32; c++) gs_w2[j * 65 + h * 32 + c] = g[c];
             for (int cc = 0; cc < 2; cc++) {
                 const int kbase = h * 64 + cc * 32;
                 if (kbase < d.obs) {   // warp-uniform
                     umma::tmem_ld32(tlane + TM_DW1 + kbase, g);
-                    if (live) adamw_run(L, d.oW1 + j * d.D + kbase, min(32, d.obs - kbase), g, hs);
+                    if (live)
+#pragma unroll
+                        for (int c = 0; c < 32; c++)
+                            if (kbase + c < d.obs) gs_w1[j * pitch1 + kbase + c] = g[c];
                 }
             }
-            // biases and the action columns of W1 from the E products
             umma::tmem_ld32(tlane + (h ? TM_DE1 : TM_DE2), g);
             if (live) {
-                if (h == 0) {
-                    const int i = d.ob2 + j;
-                    adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[0], hs);
-                } else {
-                    const int i = d.ob1 + j;
-                    adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, g[0], hs);
-                    adamw_run(L, d.oW1 + j * d.D + d.obs, d.A, g + 1, hs);
+                if (h == 0) gs_b2[j] = g[0];
+                else {
+                    gs_b1[j] = g[0];
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        if (k < d.A) gs_w1[j * pitch1 + d.obs + k] = g[1 + k];
                 }
             }
-            if (tid < HID) {   // W3: sum the four row-quarter partials of this column in fixed order
-                const int hh = tid >> 5, c = tid & 31;
-                const float gw = ((mi.redw[hh * 4 + 0][c] + mi.redw[hh * 4 + 1][c]) + mi.redw[hh * 4 + 2][c]) + mi.redw[hh * 4 + 3][c];
-                const int i = d.oW3 + tid;
-                adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, gw, hs);
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            // 2) AdamW over the flat parameter vector, all 256 threads, fully coalesced 16-byte accesses
+            const float2 sc = L.scal[round];
+            AdamScalarsTc hs;
+            hs.decay = a.decay; hs.omb1 = a.omb1; hs.beta2 = a.beta2; hs.omb2 = a.omb2; hs.eps = a.eps;
+            hs.step_size = sc.x; hs.bc2_sqrt = sc.y; hs.inv_bc2_sqrt = 1.0f / sc.y;
+            const bool vecD = ((d.D & 3) == 0) && ((d.oW2 & 3) == 0);
+            if (vecD) {
+                const int D4 = d.D >> 2;
+                for (int row = warp; row < HID; row += 8)
+                    for (int c4 = lane; c4 < D4; c4 += 32) {
+                        const int i = d.oW1 + row * d.D + c4 * 4;
+                        const float *gp = gs_w1 + row * pitch1 + c4 * 4;
+                        float4 w4 = __ldcg(reinterpret_cast<const float4 *>(L.w + i)), m4 = __ldcg(reinterpret_cast<const float4 *>(L.m + i));
+                        float4 v4 = __ldcg(reinterpret_cast<const float4 *>(L.v + i)), x4 = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i));
+                        w4.x = adam_math(w4.x, m4.x, v4.x, x4.x, gp[0], hs); w4.y = adam_math(w4.y, m4.y, v4.y, x4.y, gp[1], hs);
+                        w4.z = adam_math(w4.z, m4.z, v4.z, x4.z, gp[2], hs); w4.w = adam_math(w4.w, m4.w, v4.w, x4.w, gp[3], hs);
+                        *reinterpret_cast<float4 *>(L.w + i) = w4; *reinterpret_cast<float4 *>(L.m + i) = m4;
+                        *reinterpret_cast<float4 *>(L.v + i) = v4; *reinterpret_cast<float4 *>(L.vmax + i) = x4;
+                    }
+                for (int q4 = tid; q4 < HID * HID / 4; q4 += NTH) {   // W2: 16 float4 per row
+                    const int row = q4 >> 4, c = (q4 & 15) * 4, i = d.oW2 + q4 * 4;
+                    const float *gp = gs_w2 + row * 65 + c;
+                    float4 w4 = __ldcg(reinterpret_cast<const float4 *>(L.w + i)), m4 = __ldcg(reinterpret_cast<const float4 *>(L.m + i));
+                    float4 v4 = __ldcg(reinterpret_cast<const float4 *>(L.v + i)), x4 = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i));
+                    w4.x = adam_math(w4.x, m4.x, v4.x, x4.x, gp[0], hs); w4.y = adam_math(w4.y, m4.y, v4.y, x4.y, gp[1], hs);
+                    w4.z = adam_math(w4.z, m4.z, v4.z, x4.z, gp[2], hs); w4.w = adam_math(w4.w, m4.w, v4.w, x4.w, gp[3], hs);
+                    *reinterpret_cast<float4 *>(L.w + i) = w4; *reinterpret_cast<float4 *>(L.m + i) = m4;
+                    *reinterpret_cast<float4 *>(L.v + i) = v4; *reinterpret_cast<float4 *>(L.vmax + i) = x4;
+                }
+            } else {
+                for (int row = warp; row < HID; row += 8)
+                    for (int c = lane; c < d.D; c += 32) {
+                        const int i = d.oW1 + row * d.D + c;
+                        float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
+                        L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gs_w1[row * pitch1 + c], hs);
+                        L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
+                    }
+                for (int e = tid; e < HID * HID; e += NTH) {
+                    const int i = d.oW2 + e;
+                    float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
+                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gs_w2[(e >> 6) * 65 + (e & 63)], hs);
+                    L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
+                }
             }
-            if (tid == HID) {
-                const float gb = ((mi.reddb3[0] + mi.reddb3[1]) + mi.reddb3[2]) + mi.reddb3[3];
-                const int i = d.ob3;
-                adamw_step(L.w + i, L.m + i, L.v + i, L.vmax + i, gb, hs);
-                const float e = ((mi.redmae[0] + mi.redmae[1]) + mi.redmae[2]) + mi.redmae[3];
-                L.out_mae[round] = e / (float)a.B;   // reported "loss": mean |q - y|
+            {   // b1 | b2 | W3 | b3: 64 + 64 + 64 + 1 parameters, one per thread
+                int i = -1;
+                float gg = 0.f;
+                if (tid < 64) { i = d.ob1 + tid; gg = gs_b1[tid]; }
+                else if (tid < 128) { i = d.ob2 + tid - 64; gg = gs_b2[tid - 64]; }
+                else if (tid < 192) {   // W3: sum the four row-quarter partials of this column in fixed order
+                    const int col = tid - 128, hh = col >> 5, c = col & 31;
+                    gg = ((mi.redw[hh * 4 + 0][c] + mi.redw[hh * 4 + 1][c]) + mi.redw[hh * 4 + 2][c]) + mi.redw[hh * 4 + 3][c];
+                    i = d.oW3 + col;
+                } else if (tid == 192) {
+                    gg = ((mi.reddb3[0] + mi.reddb3[1]) + mi.reddb3[2]) + mi.reddb3[3];
+                    i = d.ob3;
+                    const float e = ((mi.redmae[0] + mi.redmae[1]) + mi.redmae[2]) + mi.redmae[3];
+                    L.out_mae[round] = e / (float)a.B;   // reported "loss": mean |q - y|
+                }
+                if (i >= 0) {
+                    float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
+                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gg, hs);
+                    L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
+                }
             }
         }
         umma::fence_before_thread_sync();
