@@ -282,6 +282,9 @@ int prl_dqn_last_kernel_ms(prl_dqn *dqn, float *ms);
  * the 3xTF32 split the learner uses for fp32 parity (passes = 3).  Test infrastructure hook. */
 int prl_test_umma_gemm(const float *a_dev, const float *b_dev, float *d_dev, int n, int k, int passes,
                        void *stream);
+/* Same product with the A operand in tensor memory (written by tcgen05.st), B in shared memory;
+ * k <= 64; reps > 1 prints a throughput probe. */
+int prl_test_umma_gemm_ts(const float *a_dev, const float *b_dev, float *d_dev, int n, int k, int reps, void *stream);
 /* General self-test: D[m][n] = A[m][k] * B[n][k]^T with m in {64,128} and a free operand chunk pitch
  * `lbo` (128 dense / 144 transposed-write friendly, see csrc/umma.cuh).  draw_dev receives the raw
  * accumulator: 128 TMEM lanes x n columns (for m = 64, row i is lane 32*(i/16) + i%16). */

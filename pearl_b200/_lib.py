@@ -78,6 +78,7 @@ _SIGNATURES = {
     "prl_dqn_set_profile": (C.c_int, [_P, _P]),
     "prl_dqn_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "prl_test_umma_gemm": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "prl_test_umma_gemm_ts": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "prl_test_umma_gemm2": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "prl_dqn_last_launch_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                            C.POINTER(C.c_int32)]),

@@ -370,17 +370,21 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         v.z = fmaxf(t1[4 * c4 + 2] + wv.z, 0.f); v.w = fmaxf(t1[4 * c4 + 3] + wv.w, 0.f);
                         st_split4(ahi, alo, umma::tile_index(m, 4 * c4, 64), v);
                     }
+                    if (t == 0 && act == 2) TC_STAMP(10);
                     umma::fence_async_smem();
                     umma::fence_before_thread_sync();
                     group_sync(h);
+                    if (t == 0 && act == 2) TC_STAMP(11);
                     if (m == 0) {
                         umma::fence_after_thread_sync();
                         umma::gemm3(tm + acc_col, A_hi, A_lo, B_hi, B_lo, 128, HID, HID, false);
                         umma::mma_commit(&bar[1 + h]);
                     }
+                    if (t == 0 && act == 2) TC_STAMP(12);
                     umma::mbar_wait(&bar[1 + h], parg);
                     parg ^= 1;
                     umma::fence_after_thread_sync();
+                    if (t == 0 && act == 2) TC_STAMP(13);
                     float acc[64];
                     umma::tmem_ld32(tlane + acc_col, acc);
                     umma::tmem_ld32(tlane + acc_col + 32, acc + 32);
@@ -397,6 +401,8 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     q += mi.b3;
                     if (act >= cnt) q = -INFINITY;   // next_state_action_values[mask] = -inf
                     best = fmaxf(best, q);
+                    if (t == 0 && act == 2) TC_STAMP(14);
+                    if (t == 0 && act == 0) TC_STAMP(15);
                 }
                 mi.vmax2[h][m] = best;
                 umma::fence_before_thread_sync();

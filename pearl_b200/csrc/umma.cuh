@@ -66,6 +66,18 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint6
         : "memory");
 }
 
+// same with the A operand in tensor memory (lanes = rows, one 32-bit column per K element): no shared
+// memory traffic for A, which at N = 64 is what bounds the SS form (6 KB of operands per MMA at 128 B/clk)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                            bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
 // generic descriptor: explicit LBO / SBO (bytes)
 __device__ __forceinline__ uint64_t make_desc2(uint32_t smem_addr, int lbo_bytes, int sbo_bytes) {
     uint64_t d = 0;
@@ -112,6 +124,22 @@ __device__ __forceinline__ void gemm3(uint32_t tmem_d, Tile a_hi, Tile a_lo, Til
         mma_tf32(tmem_d, ah, bh, idesc, acc);
         acc = true;
         ah += da; al += da; bh += db; bl += db;
+    }
+}
+
+// 3xTF32 with A (hi / lo) in tensor memory: a_hi / a_lo are TMEM column addresses of [M lanes][K columns]
+__device__ __forceinline__ void gemm3_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, Tile b_hi, Tile b_lo, int M, int N,
+                                         int K, bool accumulate_first) {
+    const uint32_t idesc = make_idesc_tf32(M, N);
+    uint64_t bh = b_hi.desc(0), bl = b_lo.desc(0);
+    const uint64_t db = (uint64_t)((2 * b_hi.lbo) >> 4);
+    bool acc = accumulate_first;
+    for (int ks = 0; ks < (K >> 3); ks++) {
+        mma_tf32_ts(tmem_d, a_lo + ks * 8, bh, idesc, acc);
+        mma_tf32_ts(tmem_d, a_hi + ks * 8, bl, idesc, true);
+        mma_tf32_ts(tmem_d, a_hi + ks * 8, bh, idesc, true);
+        acc = true;
+        bh += db; bl += db;
     }
 }
 
@@ -188,5 +216,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+
+// registers -> tensor memory: this warp's 32 lanes (rows) x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+          "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+          "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+          "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
+          "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
+          "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+          "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
+          "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 }  // namespace umma

@@ -52,3 +52,21 @@ def test_umma_m64_and_padded_chunk_pitch(m, n, k, lbo):
     err = ((got.double() - want).abs() / scale).max().item()
     print(f"    M={m} N={n} K={k} lbo={lbo}: err {err:.3e}")
     assert err < 4e-6
+
+
+@pytest.mark.parametrize("n,k", [(64, 64), (64, 32), (128, 64), (32, 8)])
+def test_umma_a_operand_in_tensor_memory(n, k):
+    """TS form: A written to TMEM by tcgen05.st (no shared-memory traffic for A)."""
+    from pearl_b200 import _lib
+    lib = _lib.init(0)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn((128, k), generator=g, device="cuda")
+    B = torch.randn((n, k), generator=g, device="cuda")
+    d = torch.full((128, n), float("nan"), device="cuda")
+    _lib.check(lib.prl_test_umma_gemm_ts(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(d.data_ptr()), n, k, 1, None))
+    torch.cuda.synchronize()
+    want = A.double() @ B.double().T
+    scale = A.abs().double() @ B.abs().double().T
+    err = ((d.double() - want).abs() / scale).max().item()
+    print(f"    TS N={n} K={k}: err {err:.3e}")
+    assert err < 4e-6
