@@ -46,6 +46,9 @@ constexpr int TL = 144;              // chunk pitch of transposed tiles
 constexpr int AR_A_HI = 0, AR_A_LO = 18432, AR_B_HI = 36864, AR_B_LO = 73728, AR_E = 110592;
 // TMEM columns
 constexpr int TM_T1 = 0, TM_ACC0 = 128, TM_ACC1 = 192, TM_DW2 = 256, TM_DW1 = 320, TM_DE2 = 448, TM_DE1 = 480;
+// A operands held in tensor memory (TS products) while the weight-gradient accumulators are not live:
+// group g: hi at TM_A + 128 g, lo 64 columns further
+constexpr int TM_A = 256;
 
 struct TcLearner {            // one per CTA, in global memory
     const uint32_t *records;
@@ -230,45 +233,53 @@ __device__ __forceinline__ float adam_math(float w, float &m, float &v, float &x
     const float denom = __fadd_rn(__fmul_rn(fast_sqrt(x), hs.inv_bc2_sqrt), hs.eps);
     return __fadd_rn(p, __fdividef(__fmul_rn(-hs.step_size, m), denom));
 }
-// 128 rows x 64 columns [kc*64, kc*64+64) of state / next_state -> A tile (hi/lo) in region 2
-__device__ void build_rows_chunk(const TcArgs &a, const TcLearner &L, const Misc &mi, char *smem, int field_off, int tile,
-                                 int kc) {
-    const int m = threadIdx.x & 127, h = threadIdx.x >> 7;
-    float *hi = reinterpret_cast<float *>(smem + REG2), *lo = reinterpret_cast<float *>(smem + REG2 + HALF);
-    const int k0 = kc * 64 + h * 32;
-    const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[tile * 128 + m] * a.lay.record_words) +
-                       field_off + k0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k0 + 4 * i < a.d.obs) v = __ldg(reinterpret_cast<const float4 *>(src + 4 * i));
-        st_split4(hi, lo, umma::tile_index(m, h * 32 + 4 * i, 64), v);
-    }
-}
-
-// T1[tile] = X[tile rows] W1s^T for every row tile, X = state (online) or next_state (target)
+// T1[tile] = X[tile rows] W1s^T, X = state (online) or next_state (target).  The two 128-thread groups
+// take alternate row tiles; each thread streams its own row from global memory, splits it and writes it
+// straight into tensor memory (TS product: no shared-memory staging of A), 64 columns of K per pass.
 __device__ void layer1_all_tiles(const TcArgs &a, const TcLearner &L, Misc &mi, char *smem, int field_off, uint32_t tm,
-                                 uint32_t &par0) {
+                                 uint32_t tlane, uint32_t &parg) {
+    const int m = threadIdx.x & 127, g = threadIdx.x >> 7;
     const int ntiles = a.B >> 7;
-    const umma::Tile A_hi = umma::make_tile(smem + REG2, 64, 128), A_lo = umma::make_tile(smem + REG2 + HALF, 64, 128);
     const umma::Tile B_hi = umma::make_tile(smem + REG1, a.d.obs, 128), B_lo = umma::make_tile(smem + REG1 + HALF, a.d.obs, 128);
-    for (int t = 0; t < ntiles; t++)
+    const uint32_t a_hi = TM_A + 128 * g, a_lo = a_hi + 64;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
+    for (int t = g; t < ntiles; t += 2) {
+        const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[t * 128 + m] * a.lay.record_words) + field_off;
         for (int kc = 0; kc * 64 < a.d.obs; kc++) {
-            build_rows_chunk(a, L, mi, smem, field_off, t, kc);
-            umma::fence_async_smem();
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int k0 = kc * 64 + half * 32;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    v[i] = (k0 + 4 * i < a.d.obs) ? __ldg(reinterpret_cast<const float4 *>(src + k0 + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float hi[32], lo[32];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    umma::split_tf32(v[i].x, hi[4 * i + 0], lo[4 * i + 0]); umma::split_tf32(v[i].y, hi[4 * i + 1], lo[4 * i + 1]);
+                    umma::split_tf32(v[i].z, hi[4 * i + 2], lo[4 * i + 2]); umma::split_tf32(v[i].w, hi[4 * i + 3], lo[4 * i + 3]);
+                }
+                umma::tmem_st32(tlane + a_hi + half * 32, hi);
+                umma::tmem_st32(tlane + a_lo + half * 32, lo);
+            }
+            umma::tmem_st_wait();
             umma::fence_before_thread_sync();
-            __syncthreads();
-            if (threadIdx.x == 0) {
+            group_sync(g);
+            if (m == 0) {
                 umma::fence_after_thread_sync();
                 const int keff = min(64, a.d.obs - kc * 64);
-                umma::gemm3(tm + TM_T1 + t * 64, A_hi, A_lo, B_hi.shifted(kc * 2048), B_lo.shifted(kc * 2048), 128, HID, keff,
-                            kc > 0);
-                umma::mma_commit(reinterpret_cast<uint64_t *>(&mi.bar[0]));
+                umma::gemm3_ts(tm + TM_T1 + t * 64, tm + a_hi, tm + a_lo, B_hi.shifted(kc * 2048), B_lo.shifted(kc * 2048), 128, HID,
+                               keff, kc > 0);
+                umma::mma_commit(&bar[1 + g]);
             }
-            umma::mbar_wait(reinterpret_cast<uint64_t *>(&mi.bar[0]), par0);
-            par0 ^= 1;
+            umma::mbar_wait(&bar[1 + g], parg);
+            parg ^= 1;
             umma::fence_after_thread_sync();
         }
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
 }
 
 // v[c] = this lane's (row's) value of column c; returns, in lane c, the sum of column c over the warp's
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     umma::fence_after_thread_sync();
     const uint32_t tm = mi.tmem_base;
     const uint32_t tlane = tm + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
-    uint32_t par0 = 0, parg = 0, par3 = 0, par4 = 0, par5 = 0;        // mbarrier phase parities
+    uint32_t parg = 0, par3 = 0, par4 = 0, par5 = 0;                  // mbarrier phase parities
     uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
 
     for (int round = 0; round < a.rounds; round++) {
@@ -342,15 +353,13 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         load_weights(L.wt, d, smem, mi, false);
         __syncthreads();
         TC_STAMP(2);
-        layer1_all_tiles(a, L, mi, smem, a.lay.off_next_state, tm, par0);
+        layer1_all_tiles(a, L, mi, smem, a.lay.off_next_state, tm, tlane, parg);
         TC_STAMP(3);
         {
-            // group g = h: own A buffer (g=0: region 2, g=1: region 1 — W1s is no longer needed), own accumulator
-            float *ahi = reinterpret_cast<float *>(smem + (h ? REG1 : REG2)), *alo = ahi + HALF / 4;
-            const umma::Tile A_hi = umma::make_tile(ahi, 64, 128), A_lo = umma::make_tile(alo, 64, 128);
+            // group g = h: own A operand in tensor memory and own accumulator; the two groups ping-pong
             const umma::Tile B_hi = umma::make_tile(smem + REG3, 64, 128), B_lo = umma::make_tile(smem + REG3 + 16384, 64, 128);
             const uint32_t acc_col = h ? TM_ACC1 : TM_ACC0;
-            __syncthreads();  // every thread is past layer 1: region 1 may be overwritten
+            const uint32_t a_hi = TM_A + 128 * h, a_lo = a_hi + 64;
             for (int t = 0; t < ntiles; t++) {
                 const int row = t * 128 + m;
                 float t1[64];
@@ -363,21 +372,28 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     int id = act;
                     if ((L.buf_flags & PRL_BUF_DYNAMIC_ACTIONS) && act < cnt) id = ids[act];
 #pragma unroll
-                    for (int c4 = 0; c4 < 16; c4++) {
-                        const float4 wv = *reinterpret_cast<const float4 *>(&mi.watb[id][4 * c4]);
-                        float4 v;
-                        v.x = fmaxf(t1[4 * c4 + 0] + wv.x, 0.f); v.y = fmaxf(t1[4 * c4 + 1] + wv.y, 0.f);
-                        v.z = fmaxf(t1[4 * c4 + 2] + wv.z, 0.f); v.w = fmaxf(t1[4 * c4 + 3] + wv.w, 0.f);
-                        st_split4(ahi, alo, umma::tile_index(m, 4 * c4, 64), v);
+                    for (int half = 0; half < 2; half++) {
+                        float hi[32], lo[32];
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; c4++) {
+                            const float4 wv = *reinterpret_cast<const float4 *>(&mi.watb[id][half * 32 + 4 * c4]);
+                            const int c = half * 32 + 4 * c4;
+                            umma::split_tf32(fmaxf(t1[c + 0] + wv.x, 0.f), hi[4 * c4 + 0], lo[4 * c4 + 0]);
+                            umma::split_tf32(fmaxf(t1[c + 1] + wv.y, 0.f), hi[4 * c4 + 1], lo[4 * c4 + 1]);
+                            umma::split_tf32(fmaxf(t1[c + 2] + wv.z, 0.f), hi[4 * c4 + 2], lo[4 * c4 + 2]);
+                            umma::split_tf32(fmaxf(t1[c + 3] + wv.w, 0.f), hi[4 * c4 + 3], lo[4 * c4 + 3]);
+                        }
+                        umma::tmem_st32(tlane + a_hi + half * 32, hi);
+                        umma::tmem_st32(tlane + a_lo + half * 32, lo);
                     }
+                    umma::tmem_st_wait();
                     if (t == 0 && act == 2) TC_STAMP(10);
-                    umma::fence_async_smem();
                     umma::fence_before_thread_sync();
                     group_sync(h);
                     if (t == 0 && act == 2) TC_STAMP(11);
                     if (m == 0) {
                         umma::fence_after_thread_sync();
-                        umma::gemm3(tm + acc_col, A_hi, A_lo, B_hi, B_lo, 128, HID, HID, false);
+                        umma::gemm3_ts(tm + acc_col, tm + a_hi, tm + a_lo, B_hi, B_lo, 128, HID, HID, false);
                         umma::mma_commit(&bar[1 + h]);
                     }
                     if (t == 0 && act == 2) TC_STAMP(12);
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         load_weights(L.w, d, smem, mi, true);
         __syncthreads();
         TC_STAMP(5);
-        layer1_all_tiles(a, L, mi, smem, a.lay.off_state, tm, par0);
+        layer1_all_tiles(a, L, mi, smem, a.lay.off_state, tm, tlane, parg);
         TC_STAMP(6);
         float dw3_acc = 0.f, mae_acc = 0.f, db3_acc = 0.f;
         const umma::Tile W2_hi = umma::make_tile(smem + REG3, 64, 128), W2_lo = umma::make_tile(smem + REG3 + 16384, 64, 128);
