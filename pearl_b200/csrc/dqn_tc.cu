@@ -90,6 +90,11 @@ struct Misc {
     uint32_t tmem_base;
 };
 
+__device__ __forceinline__ void cp_async16_zfill_tc(void *smem_dst, const void *gmem_src, int src_bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory"); }
 
 __device__ __forceinline__ void st_split4(float *hi_base, float *lo_base, int idx, float4 v) {
@@ -237,34 +242,48 @@ __device__ __forceinline__ float adam_math(float w, float &m, float &v, float &x
 // take alternate row tiles; each thread streams its own row from global memory, splits it and writes it
 // straight into tensor memory (TS product: no shared-memory staging of A), 64 columns of K per pass.
 __device__ void layer1_all_tiles(const TcArgs &a, const TcLearner &L, Misc &mi, char *smem, int field_off, uint32_t tm,
-                                 uint32_t tlane, uint32_t &parg) {
+                                 uint32_t tlane, uint32_t &parg, int round = 0, bool stamp = false) {
     const int m = threadIdx.x & 127, g = threadIdx.x >> 7;
     const int ntiles = a.B >> 7;
     const umma::Tile B_hi = umma::make_tile(smem + REG1, a.d.obs, 128), B_lo = umma::make_tile(smem + REG1 + HALF, a.d.obs, 128);
     const uint32_t a_hi = TM_A + 128 * g, a_lo = a_hi + 64;
     uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
+    // staging buffer of this group in region 2: [128 rows][64 floats], 16-byte chunk c of row r stored at
+    // chunk position c ^ (r & 7): rows arrive by coalesced 16-byte cp.async (16 lanes per row), and the
+    // row-owning thread reads its row back with conflict-free 128-bit loads.
+    float *sbuf = reinterpret_cast<float *>(smem + REG2 + g * 32768);
     for (int t = g; t < ntiles; t += 2) {
-        const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[t * 128 + m] * a.lay.record_words) + field_off;
         for (int kc = 0; kc * 64 < a.d.obs; kc++) {
+            if (stamp && kc == 1) TC_STAMP(10);
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int item = i * 128 + m, rr = item >> 4, c = item & 15, k = kc * 64 + c * 4;
+                const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[t * 128 + rr] * a.lay.record_words) +
+                                   field_off + k;
+                const int nb = k < a.d.obs ? 16 : 0;
+                cp_async16_zfill_tc(sbuf + rr * 64 + ((c ^ (rr & 7)) << 2), nb ? src : reinterpret_cast<const float *>(L.records), nb);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            group_sync(g);
 #pragma unroll
             for (int half = 0; half < 2; half++) {
-                const int k0 = kc * 64 + half * 32;
-                float4 v[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++)
-                    v[i] = (k0 + 4 * i < a.d.obs) ? __ldg(reinterpret_cast<const float4 *>(src + k0 + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float hi[32], lo[32];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    umma::split_tf32(v[i].x, hi[4 * i + 0], lo[4 * i + 0]); umma::split_tf32(v[i].y, hi[4 * i + 1], lo[4 * i + 1]);
-                    umma::split_tf32(v[i].z, hi[4 * i + 2], lo[4 * i + 2]); umma::split_tf32(v[i].w, hi[4 * i + 3], lo[4 * i + 3]);
+                    const int c = half * 8 + i;
+                    const float4 v = *reinterpret_cast<const float4 *>(sbuf + m * 64 + ((c ^ (m & 7)) << 2));
+                    umma::split_tf32(v.x, hi[4 * i + 0], lo[4 * i + 0]); umma::split_tf32(v.y, hi[4 * i + 1], lo[4 * i + 1]);
+                    umma::split_tf32(v.z, hi[4 * i + 2], lo[4 * i + 2]); umma::split_tf32(v.w, hi[4 * i + 3], lo[4 * i + 3]);
                 }
                 umma::tmem_st32(tlane + a_hi + half * 32, hi);
                 umma::tmem_st32(tlane + a_lo + half * 32, lo);
             }
             umma::tmem_st_wait();
+            if (stamp && kc == 1) TC_STAMP(11);
             umma::fence_before_thread_sync();
             group_sync(g);
+            if (stamp && kc == 1) TC_STAMP(12);
             if (m == 0) {
                 umma::fence_after_thread_sync();
                 const int keff = min(64, a.d.obs - kc * 64);
@@ -272,11 +291,14 @@ __device__ void layer1_all_tiles(const TcArgs &a, const TcLearner &L, Misc &mi, 
                                keff, kc > 0);
                 umma::mma_commit(&bar[1 + g]);
             }
+            if (stamp && kc == 1) TC_STAMP(13);
             umma::mbar_wait(&bar[1 + g], parg);
             parg ^= 1;
             umma::fence_after_thread_sync();
+            if (stamp && kc == 1) TC_STAMP(14);
         }
     }
+    if (stamp) TC_STAMP(15);
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
@@ -387,20 +409,20 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         umma::tmem_st32(tlane + a_lo + half * 32, lo);
                     }
                     umma::tmem_st_wait();
-                    if (t == 0 && act == 2) TC_STAMP(10);
+                    
                     umma::fence_before_thread_sync();
                     group_sync(h);
-                    if (t == 0 && act == 2) TC_STAMP(11);
+                    
                     if (m == 0) {
                         umma::fence_after_thread_sync();
                         umma::gemm3_ts(tm + acc_col, tm + a_hi, tm + a_lo, B_hi, B_lo, 128, HID, HID, false);
                         umma::mma_commit(&bar[1 + h]);
                     }
-                    if (t == 0 && act == 2) TC_STAMP(12);
+                    
                     umma::mbar_wait(&bar[1 + h], parg);
                     parg ^= 1;
                     umma::fence_after_thread_sync();
-                    if (t == 0 && act == 2) TC_STAMP(13);
+                    
                     float acc[64];
                     umma::tmem_ld32(tlane + acc_col, acc);
                     umma::tmem_ld32(tlane + acc_col + 32, acc + 32);
@@ -417,8 +439,8 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     q += mi.b3;
                     if (act >= cnt) q = -INFINITY;   // next_state_action_values[mask] = -inf
                     best = fmaxf(best, q);
-                    if (t == 0 && act == 2) TC_STAMP(14);
-                    if (t == 0 && act == 0) TC_STAMP(15);
+                    
+                    
                 }
                 mi.vmax2[h][m] = best;
                 umma::fence_before_thread_sync();
@@ -436,7 +458,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         load_weights(L.w, d, smem, mi, true);
         __syncthreads();
         TC_STAMP(5);
-        layer1_all_tiles(a, L, mi, smem, a.lay.off_state, tm, tlane, parg);
+        layer1_all_tiles(a, L, mi, smem, a.lay.off_state, tm, tlane, parg, round, true);
         TC_STAMP(6);
         float dw3_acc = 0.f, mae_acc = 0.f, db3_acc = 0.f;
         const umma::Tile W2_hi = umma::make_tile(smem + REG3, 64, 128), W2_lo = umma::make_tile(smem + REG3 + 16384, 64, 128);
@@ -564,19 +586,29 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         umma::split_tf32(dz1[c], hi, lo);          // dZ1^T
                         arena[AR_A_HI / 4 + idx] = hi; arena[AR_A_LO / 4 + idx] = lo;
                     }
-                    // S^T: this thread scatters half of its row's state vector into column rr
-                    const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[row] * W) + a.lay.off_state;
-                    const int kh = (d.obs + 1) >> 1, kb = h * kh & ~3, ke = h ? d.obs : (kh & ~3);
-                    for (int k = kb; k < ke; k += 4) {
-                        const float4 v = __ldg(reinterpret_cast<const float4 *>(src + k));
-                        const float vv[4] = {v.x, v.y, v.z, v.w};
+                }
+                // S^T: every warp reads whole state rows of this half coalesced (lane = k) and scatters them
+                // into column rr of the transposed tile
+                for (int r0 = 0; r0 < 8; r0 += 4) {
+                    float v[4][4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            float hi, lo;
-                            umma::split_tf32(vv[u], hi, lo);
-                            const int idx = umma::tile_index2(k + u, rr, 64, TL);
-                            arena[AR_B_HI / 4 + idx] = hi; arena[AR_B_LO / 4 + idx] = lo;
-                        }
+                    for (int ri = 0; ri < 4; ri++) {
+                        const int rq = warp + 8 * (r0 + ri);
+                        const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[t * 128 + hf * 64 + rq] * W) + a.lay.off_state;
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++) v[ri][jj] = (lane + 32 * jj < d.obs) ? __ldg(src + lane + 32 * jj) : 0.f;
+                    }
+#pragma unroll
+                    for (int ri = 0; ri < 4; ri++) {
+                        const int rq = warp + 8 * (r0 + ri);
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++)
+                            if (lane + 32 * jj < d.obs) {
+                                float hi, lo;
+                                umma::split_tf32(v[ri][jj], hi, lo);
+                                const int idx = umma::tile_index2(lane + 32 * jj, rq, 64, TL);
+                                arena[AR_B_HI / 4 + idx] = hi; arena[AR_B_LO / 4 + idx] = lo;
+                            }
                     }
                 }
                 umma::fence_async_smem();

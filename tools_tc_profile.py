@@ -31,5 +31,5 @@ print(f"kernel {ms*1e3/rounds:.1f} us/round; {tot:.0f} clk/round")
 for i, n in enumerate(names):
     print(f"  {n:36s} {(s[:, i+1]-s[:, i]).mean():10.0f} clk")
 
-print("all-actions iteration of group 0 (tile 0, action 2): build %.0f | fence+group sync %.0f | issue 24 MMAs %.0f | wait %.0f | epilogue %.0f" % (
-    (s[:, 10]-s[:, 15]).mean(), (s[:, 11]-s[:, 10]).mean(), (s[:, 12]-s[:, 11]).mean(), (s[:, 13]-s[:, 12]).mean(), (s[:, 14]-s[:, 13]).mean()))
+print("online layer 1, group 0, chunk 1: loads+split+tmem st %.0f | fence+sync %.0f | issue %.0f | wait %.0f | (chunk0 total %.0f) | tail-to-barrier %.0f" % (
+    (s[:, 11]-s[:, 10]).mean(), (s[:, 12]-s[:, 11]).mean(), (s[:, 13]-s[:, 12]).mean(), (s[:, 14]-s[:, 13]).mean(), (s[:, 10]-s[:, 5]).mean(), (s[:, 6]-s[:, 15]).mean()))
