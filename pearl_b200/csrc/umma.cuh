@@ -2,7 +2,7 @@
 // (tcgen05.mma with TMEM accumulators) for the dense contractions of the learner.
 //
 // fp32 parity needs more than one TF32 pass: every fp32 operand x is split
-//   x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi)
+//   x = hi + lo,  hi = trunc_tf32(x) (done by the hardware),  lo = x - hi
 // and a product is accumulated as hi*hi + hi*lo + lo*hi in the fp32 TMEM
 // accumulator ("3xTF32"): relative error ~2^-21 per product instead of 2^-11.
 //
@@ -35,9 +35,11 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+// The tensor core TRUNCATES fp32 operands to TF32 (measured, tests/test_gpu_umma.py), so the "hi" operand
+// can be x itself and lo = x - trunc_tf32(x) (exact in fp32; its own truncation costs 2^-21 relative).
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
+    hi = x;
+    lo = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
 
 // ---- descriptors ------------------------------------------------------------

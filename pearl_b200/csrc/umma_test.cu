@@ -100,7 +100,12 @@ k_umma_test_ts(const float *__restrict__ A, const float *__restrict__ B, float *
         float hi[32], lo[32];
         for (int c = 0; c < 32; c++) {
             const float x = (c0 + c < K) ? A[(size_t)tid * K + c0 + c] : 0.f;
-            umma::split_tf32(x, hi[c], lo[c]);
+            if (reps < 0) {   // probe: does the tensor core TRUNCATE fp32 inputs to tf32?  hi = x unrounded
+                hi[c] = x;
+                lo[c] = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+            } else {
+                umma::split_tf32(x, hi[c], lo[c]);
+            }
         }
         umma::tmem_st32(tl + 256 + c0, hi);
         umma::tmem_st32(tl + 384 + c0, lo);
@@ -111,7 +116,7 @@ k_umma_test_ts(const float *__restrict__ A, const float *__restrict__ B, float *
     if (tid == 0) {
         umma::fence_after_thread_sync();
         const long long t0 = clock64();
-        for (int r = 0; r < reps; r++)
+        for (int r = 0; r < (reps < 1 ? 1 : reps); r++)
             umma::gemm3_ts(tm, tm + 256, tm + 384, umma::make_tile(b_hi, K, 128), umma::make_tile(b_lo, K, 128), 128, N, K, r > 0);
         const long long t1 = clock64();
         umma::mma_commit(&bar);
@@ -207,7 +212,7 @@ extern "C" int prl_test_umma_gemm_ts(const float *a_dev, const float *b_dev, flo
     PRL_REQUIRE(k >= 8 && k % 8 == 0 && k <= 64, "K must be a multiple of 8 in [8,64]");
     const size_t smem = (size_t)2 * umma::tile_bytes(n, k);
     PRL_CUDA(cudaFuncSetAttribute(k_umma_test_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_umma_test_ts<<<1, 128, smem, (cudaStream_t)stream>>>(a_dev, b_dev, d_dev, n, k, reps < 1 ? 1 : reps);
+    k_umma_test_ts<<<1, 128, smem, (cudaStream_t)stream>>>(a_dev, b_dev, d_dev, n, k, reps == 0 ? 1 : reps);
     PRL_CUDA(cudaGetLastError());
     return PRL_OK;
 }
