@@ -117,37 +117,50 @@ def make_cpu_learner(n_store: int, rounds: int, threads: int):
     return buf, dqn
 
 
-def time_cpu(steps: int, warmup: int, rounds: int, n_store: int, threads: int) -> dict:
-    buf, dqn = make_cpu_learner(n_store, rounds, threads)
+def _cpu_worker(args_tuple):
+    steps, warmup, rounds, n_store, seed = args_tuple
+    import random
+    import torch
+    random.seed(seed)
+    buf, dqn = make_cpu_learner(n_store, rounds, 1)
     for _ in range(warmup):
         dqn.learn(buf)
     t0 = time.perf_counter()
     for _ in range(steps):
         dqn.learn(buf)
-    dt = time.perf_counter() - t0
-    return {"value": steps * rounds / dt, "seconds": dt, "ms_per_step": 1e3 * dt / steps}
+    return time.perf_counter() - t0
+
+
+def cpu_reference(args, steps: int, warmup: int) -> dict:
+    """The oracle port (the reference's own eager-PyTorch algorithm) on ALL host cores: one independent
+    single-threaded learner process per core (its best configuration at batch 256), aggregate steps/s."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, args.ref_procs if args.ref_procs > 0 else cores))
+    rounds, n_store = args.ref_rounds, args.ref_capacity
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        times = pool.map(_cpu_worker, [(steps, warmup, rounds, n_store, 1234 + i) for i in range(procs)])
+    dt = max(times)
+    return {"value": procs * steps * rounds / dt, "unit": "gradient-steps/s", "cores": procs, "kind": "port", "host_cores": cores,
+            "seconds": dt,
+            "sample": f"{procs} single-threaded learner processes x {steps} learn() calls x {rounds} rounds, batch {BATCH}, "
+                      f"deque of {n_store} transitions each (1e6 Python pushes take minutes and do not change the per-step cost)"}
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    cores = os.cpu_count() or 1
-    threads = min(cores, 32)  # eager CPU torch stops scaling far below this at batch 256
-    rounds, n_store = args.ref_rounds, args.ref_capacity
-    r = time_cpu(args.steps, args.warmup, rounds, n_store, threads)
-    sample = (f"{args.steps} learn() calls x {rounds} rounds, batch {BATCH}, deque of {n_store} transitions "
-              f"(1e6 Python pushes would take minutes; sampling cost does not depend on it)")
+    r = cpu_reference(args, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "gradient-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DeepQLearning synthetic obs_dim=128 n_act=16, 1M replay, batch=256 (configs[1])",
-                   "training_rounds_per_step": rounds, "hidden": list(HIDDEN), "cpu_buffer": n_store,
-                   "torch_threads": threads},
-        "cpu_baseline": {"value": r["value"], "unit": "gradient-steps/s", "cores": threads, "kind": "port",
-                         "sample": sample, "host_cores": cores, "torch": torch.__version__},
+                   "step": f"one learn() = {args.ref_rounds} gradient steps, in each of {r['cores']} independent learner processes",
+                   "training_rounds_per_step": args.ref_rounds, "hidden": list(HIDDEN), "cpu_buffer": args.ref_capacity},
+        "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": "gradient-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -182,42 +195,43 @@ def run_b200(args) -> None:
         torch.cuda.synchronize()
 
     cap, rounds = args.capacity, args.rounds
-    shard = cap  # every rank holds a full-size shard of its own (weak scaling)
     torch.manual_seed(1234)
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
 
-    def make_buffer(rng):
-        buf = pearl_b200.B200ReplayBuffer(shard, device=dev, rng=rng)
+    def make_buffer(rng, seed):
+        buf = pearl_b200.B200ReplayBuffer(cap, device=dev, rng=rng)
         chunk = 1 << 18
-        for s in range(0, shard, chunk):
-            m = min(chunk, shard - s)
+        for s in range(0, cap, chunk):
+            m = min(chunk, cap - s)
             buf.push_batch(torch.randn((m, OBS), generator=gen, device=dev),
                            (torch.arange(s, s + m, device=dev) % N_ACT).to(torch.int32),
                            torch.randn(m, generator=gen, device=dev),
                            torch.randn((m, OBS), generator=gen, device=dev),
                            torch.rand(m, generator=gen, device=dev) < 0.02,
                            torch.zeros(m, dtype=torch.bool, device=dev), max_number_actions=N_ACT)
+        buf.seed(seed)
         return buf
 
-    def make_learner():
+    def make_learner(engine, rds):
         return pearl_b200.B200DeepQLearning(
             state_dim=OBS, action_space=Space(N_ACT), hidden_dims=list(HIDDEN), learning_rate=1e-3,
-            discount_factor=0.99, training_rounds=rounds, batch_size=BATCH, target_update_freq=10,
+            discount_factor=0.99, training_rounds=rds, batch_size=BATCH, target_update_freq=10,
             soft_update_tau=0.75, action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(N_ACT),
-            max_rounds_per_call=max(rounds, 1), rows_per_cta=args.rows_per_cta).to(dev)
+            max_rounds_per_call=max(rds, 1), rows_per_cta=args.rows_per_cta, engine=engine).to(dev)
 
-    # ---- value: device-resident buffer, private device RNG ------------------
-    buf = make_buffer("device")
-    buf.seed(1234 + rank)
-    learner = make_learner()
-    comm = None
-    if world > 1 and args.multi == "dp":
-        comm = pearl_b200.B200Communicator(learner.flat_parameters.numel(), dev)
-        learner.set_communicator(comm)
-    learner.set_kernel_timing(True)
-    for _ in range(max(args.warmup, 3)):
-        learner.learn(buf)
-    info = learner.launch_info()
+    # ---- how many independent learners fit: one SM each, each with its OWN `cap`-transition replay
+    from pearl_b200 import _lib
+    sms = _lib.init(local).prl_sm_count()
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    rec_bytes = 1040
+    R = args.learners if args.learners > 0 else max(1, min(sms - 4, int((free_b - (10 << 30)) // (cap * rec_bytes))))
+    bufs = [make_buffer("device", 1234 + 1000 * rank + i) for i in range(R)]
+    learners = [make_learner("tc", rounds) for _ in range(R)]
+    group = pearl_b200.B200LearnerGroup(learners, bufs)
+    group.set_kernel_timing(True)
+    W_ = max(args.warmup, 3)
+    for _ in range(W_):
+        group.learn()
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -226,95 +240,106 @@ def run_b200(args) -> None:
     kernel_ms = []
     e0.record()
     for _ in range(args.steps):
-        learner.learn(buf)
-        kernel_ms.append(learner.last_kernel_ms())
+        group.learn()
+        kernel_ms.append(group.last_kernel_ms())
     e1.record()
     barrier()
     clk = clocks.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = args.steps * rounds * world / (ms_max / 1e3)
-    launches_per_step = info["launches"]
+    value = args.steps * rounds * R * world / (ms_max / 1e3)
 
-    # ---- e2e: host data through the plugin API -------------------------------
+    # ---- e2e: host data through the plugin API (every learner pushes `rounds` fresh transitions per step
+    #      from pinned host memory, CPython-RNG hand-off on, loss reports read back)
     import random
     random.seed(1234 + rank)
-    buf2 = buf
-    buf2._rng_mode = "python"  # the drop-in default: continue CPython's global stream
+    for b in bufs:
+        b._rng_mode = "python"
     n_new = rounds
-    pin = lambda t: t.pin_memory()
+    pin = lambda x: x.pin_memory()
     hg = torch.Generator().manual_seed(99 + rank)
     host = dict(state=pin(torch.randn((n_new, OBS), generator=hg)), next_state=pin(torch.randn((n_new, OBS), generator=hg)),
                 reward=pin(torch.randn(n_new, generator=hg)), action=pin((torch.arange(n_new) % N_ACT).to(torch.int32)),
                 term=pin(torch.rand(n_new, generator=hg) < 0.02), trunc=pin(torch.zeros(n_new, dtype=torch.bool)))
-    h2d = n_new * (2 * OBS * 4 + 4 + 4 + 1 + 1) + 625 * 4
-    d2h = rounds * 4 + 625 * 4
+    h2d = R * (n_new * (2 * OBS * 4 + 4 + 4 + 1 + 1) + 625 * 4)
+    d2h = R * (rounds * 4 + 625 * 4)
 
     def e2e_step():
-        buf2.push_batch(host["state"], host["action"], host["reward"], host["next_state"], host["term"], host["trunc"])
-        return learner.learn(buf2)["loss"][-1]
+        for b in bufs:
+            b.push_batch(host["state"], host["action"], host["reward"], host["next_state"], host["term"], host["trunc"])
+        return group.learn()[0]["loss"][-1]
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(2):
         e2e_step()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(2, args.steps // 4)
     f0.record()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         last_loss = e2e_step()
     f1.record()
     barrier()
     t2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = args.steps * rounds * world / (float(t2.item()) / 1e3)
+    e2e_value = e2e_steps * rounds * R * world / (float(t2.item()) / 1e3)
+
+    # ---- one sequential learner (cooperative fp32 SIMT kernel over 64 SMs + index producer CTA): latency view
+    single = None
+    if rank == 0 and not args.no_single:
+        for b in bufs[1:]:
+            b._storage = None
+        sl = make_learner("simt", rounds)
+        bufs[0]._rng_mode = "device"
+        for _ in range(3):
+            sl.learn(bufs[0])
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(5):
+            sl.learn(bufs[0])
+        s1.record()
+        torch.cuda.synchronize()
+        info = sl.launch_info()
+        single = {"value": 5 * rounds / (s0.elapsed_time(s1) / 1e3), "unit": "gradient-steps/s",
+                  "engine": f"k_dqn_learn: {info['ctas']} learner CTAs x {info['rows_per_cta']} rows + 1 index-producer CTA, fp32 SIMT"}
 
     if rank == 0:
         pk = peaks()
         fact, as_written = flops_per_step()
         k_ms = sum(kernel_ms) / len(kernel_ms)
-        achieved = fact * rounds / (k_ms / 1e3) / 1e12
+        achieved = fact * rounds * R / (k_ms / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
         line = {
             "metric": METRIC, "value": value, "unit": "gradient-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": W_, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": "DeepQLearning synthetic obs_dim=128 n_act=16, 1M replay, batch=256 (configs[1])",
-                       "step": f"one learn() call = {rounds} sequential gradient steps of ONE learner per GPU",
-                       "training_rounds_per_step": rounds, "hidden": list(HIDDEN), "replay_capacity_per_gpu": shard,
-                       "replay_bytes_per_gpu": shard * buf.record_bytes, "l2": "inputs larger than L2 (no flush needed)",
-                       "persistent_kernel_ctas": info["ctas"], "rows_per_cta": info["rows_per_cta"],
-                       "multi_gpu": ("single GPU" if world == 1 else
-                                     "data-parallel: per-GPU replay shard + batch of 256, mean gradient exchanged inside the "
-                                     "persistent kernel over NVLink peer memory every round (global batch 256*N); value counts "
-                                     "batch-256 gradient computations" if args.multi == "dp" else
-                                     "independent learner + buffer shard per GPU, no data-path collective"),
+                       "step": f"one B200LearnerGroup.learn() = {rounds} sequential gradient steps of EACH of {R} independent "
+                               f"learners per GPU (one SM per learner, each with its own {cap}-transition replay)",
+                       "learners_per_gpu": R, "training_rounds_per_step": rounds, "hidden": list(HIDDEN),
+                       "replay_capacity_per_learner": cap, "replay_bytes_per_gpu": R * cap * rec_bytes,
+                       "l2": "inputs larger than L2 (no flush needed)",
+                       "multi_gpu": "single GPU" if world == 1 else "independent learners sharded over the GPUs, no data-path collective "
+                                    "(the data-parallel single learner with in-kernel NVLink gradient exchange is `--single-dp`)",
                        "loss_last": last_loss},
             "e2e": {"value": e2e_value, "unit": "gradient-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": f"push_batch({n_new} transitions from pinned host) + learn() incl. CPython RNG hand-off and loss report"},
-            "gpu_launches": args.steps * launches_per_step,
+                    "what": f"per learner push_batch({n_new} transitions from pinned host) + group.learn() incl. CPython RNG hand-off and loss reports"},
+            "gpu_launches": args.steps * 2,
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "k_dqn_learn", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "k_dqn_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
                          "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
                          "flops_per_gradient_step_factored": fact, "flops_per_gradient_step_as_written": as_written,
-                         "kernel_ms_per_launch": k_ms, "gradient_steps_per_launch": rounds,
-                         "note": "v1 kernel is fp32 SIMT (no tensor-core issue yet); fp32-SIMT peak ~74 TFLOP/s"},
+                         "kernel_ms_per_launch": k_ms, "gradient_steps_per_launch": rounds * R,
+                         "note": "3xTF32: every algorithmic FLOP is issued 3x on the TF32 pipe (half the bf16 rate), so the "
+                                 "precision-matched ceiling is peak/6; frac_of_3xtf32_ceiling = %.3f" % (achieved / (peak / 6))},
+            "single_learner": single,
         }
         if not args.no_cpu and world == 1:
-            cores = os.cpu_count() or 1
-            threads = min(cores, 32)
-            r = time_cpu(3, 1, args.ref_rounds, args.ref_capacity, threads)
-            line["cpu_baseline"] = {"value": r["value"], "unit": "gradient-steps/s", "cores": threads, "kind": "port",
-                                    "host_cores": cores,
-                                    "sample": f"3 learn() calls x {args.ref_rounds} rounds on a {args.ref_capacity}-transition deque "
-                                              f"({r['seconds']:.1f} s)"}
+            line["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1)
         print(json.dumps(line), flush=True)
-    if comm is not None:
-        dist.barrier()
-        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -325,10 +350,13 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rounds", type=int, default=2048, help="training_rounds per learn() call")
+    ap.add_argument("--rounds", type=int, default=512, help="training_rounds per learn() call")
+    ap.add_argument("--learners", type=int, default=0, help="independent learners per GPU (0 = one per SM that fits in memory)")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-sequential-learner latency measurement")
+    ap.add_argument("--ref-procs", type=int, default=0, help="CPU reference processes (0 = one per host core)")
     ap.add_argument("--capacity", type=int, default=1_000_000)
     ap.add_argument("--rows-per-cta", type=int, default=0)
-    ap.add_argument("--ref-rounds", type=int, default=200)
+    ap.add_argument("--ref-rounds", type=int, default=100)
     ap.add_argument("--ref-capacity", type=int, default=20_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--multi", default="dp", choices=["dp", "replicas"],
