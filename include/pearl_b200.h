@@ -268,6 +268,17 @@ int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, int count, i
                         const int64_t *training_steps0, float *const *out_mae_dev, float *const *out_q_dev,
                         float *const *out_y_dev, int32_t *const *out_logical_dev, void *stream);
 
+/* ---- PPO preprocessing: GAE + truncated lambda returns --------------------------------------
+ * Replaces the per-transition loop of ProximalPolicyOptimization.preprocess_replay_buffer
+ * (policy_learners/sequential_decision_making/ppo.py:271-293).  All arrays are device pointers in
+ * TIME order (index 0 = oldest stored transition): values[i] = critic(state_i), last_next_value =
+ * critic(next_state of the newest transition), reward f32, terminated / truncated u8.  Outputs gae[i],
+ * lam_return[i] are bit-identical to the reference loop (same fp32 operation order); episodes
+ * (chains between terminated / truncated transitions) are processed in parallel. */
+int prl_ppo_gae(int n, const float *values_dev, float last_next_value, const float *reward_dev,
+                const uint8_t *terminated_dev, const uint8_t *truncated_dev, double gamma, double lam,
+                float *out_gae_dev, float *out_lam_return_dev, void *stream);
+
 /* Device timing of the persistent learner kernel alone (CUDA events recorded on
  * the launch stream around the kernel); used by bench.py for the roofline line.
  * prl_dqn_last_kernel_ms synchronises on the end event. */

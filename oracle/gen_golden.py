@@ -231,9 +231,54 @@ def gen_random_sample_vectors():
     print("random_sample_kat.json:", len(out), "cases")
 
 
+def gen_ppo_gae_golden():
+    """GAE / lambda-return vectors from the reference's own preprocess_replay_buffer (ppo.py:201-293)."""
+    from pearl.policy_learners.sequential_decision_making.ppo import PPOReplayBuffer, ProximalPolicyOptimization
+    torch.manual_seed(31)
+    random.seed(31)
+    obs, n_act, n = 6, 4, 700
+    space = DiscreteActionSpace(actions=list(torch.arange(n_act).view(-1, 1)))
+    pl = ProximalPolicyOptimization(state_dim=obs, action_space=space, actor_hidden_dims=[16, 16], critic_hidden_dims=[16, 16],
+                                    training_rounds=1, batch_size=32, epsilon=0.1, discount_factor=0.97, trace_decay_param=0.9,
+                                    action_representation_module=OneHotActionTensorRepresentationModule(n_act))
+    buf = PPOReplayBuffer(n)
+    agent = PearlAgent(policy_learner=pl, replay_buffer=buf, device_id=-1)
+    rng = np.random.Generator(np.random.PCG64(5))
+    states = (np.rint(rng.standard_normal((n + 1, obs)) * 256) / 256).astype(np.float32)
+    rewards = (np.rint(rng.standard_normal(n) * 256) / 256).astype(np.float32)
+    terminated = np.zeros(n, dtype=bool); truncated = np.zeros(n, dtype=bool)
+    terminated[49::50] = True
+    truncated[[120, 333, 512]] = True
+    terminated[[7, 8]] = True          # adjacent episode ends
+    for i in range(n):
+        buf.push(state=torch.from_numpy(states[i]), action=torch.tensor(i % n_act), reward=float(rewards[i]),
+                 terminated=bool(terminated[i]), truncated=bool(truncated[i]), curr_available_actions=space,
+                 next_state=torch.from_numpy(states[i + 1]), next_available_actions=space, max_number_actions=n_act)
+    with torch.no_grad():
+        values = pl._critic(torch.from_numpy(states[:n])).reshape(n).numpy().copy()
+        last_next_value = float(pl._critic(torch.from_numpy(states[n:n + 1]))[0])
+    pl.preprocess_replay_buffer(buf)
+    gae = np.asarray([float(t.gae) for t in buf.memory], dtype=np.float32)
+    lam = np.asarray([float(t.lam_return) for t in buf.memory], dtype=np.float32)
+    # the closed form of the reference's unit test (test_ppo.py:48-115): gamma 0.6, lambda 0.5, rewards 4,6,5
+    v = np.asarray([0.37, -1.25, 0.5, 2.0], dtype=np.float32)
+    g2 = np.float32(5) + np.float32(0.6) * v[3] - v[2]
+    g1 = np.float32(6) + np.float32(0.6) * v[2] - v[1] + np.float32(0.6 * 0.5) * g2
+    g0 = np.float32(4) + np.float32(0.6) * v[1] - v[0] + np.float32(0.6 * 0.5) * g1
+    np.savez_compressed(os.path.join(GOLDEN, "ppo_gae.npz"), values=values, last_next_value=np.float32(last_next_value),
+                        reward=rewards, terminated=terminated, truncated=truncated, gae=gae, lam_return=lam,
+                        gamma=0.97, lam=0.9, kat_v=v, kat_gae=np.asarray([g0, g1, g2], dtype=np.float32),
+                        kat_reward=np.asarray([4, 6, 5], dtype=np.float32))
+    print("ppo_gae.npz:", n, "transitions; gae[0..2] =", gae[:3])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "ppo":
+        gen_ppo_gae_golden()
+        sys.exit(0)
     gen_random_sample_vectors()
+    gen_ppo_gae_golden()
     # small everything; ring wraps (n_push > capacity); pool branch (n=48 <= 85)
     run_dqn_case("dqn_tiny", obs=8, n_act=4, hidden=(16, 16), capacity=48, n_push=70, batch=16,
                  rounds=12, target_update_freq=5, tau=0.75, double=False, seed=11, data_seed=101,

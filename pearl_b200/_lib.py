@@ -74,6 +74,7 @@ _SIGNATURES = {
     "prl_dqn_set_comm": (C.c_int, [_P, _P]),
     "prl_dqn_tc_supported": (C.c_int, [_P, C.c_int]),
     "prl_dqn_learn_multi": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "prl_ppo_gae": (C.c_int, [C.c_int, _P, C.c_float, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
     "prl_dqn_set_timing": (C.c_int, [_P, C.c_int]),
     "prl_dqn_set_profile": (C.c_int, [_P, _P]),
     "prl_dqn_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
