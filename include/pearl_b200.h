@@ -268,6 +268,40 @@ int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, int count, i
                         const int64_t *training_steps0, float *const *out_mae_dev, float *const *out_q_dev,
                         float *const *out_y_dev, int32_t *const *out_logical_dev, void *stream);
 
+/* ---- prioritized replay (sum tree) ----------------------------------------------------------
+ * NOT in the reference (no prioritized replay exists in Pearl @ 48f1fbb): parity is
+ * pinned against oracle/per_oracle.py, the restatement of proportional prioritization (Schaul et al.
+ * 2016) that both sides implement with bit-identical fp32 trees.  Leaves are the physical ring slots
+ * of a replay buffer of `capacity` records.  The caller provides two device arrays of
+ * prl_per_tree_floats(capacity) floats (sum tree, min tree) and one device float (running maximum
+ * priority); prl_per_create initialises them on `stream`. */
+typedef struct prl_per_cfg {
+    int64_t capacity;
+    double alpha, beta, eps;   /* p = (|td| + eps)^alpha ; w = (p_min / p)^beta */
+    uint64_t seed;             /* Philox4x32-10 key of the stratified draws */
+} prl_per_cfg;
+typedef struct prl_per prl_per;
+int64_t prl_per_tree_floats(int64_t capacity);
+int prl_per_create(prl_per **out, const prl_per_cfg *cfg, float *sum_tree_dev, float *min_tree_dev,
+                   float *max_priority_dev, void *stream);
+int prl_per_destroy(prl_per *per);
+int prl_per_set_beta(prl_per *per, double beta);
+int64_t prl_per_draws(const prl_per *per);
+/* transitions just written to ring slots [first_slot, first_slot + count) (wrapping) enter at the
+ * running maximum priority */
+int prl_per_push(prl_per *per, int64_t first_slot, int64_t count, void *stream);
+/* k <= 1024 stratified draws: out_slots_dev i32[k] (ring slots), out_weights_dev f32[k] (IS weights) */
+int prl_per_sample(prl_per *per, int k, int32_t *out_slots_dev, float *out_weights_dev, void *stream);
+/* new priorities (|td| + eps)^alpha for k <= 1024 sampled slots; out_priority_dev (optional) f32[k] */
+int prl_per_set_priorities(prl_per *per, const int32_t *slots_dev, const float *td_dev, int k,
+                           float *out_priority_dev, void *stream);
+/* PolicyLearner.learn() over a prioritized buffer: per round sample -> weighted MSE step (the IS weight
+ * multiplies the squared TD error) -> priority update from |q - y|.  Same outputs as prl_dqn_learn;
+ * out_slots_dev (optional) i32[rounds][batch] receives the sampled ring slots. */
+int prl_dqn_learn_per(prl_dqn *dqn, prl_buf *buf, prl_per *per, int rounds, int batch, int64_t training_steps0,
+                      float *out_mae_dev, float *out_q_dev, float *out_y_dev, int32_t *out_slots_dev,
+                      float *out_weights_dev, void *stream);
+
 /* ---- PPO preprocessing: GAE + truncated lambda returns --------------------------------------
  * Replaces the per-transition loop of ProximalPolicyOptimization.preprocess_replay_buffer
  * (policy_learners/sequential_decision_making/ppo.py:271-293).  All arrays are device pointers in

@@ -164,7 +164,10 @@ class OracleDQN:
                     pt.copy_(self.tau * p + (1.0 - self.tau) * pt)
         q = self._q_values(self.Q, b["state"], b["action"])
         y = self._next_values(b) * self.gamma * (1 - b["terminated"].float()) + b["reward"]
-        loss = torch.nn.MSELoss()(q, y)
+        if b.get("weight") is not None:   # prioritized replay: importance-weighted squared TD error
+            loss = (b["weight"] * (q - y) ** 2).mean()
+        else:
+            loss = torch.nn.MSELoss()(q, y)
         self.opt.zero_grad()
         loss.backward()
         self.opt.step()

@@ -28,6 +28,11 @@ class BufLayout(C.Structure):
                 ("off_avail", C.c_int32), ("act_words", C.c_int32), ("storage_bytes", C.c_int64)]
 
 
+class PerCfg(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("alpha", C.c_double), ("beta", C.c_double), ("eps", C.c_double),
+                ("seed", C.c_uint64)]
+
+
 class DqnCfg(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("n_actions", C.c_int32), ("hidden1", C.c_int32),
                 ("hidden2", C.c_int32), ("double_dqn", C.c_int32), ("target_update_freq", C.c_int32),
@@ -74,6 +79,15 @@ _SIGNATURES = {
     "prl_dqn_set_comm": (C.c_int, [_P, _P]),
     "prl_dqn_tc_supported": (C.c_int, [_P, C.c_int]),
     "prl_dqn_learn_multi": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "prl_per_tree_floats": (C.c_int64, [C.c_int64]),
+    "prl_per_create": (C.c_int, [C.POINTER(_P), C.POINTER(PerCfg), _P, _P, _P, _P]),
+    "prl_per_destroy": (C.c_int, [_P]),
+    "prl_per_set_beta": (C.c_int, [_P, C.c_double]),
+    "prl_per_draws": (C.c_int64, [_P]),
+    "prl_per_push": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    "prl_per_sample": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "prl_per_set_priorities": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
+    "prl_dqn_learn_per": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "prl_ppo_gae": (C.c_int, [C.c_int, _P, C.c_float, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
     "prl_dqn_set_timing": (C.c_int, [_P, C.c_int]),
     "prl_dqn_set_profile": (C.c_int, [_P, _P]),

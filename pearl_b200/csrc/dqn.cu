@@ -82,6 +82,8 @@ struct LearnArgs {
     float *gpart;             // [G][Pp]
     const float2 *scal;       // [rounds] (step_size, sqrt(bias_correction2)) as torch computes them
     float *out_mae, *out_q, *out_y;
+    const float *is_weight;   // optional [rounds][B] importance weights (prioritized replay)
+    float *out_td;            // optional [rounds][B] |q - y| per row
     Dims d;
     Plan plan;
     int B, R, rounds, mch, double_dqn, freq;
@@ -477,7 +479,10 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
         const float y = __fadd_rn(__fmul_rn(__fmul_rn(sc.v[tid], a.gamma), 1.f - sc.term[tid]), sc.rew[tid]);
         const float q = sc.q[tid];
         sc.y[tid] = y;
-        sc.dq[tid] = (q - y) * a.inv_b2;  // d/dq mean((q-y)^2) = 2 (q-y) / B
+        float dqv = (q - y) * a.inv_b2;  // d/dq mean((q-y)^2) = 2 (q-y) / B
+        if (a.is_weight) dqv *= __ldg(a.is_weight + (size_t)round * a.B + r0 + tid);   // d/dq mean(w (q-y)^2)
+        sc.dq[tid] = dqv;
+        if (a.out_td) a.out_td[(size_t)round * a.B + r0 + tid] = fabsf(q - y);
         if (a.out_q) a.out_q[(size_t)round * a.B + r0 + tid] = q;
         if (a.out_y) a.out_y[(size_t)round * a.B + r0 + tid] = y;
     }
@@ -765,7 +770,7 @@ extern "C" int64_t prl_dqn_param_count(const prl_dqn_cfg *c) {
     return make_dims(c->obs_dim, c->n_actions, c->hidden1, c->hidden2).P;
 }
 
-struct WsPlan { int64_t gpart, slots, logical, scal, tmp_rec, tmp_slots, multi, total; };
+struct WsPlan { int64_t gpart, slots, logical, scal, tmp_rec, tmp_slots, multi, is_w, td, total; };
 static WsPlan ws_plan(const prl_dqn_cfg *c) {
     Dims d = make_dims(c->obs_dim, c->n_actions, c->hidden1, c->hidden2);
     WsPlan w;
@@ -777,6 +782,8 @@ static WsPlan ws_plan(const prl_dqn_cfg *c) {
     w.tmp_rec = o; o = align_up64(o + tmp_layout(c).storage_bytes, 256);
     w.tmp_slots = o; o = align_up64(o + (int64_t)c->max_batch * 4, 256);
     w.multi = o; o = align_up64(o + 64 * 1024, 256);
+    w.is_w = o; o = align_up64(o + (int64_t)c->max_rounds * c->max_batch * 4, 256);
+    w.td = o; o = align_up64(o + (int64_t)c->max_batch * 4, 256);
     w.total = o;
     return w;
 }
@@ -807,6 +814,8 @@ extern "C" int prl_dqn_create(prl_dqn **out, const prl_dqn_cfg *cfg, float *w, f
     q->tmp_rec = (uint32_t *)(base + ws.tmp_rec);
     q->tmp_slots = (int32_t *)(base + ws.tmp_slots);
     q->multi_dev = (void *)(base + ws.multi);
+    q->is_w = (float *)(base + ws.is_w);
+    q->td = (float *)(base + ws.td);
     q->tmp_lay = tmp_layout(cfg);
     q->scal_next = 0;
     q->scal_host[0] = q->scal_host[1] = nullptr;
@@ -994,19 +1003,23 @@ int prl_dqn_stage_scalars(prl_dqn *q, int rounds, cudaStream_t stream) {
 static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layout &lay, int buf_flags,
                         const int32_t *slots, int rounds, int B, int64_t steps0, int first_update, float *out_mae,
                         float *out_q, float *out_y, cudaStream_t stream, prl_buf *sample_from = nullptr,
-                        int32_t *out_logical = nullptr) {
+                        int32_t *out_logical = nullptr, const float *is_weight = nullptr, float *out_td = nullptr,
+                        int prestaged_scal_offset = -1) {
     int R, mch;
     Plan pl;
     int rc = choose_tiling(q, B, lay.record_words, &R, &mch, &pl);
     if (rc) return rc;
     const prl_dqn_cfg &c = q->cfg;
-    rc = prl_dqn_stage_scalars(q, rounds, stream);
-    if (rc) return rc;
+    if (prestaged_scal_offset < 0) {
+        rc = prl_dqn_stage_scalars(q, rounds, stream);
+        if (rc) return rc;
+    }
 
     LearnArgs a;
     a.records = records; a.lay = lay; a.buf_flags = buf_flags; a.slots = slots;
     a.w = q->w; a.wt = q->wt; a.m = q->m; a.v = q->v; a.vmax = q->vmax;
-    a.gpart = q->gpart; a.scal = q->scal_dev;
+    a.gpart = q->gpart; a.scal = q->scal_dev + (prestaged_scal_offset < 0 ? 0 : prestaged_scal_offset);
+    a.is_weight = is_weight; a.out_td = out_td;
     a.out_mae = out_mae; a.out_q = out_q; a.out_y = out_y;
     a.d = q->d; a.plan = pl;
     a.B = B; a.R = R; a.rounds = rounds; a.mch = mch; a.double_dqn = c.double_dqn; a.freq = c.target_update_freq;
@@ -1078,6 +1091,37 @@ extern "C" int prl_dqn_learn(prl_dqn *q, prl_buf *buf, int rounds, int batch, in
                           buf, out_logical);
     if (rc) return rc;
     q->last_launches = 1;  // one persistent kernel: index producer CTA + learner CTAs
+    return PRL_OK;
+}
+
+extern "C" int prl_dqn_learn_per(prl_dqn *q, prl_buf *buf, prl_per *per, int rounds, int batch, int64_t training_steps0,
+                                 float *out_mae, float *out_q, float *out_y, int32_t *out_slots, float *out_weights,
+                                 void *stream_) {
+    PRL_REQUIRE(q && buf && per && out_mae, "null argument");
+    PRL_REQUIRE(rounds > 0 && rounds <= q->cfg.max_rounds, "rounds %d outside [1, max_rounds=%d]", rounds, q->cfg.max_rounds);
+    PRL_REQUIRE(batch > 0 && batch <= q->cfg.max_batch && batch <= 1024, "batch %d outside [1, min(max_batch, 1024)]", batch);
+    PRL_REQUIRE(buf->desc.flags & PRL_BUF_DISCRETE, "DQN needs a discrete-action buffer");
+    PRL_REQUIRE(buf->desc.obs_dim == q->cfg.obs_dim && buf->desc.n_actions == q->cfg.n_actions, "buffer does not match the learner");
+    PRL_REQUIRE(buf->len > 0, "empty replay buffer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = prl_dqn_stage_scalars(q, rounds, stream);
+    if (rc) return rc;
+    for (int r = 0; r < rounds; r++) {
+        int32_t *slots = q->slots + (size_t)r * batch;
+        float *w = q->is_w + (size_t)r * batch;
+        rc = prl_per_sample(per, batch, slots, w, stream_);
+        if (rc) return rc;
+        const int64_t s0 = training_steps0 + r;
+        rc = launch_learn(q, buf->records, buf->lay, buf->desc.flags, slots, 1, batch, s0,
+                          (s0 + 2) % q->cfg.target_update_freq == 0, out_mae + r, out_q ? out_q + (size_t)r * batch : nullptr,
+                          out_y ? out_y + (size_t)r * batch : nullptr, stream, nullptr, nullptr, w, q->td, r);
+        if (rc) return rc;
+        rc = prl_per_set_priorities(per, slots, q->td, batch, nullptr, stream_);
+        if (rc) return rc;
+    }
+    if (out_slots) PRL_CUDA(cudaMemcpyAsync(out_slots, q->slots, (size_t)rounds * batch * 4, cudaMemcpyDeviceToDevice, stream));
+    if (out_weights) PRL_CUDA(cudaMemcpyAsync(out_weights, q->is_w, (size_t)rounds * batch * 4, cudaMemcpyDeviceToDevice, stream));
+    q->last_launches = 3 * rounds;
     return PRL_OK;
 }
 

@@ -57,6 +57,7 @@ struct prl_dqn {
     int32_t *slots, *logical;
     float2 *scal_dev;
     uint32_t *tmp_rec;
+    float *is_w, *td;         // prioritized replay: importance weights [rounds][B], |q-y| [B]
     void *multi_dev;          // 64 KB: per-learner descriptors of a multi-learner launch
     int32_t *tmp_slots;
     prl_buf_layout tmp_lay;

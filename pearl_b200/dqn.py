@@ -230,6 +230,9 @@ class _B200DQNMixin:
         dev = self._device
         if replay_buffer.device != dev:
             raise RuntimeError(f"replay buffer is on {replay_buffer.device}, learner on {dev}")
+        from .per import B200PrioritizedReplayBuffer
+        if isinstance(replay_buffer, B200PrioritizedReplayBuffer):
+            return self._learn_prioritized(replay_buffer, bs, rounds, trace)
         mae = torch.empty(rounds, dtype=torch.float32, device=dev)
         q = y = idx = None
         if trace:
@@ -262,6 +265,33 @@ class _B200DQNMixin:
         report = {"loss": mae.cpu().tolist()}  # the one device->host read of the call
         if trace:
             report.update(q=q, y=y, idx=idx)
+        return report
+
+    def _learn_prioritized(self, rb, bs: int, rounds: int, trace: bool) -> dict:
+        """learn() over a B200PrioritizedReplayBuffer: per round stratified sum-tree draw, importance-weighted
+        MSE step, priority update from |q - y| (prl_dqn_learn_per)."""
+        dev = self._device
+        mae = torch.empty(rounds, dtype=torch.float32, device=dev)
+        q = y = slots = w = None
+        if trace:
+            q = torch.empty((rounds, bs), dtype=torch.float32, device=dev)
+            y = torch.empty((rounds, bs), dtype=torch.float32, device=dev)
+            slots = torch.empty((rounds, bs), dtype=torch.int32, device=dev)
+            w = torch.empty((rounds, bs), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            done = 0
+            while done < rounds:
+                r = min(self._max_rounds, rounds - done)
+                off = lambda t, k=1: C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr() + 4 * done * k)
+                _lib.check(self._libh.prl_dqn_learn_per(self._handle, rb.handle, rb.per_handle, r, bs, int(self._training_steps),
+                                                        off(mae), off(q, bs), off(y, bs), off(slots, bs), off(w, bs),
+                                                        _stream_ptr(dev)))
+                self._training_steps += r
+                done += r
+        self._sync_step_tensors()
+        report = {"loss": mae.cpu().tolist()}
+        if trace:
+            report.update(q=q, y=y, slots=slots, weight=w)
         return report
 
     def preprocess_batch(self, batch):
