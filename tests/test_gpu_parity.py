@@ -22,7 +22,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 KAT = json.load(open(os.path.join(GOLDEN, "random_sample_kat.json")))["cases"]
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+CASES = sorted(os.path.basename(p)[:-4] for pat in ("dqn_*.npz", "ddqn_*.npz") for p in glob.glob(os.path.join(GOLDEN, pat)))
 RTOL = 1e-4
 
 

@@ -20,7 +20,7 @@ from oracle.pearl_oracle import OracleDQN, OracleReplayBuffer, flat
 from oracle.synth import from_fixture
 
 KAT = json.load(open(os.path.join(GOLDEN, "random_sample_kat.json")))["cases"]
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+CASES = sorted(os.path.basename(p)[:-4] for pat in ("dqn_*.npz", "ddqn_*.npz") for p in glob.glob(os.path.join(GOLDEN, pat)))
 
 
 @pytest.mark.parametrize("case", KAT, ids=lambda c: f"seed{c['seed']}_n{c['n']}_k{c['k']}")
