@@ -272,13 +272,77 @@ def gen_ppo_gae_golden():
     print("ppo_gae.npz:", n, "transitions; gae[0..2] =", gae[:3])
 
 
+def gen_sac_golden():
+    """Continuous SAC: PearlAgent(ContinuousSoftActorCritic, BasicReplayBuffer).learn() with the two
+    Normal.rsample noise draws per step recorded (torch.distributions.normal._standard_normal)."""
+    import torch.distributions.normal as tdn
+    from pearl.policy_learners.sequential_decision_making.soft_actor_critic_continuous import ContinuousSoftActorCritic
+    from pearl.utils.instantiations.spaces.box_action import BoxActionSpace
+    torch.manual_seed(41)
+    random.seed(41)
+    torch.set_num_threads(1)
+    obs, act, n, B, rounds = 11, 3, 300, 64, 6
+    low, high = torch.tensor([-0.4, -0.8, -0.4]), torch.tensor([0.4, 0.8, 1.2])
+    space = BoxActionSpace(low=low, high=high)
+    pl = ContinuousSoftActorCritic(state_dim=obs, action_space=space, actor_hidden_dims=[32, 32], critic_hidden_dims=[32, 32],
+                                   training_rounds=rounds, batch_size=B, actor_learning_rate=3e-4, critic_learning_rate=5e-4,
+                                   critic_soft_update_tau=0.05, discount_factor=0.98, entropy_autotune=True)
+    buf = BasicReplayBuffer(n)
+    agent = PearlAgent(policy_learner=pl, replay_buffer=buf, device_id=-1)
+    rng = np.random.Generator(np.random.PCG64(9))
+    q8 = lambda x: (np.rint(x * 256) / 256).astype(np.float32)
+    st, ns, rw = q8(rng.standard_normal((n, obs))), q8(rng.standard_normal((n, obs))), q8(rng.standard_normal(n))
+    ac = q8(rng.uniform(low.numpy(), high.numpy(), size=(n, act)))
+    term = rng.random(n) < 0.05
+    for i in range(n):
+        buf.push(state=torch.from_numpy(st[i]), action=torch.from_numpy(ac[i]), reward=float(rw[i]), terminated=bool(term[i]),
+                 truncated=False, curr_available_actions=space, next_state=torch.from_numpy(ns[i]), next_available_actions=space)
+    fl = lambda m: np.concatenate([p.detach().numpy().ravel() for p in m.parameters()])
+    init = dict(actor=fl(pl._actor), q1=fl(pl._critic._critic_1), q2=fl(pl._critic._critic_2),
+                q1t=fl(pl._critic_target._critic_1), q2t=fl(pl._critic_target._critic_2))
+    noises, idxs = [], []
+    orig_sn = tdn._standard_normal
+
+    def sn_spy(shape, dtype, device):
+        x = orig_sn(shape, dtype, device)
+        noises.append(x.numpy().copy())
+        return x
+    tdn._standard_normal = sn_spy
+    orig_sample = buf.sample
+
+    def sample_spy(k):
+        pos = {id(t): j for j, t in enumerate(buf.memory)}
+        stt = random.getstate()
+        idxs.append([pos[id(t)] for t in random.sample(buf.memory, k)])
+        random.setstate(stt)
+        return orig_sample(k)
+    buf.sample = sample_spy
+    rep = agent.learn()
+    tdn._standard_normal = orig_sn
+    assert len(noises) == 2 * rounds
+    out = dict(obs=obs, act=act, n=n, batch=B, rounds=rounds, low=low.numpy(), high=high.numpy(), actor_lr=3e-4, critic_lr=5e-4,
+               tau=0.05, gamma=0.98, state=st, next_state=ns, reward=rw, action=ac, terminated=term,
+               idx=np.asarray(idxs, dtype=np.int32), noise=np.asarray(noises, dtype=np.float32),
+               actor_loss=np.asarray(rep["actor_loss"]), critic_loss=np.asarray(rep["critic_loss"]),
+               entropy_loss=np.asarray([float(x) for x in rep["entropy_coef"]]),
+               actor_after=fl(pl._actor), q1_after=fl(pl._critic._critic_1), q2_after=fl(pl._critic._critic_2),
+               q1t_after=fl(pl._critic_target._critic_1), q2t_after=fl(pl._critic_target._critic_2),
+               log_alpha_after=pl._log_entropy.detach().numpy().copy(), **{f"init_{k}": v for k, v in init.items()})
+    np.savez_compressed(os.path.join(GOLDEN, "sac_small.npz"), **out)
+    print("sac_small.npz: actor_loss", rep["actor_loss"][:2], "critic_loss", rep["critic_loss"][:2])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "sac":
+        gen_sac_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ppo":
         gen_ppo_gae_golden()
         sys.exit(0)
     gen_random_sample_vectors()
     gen_ppo_gae_golden()
+    gen_sac_golden()
     # small everything; ring wraps (n_push > capacity); pool branch (n=48 <= 85)
     run_dqn_case("dqn_tiny", obs=8, n_act=4, hidden=(16, 16), capacity=48, n_push=70, batch=16,
                  rounds=12, target_update_freq=5, tau=0.75, double=False, seed=11, data_seed=101,
