@@ -313,6 +313,42 @@ int prl_ppo_gae(int n, const float *values_dev, float last_next_value, const flo
                 const uint8_t *terminated_dev, const uint8_t *truncated_dev, double gamma, double lam,
                 float *out_gae_dev, float *out_lam_return_dev, void *stream);
 
+/* ---- continuous Soft Actor-Critic ---------------------------------------------------------------
+ * Replaces ContinuousSoftActorCritic.learn_batch (policy_learners/sequential_decision_making/
+ * actor_critic_base.py:309-366, soft_actor_critic_continuous.py:131-231) driven by PolicyLearner.learn
+ * (policy_learner.py:162-204) over a continuous-action ring: per round sample -> actor step
+ * (GaussianActorNetwork.sample_action, actor_networks.py:551-591, twin-critic minimum) -> critic step
+ * with the updated actor (twin MSE against the entropy-regularised target, critic_utils.py:170-203)
+ * -> soft target update (tau every step) -> entropy-coefficient step.  Three AdamW(amsgrad) states.
+ * Flat parameter layouts (fp32, row-major [out][in] like nn.Linear):
+ *   actor : W1[h1][obs] b1 W2[h2][h1] b2 Wmu[A][h2] bmu Wstd[A][h2] bstd
+ *   critic: TWO consecutive copies (q1 then q2) of W1[c1][obs+A] b1 W2[c2][c1] b2 W3[1][c2] b3
+ * The reparameterisation noise is an input (device f32[rounds][2][batch][A]: first draw on `state`
+ * for the actor loss, second on `next_state` for the target), as torch's Normal.rsample consumes it. */
+typedef struct prl_sac_cfg {
+    int32_t obs_dim, act_dim, actor_h1, actor_h2, critic_h1, critic_h2;
+    int32_t autotune;     /* entropy_autotune */
+    int32_t max_batch, max_rounds;
+    double actor_lr, critic_lr, beta1, beta2, eps, weight_decay, gamma, tau;
+} prl_sac_cfg;
+typedef struct prl_sac prl_sac;
+int64_t prl_sac_actor_param_count(const prl_sac_cfg *cfg);
+int64_t prl_sac_critic_param_count(const prl_sac_cfg *cfg);   /* ONE critic */
+int64_t prl_sac_workspace_bytes(const prl_sac_cfg *cfg);
+/* All pointers are device memory owned by the caller: actor vectors f32[actor_param_count], critic
+ * vectors f32[2 * critic_param_count], log_alpha4 = {log_alpha, exp_avg, exp_avg_sq, max_exp_avg_sq},
+ * alpha1 = the entropy coefficient in use, low/high f32[act_dim] action-space bounds. */
+int prl_sac_create(prl_sac **out, const prl_sac_cfg *cfg, float *actor_w, float *actor_m, float *actor_v,
+                   float *actor_vmax, float *critic_w, float *critic_m, float *critic_v, float *critic_vmax,
+                   float *critic_target_w, float *log_alpha4, float *alpha1, const float *low_dev,
+                   const float *high_dev, int64_t adam_step, void *workspace);
+int prl_sac_destroy(prl_sac *sac);
+int64_t prl_sac_adam_step(const prl_sac *sac);
+/* out_*_loss: device f32[rounds]; out_logical_dev (optional) i32[rounds][batch] = sampled indices */
+int prl_sac_learn(prl_sac *sac, prl_buf *buf, int rounds, int batch, const float *noise_dev,
+                  float *out_actor_loss_dev, float *out_critic_loss_dev, float *out_entropy_loss_dev,
+                  int32_t *out_logical_dev, void *stream);
+
 /* Device timing of the persistent learner kernel alone (CUDA events recorded on
  * the launch stream around the kernel); used by bench.py for the roofline line.
  * prl_dqn_last_kernel_ms synchronises on the end event. */

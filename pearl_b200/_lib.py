@@ -33,6 +33,14 @@ class PerCfg(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+class SacCfg(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("actor_h1", C.c_int32), ("actor_h2", C.c_int32),
+                ("critic_h1", C.c_int32), ("critic_h2", C.c_int32), ("autotune", C.c_int32), ("max_batch", C.c_int32),
+                ("max_rounds", C.c_int32), ("actor_lr", C.c_double), ("critic_lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double), ("gamma", C.c_double),
+                ("tau", C.c_double)]
+
+
 class DqnCfg(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("n_actions", C.c_int32), ("hidden1", C.c_int32),
                 ("hidden2", C.c_int32), ("double_dqn", C.c_int32), ("target_update_freq", C.c_int32),
@@ -89,6 +97,13 @@ _SIGNATURES = {
     "prl_per_set_priorities": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "prl_dqn_learn_per": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "prl_ppo_gae": (C.c_int, [C.c_int, _P, C.c_float, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
+    "prl_sac_actor_param_count": (C.c_int64, [C.POINTER(SacCfg)]),
+    "prl_sac_critic_param_count": (C.c_int64, [C.POINTER(SacCfg)]),
+    "prl_sac_workspace_bytes": (C.c_int64, [C.POINTER(SacCfg)]),
+    "prl_sac_create": (C.c_int, [C.POINTER(_P), C.POINTER(SacCfg)] + [_P] * 13 + [C.c_int64, _P]),
+    "prl_sac_destroy": (C.c_int, [_P]),
+    "prl_sac_adam_step": (C.c_int64, [_P]),
+    "prl_sac_learn": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "prl_dqn_set_timing": (C.c_int, [_P, C.c_int]),
     "prl_dqn_set_profile": (C.c_int, [_P, _P]),
     "prl_dqn_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),

@@ -1,0 +1,131 @@
+"""Continuous SAC on the GPU against (a) the recording of the reference (tests/golden/sac_small.npz: same
+indices from CPython's `random.sample`, same reparameterisation noise) and (b) oracle/sac_oracle.py on a
+cfg3-shaped problem (obs 17, 6 actions, [256, 256] networks, batch 256).  Tolerance 1e-4 relative (fp32,
+different summation order), as BASELINE.json's north_star states."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle.pearl_oracle import flat
+from oracle.sac_oracle import OracleSAC
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, what, rtol=1e-4, atol=2e-6):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(float(np.abs(b).max()), 1e-30)
+    err = float(np.abs(a - b).max())
+    assert err <= atol + rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+def _fill(buf, st, ac, rw, ns, term):
+    n = st.shape[0]
+    buf.push_batch(torch.from_numpy(st), torch.from_numpy(ac), torch.from_numpy(rw), torch.from_numpy(ns),
+                   torch.from_numpy(term), torch.zeros(n, dtype=torch.bool))
+
+
+def test_sac_matches_reference_recording():
+    import pearl_b200
+    fx = np.load(os.path.join(GOLDEN, "sac_small.npz"))
+    R, B = int(fx["rounds"]), int(fx["batch"])
+    buf = pearl_b200.B200ReplayBuffer(int(fx["n"]))
+    buf.is_action_continuous = True
+    _fill(buf, fx["state"], fx["action"], fx["reward"], fx["next_state"], fx["terminated"])
+    pl = pearl_b200.B200ContinuousSoftActorCritic(
+        state_dim=int(fx["obs"]), low=fx["low"], high=fx["high"], actor_hidden_dims=[32, 32], critic_hidden_dims=[32, 32],
+        training_rounds=R, batch_size=B, actor_learning_rate=float(fx["actor_lr"]), critic_learning_rate=float(fx["critic_lr"]),
+        critic_soft_update_tau=float(fx["tau"]), discount_factor=float(fx["gamma"]), entropy_autotune=True)
+    pl.load_parameters(fx["init_actor"], fx["init_q1"], fx["init_q2"], fx["init_q1t"], fx["init_q2t"])
+    random.seed(41)                                   # the state the recording sampled from
+    trace = {}
+    noise = torch.from_numpy(fx["noise"]).view(R, 2, B, -1)
+    rep = pl.learn(buf, noise=noise, trace=trace)
+    assert trace["idx"].tolist() == fx["idx"].tolist()            # bit-exact sampling
+    _close(rep["actor_loss"], fx["actor_loss"], "actor_loss")
+    _close(rep["critic_loss"], fx["critic_loss"], "critic_loss")
+    _close(rep["entropy_coef"], fx["entropy_loss"], "entropy loss")
+    pc = pl.critic_params.numel() // 2
+    _close(pl.actor_params.cpu().numpy(), fx["actor_after"], "actor")
+    _close(pl.critic_params[:pc].cpu().numpy(), fx["q1_after"], "q1")
+    _close(pl.critic_params[pc:].cpu().numpy(), fx["q2_after"], "q2")
+    _close(pl.critic_target_params[:pc].cpu().numpy(), fx["q1t_after"], "q1 target")
+    _close(pl.critic_target_params[pc:].cpu().numpy(), fx["q2t_after"], "q2 target")
+    _close(pl._log_entropy[:1].cpu().numpy(), fx["log_alpha_after"], "log_alpha")
+    # the python RNG advanced exactly as R calls of random.sample would have
+    after = random.getstate()
+    random.seed(41)
+    for _ in range(R):
+        random.sample(range(int(fx["n"])), B)
+    assert random.getstate() == after
+
+
+@pytest.mark.parametrize("autotune", [True, False])
+def test_sac_cfg3_shape_against_oracle(autotune):
+    """BASELINE configs[3] shape: obs 17, act 6, hidden [256, 256], batch 256."""
+    import pearl_b200
+    torch.manual_seed(5)
+    torch.set_num_threads(4)
+    obs, act, n, B, R = 17, 6, 2000, 256, 5
+    rng = np.random.Generator(np.random.PCG64(3))
+    q8 = lambda x: (np.rint(x * 256) / 256).astype(np.float32)
+    low, high = -np.ones(act, dtype=np.float32), np.ones(act, dtype=np.float32)
+    st, ns, rw = q8(rng.standard_normal((n, obs))), q8(rng.standard_normal((n, obs))), q8(rng.standard_normal(n))
+    ac = q8(rng.uniform(low, high, size=(n, act)))
+    term = rng.random(n) < 0.05
+    orc = OracleSAC(obs, act, (256, 256), (256, 256), low, high, actor_lr=3e-4, critic_lr=3e-4, gamma=0.99, tau=0.005,
+                    entropy_coef=0.2, autotune=autotune)
+    for m in [orc.actor] + orc.q:                          # xavier + 0.01 biases like the reference
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Linear):
+                torch.nn.init.xavier_uniform_(mod.weight)
+                mod.bias.data.fill_(0.01)
+    for i in range(2):
+        orc.qt[i].load_state_dict(orc.q[i].state_dict())
+    buf = pearl_b200.B200ReplayBuffer(n)
+    buf.is_action_continuous = True
+    _fill(buf, st, ac, rw, ns, term)
+    pl = pearl_b200.B200ContinuousSoftActorCritic(
+        state_dim=obs, low=low, high=high, actor_hidden_dims=[256, 256], critic_hidden_dims=[256, 256], training_rounds=R,
+        batch_size=B, actor_learning_rate=3e-4, critic_learning_rate=3e-4, critic_soft_update_tau=0.005, discount_factor=0.99,
+        entropy_coef=0.2, entropy_autotune=autotune)
+    pl.load_parameters(flat(orc.actor), flat(orc.q[0]), flat(orc.q[1]))
+    noise = torch.randn(R, 2, B, act)
+    random.seed(77)
+    trace = {}
+    rep = pl.learn(buf, noise=noise, trace=trace)
+    random.seed(77)
+    al, cl = [], []
+    for r in range(R):
+        idx = random.sample(range(n), B)
+        assert idx == trace["idx"][r].tolist()
+        t = lambda x: torch.from_numpy(x[idx])
+        out = orc.learn_batch(dict(state=t(st), action=t(ac), reward=t(rw), next_state=t(ns), terminated=t(term)),
+                              noise[r, 0], noise[r, 1])
+        al.append(out["actor_loss"])
+        cl.append(out["critic_loss"])
+    _close(rep["actor_loss"], al, "actor_loss")
+    _close(rep["critic_loss"], cl, "critic_loss")
+    pc = pl.critic_params.numel() // 2
+    _close(pl.actor_params.cpu().numpy(), flat(orc.actor).numpy(), "actor")
+    _close(pl.critic_params[:pc].cpu().numpy(), flat(orc.q[0]).numpy(), "q1")
+    _close(pl.critic_params[pc:].cpu().numpy(), flat(orc.q[1]).numpy(), "q2")
+    _close(pl.critic_target_params[:pc].cpu().numpy(), flat(orc.qt[0]).numpy(), "q1 target")
+    _close(pl.critic_target_params[pc:].cpu().numpy(), flat(orc.qt[1]).numpy(), "q2 target")
+    _close([pl.entropy_coef], [float(orc.alpha)], "entropy coefficient")
+
+
+def test_sac_rejects_bad_inputs():
+    import pearl_b200
+    buf = pearl_b200.B200ReplayBuffer(16)
+    pl = pearl_b200.B200ContinuousSoftActorCritic(state_dim=4, low=[-1.0, -1.0], high=[1.0, 1.0], actor_hidden_dims=[8, 8],
+                                                  critic_hidden_dims=[8, 8], training_rounds=1, batch_size=4)
+    assert pl.learn(buf) == {}                              # empty buffer: nothing to do (policy_learner.py:171-173)
+    with pytest.raises(NotImplementedError):
+        pearl_b200.B200ContinuousSoftActorCritic(state_dim=4, low=[-1.0], high=[1.0], actor_hidden_dims=[8], critic_hidden_dims=[8, 8])
+    with pytest.raises(ValueError):
+        pearl_b200.B200ContinuousSoftActorCritic(state_dim=4, actor_hidden_dims=[8, 8], critic_hidden_dims=[8, 8])
