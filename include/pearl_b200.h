@@ -348,6 +348,43 @@ int64_t prl_sac_adam_step(const prl_sac *sac);
 int prl_sac_learn(prl_sac *sac, prl_buf *buf, int rounds, int batch, const float *noise_dev,
                   float *out_actor_loss_dev, float *out_critic_loss_dev, float *out_entropy_loss_dev,
                   int32_t *out_logical_dev, void *stream);
+/* The round is a fixed sequence of kernel launches replayed from a CUDA graph (default on; 0 = plain
+ * stream launches, e.g. under a profiler).  prl_sac_last_launches: kernels launched by the last learn. */
+int prl_sac_set_graph(prl_sac *sac, int enable);
+int64_t prl_sac_last_launches(const prl_sac *sac);
+
+/* ---- PPO learner ------------------------------------------------------------------------------
+ * Replaces ProximalPolicyOptimization.learn (policy_learners/sequential_decision_making/ppo.py:195-293):
+ * prl_ppo_preprocess = preprocess_replay_buffer (state values, taken-action probabilities under the current
+ * policy, GAE and truncated lambda returns over the whole rollout, time order), prl_ppo_learn =
+ * PolicyLearner.learn (policy_learner.py:162-204) x ActorCriticBase.learn_batch (actor_critic_base.py:309-349):
+ * clipped-surrogate actor step (ppo.py:152-184; VanillaActorNetwork softmax policy) then the state-value critic
+ * step (critic_utils.py:139-167).  Flat parameter layouts (row-major [out][in]):
+ *   actor : W1[h1][obs] b1 W2[h2][h1] b2 W3[A][h2] b3      critic: W1[c1][obs] b1 W2[c2][c1] b2 W3[1][c2] b3 */
+typedef struct prl_ppo_cfg {
+    int32_t obs_dim, n_actions, actor_h1, actor_h2, critic_h1, critic_h2;
+    int32_t max_batch, max_rounds;
+    int64_t max_rollout;
+    double actor_lr, critic_lr, beta1, beta2, eps, weight_decay, gamma, lam, epsilon, entropy_bonus;
+} prl_ppo_cfg;
+typedef struct prl_ppo prl_ppo;
+int64_t prl_ppo_actor_param_count(const prl_ppo_cfg *cfg);
+int64_t prl_ppo_critic_param_count(const prl_ppo_cfg *cfg);
+int64_t prl_ppo_workspace_bytes(const prl_ppo_cfg *cfg);
+int prl_ppo_create(prl_ppo **out, const prl_ppo_cfg *cfg, float *actor_w, float *actor_m, float *actor_v, float *actor_vmax,
+                   float *critic_w, float *critic_m, float *critic_v, float *critic_vmax, int64_t adam_step,
+                   void *workspace);
+int prl_ppo_destroy(prl_ppo *ppo);
+int64_t prl_ppo_adam_step(const prl_ppo *ppo);
+int prl_ppo_set_graph(prl_ppo *ppo, int enable);
+int64_t prl_ppo_last_launches(const prl_ppo *ppo);
+/* outputs: device f32[len(buf)] each, index 0 = oldest stored transition */
+int prl_ppo_preprocess(prl_ppo *ppo, prl_buf *buf, float *out_values_dev, float *out_action_probs_dev,
+                       float *out_gae_dev, float *out_lam_return_dev, void *stream);
+/* gae / lam_return / action_probs: the arrays prl_ppo_preprocess produced; out_*_loss: device f32[rounds] */
+int prl_ppo_learn(prl_ppo *ppo, prl_buf *buf, int rounds, int batch, const float *gae_dev,
+                  const float *lam_return_dev, const float *action_probs_dev, float *out_actor_loss_dev,
+                  float *out_critic_loss_dev, int32_t *out_logical_dev, void *stream);
 
 /* Device timing of the persistent learner kernel alone (CUDA events recorded on
  * the launch stream around the kernel); used by bench.py for the roofline line.

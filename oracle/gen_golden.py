@@ -272,6 +272,62 @@ def gen_ppo_gae_golden():
     print("ppo_gae.npz:", n, "transitions; gae[0..2] =", gae[:3])
 
 
+def gen_ppo_learn_golden():
+    """PPO end to end: PearlAgent(ProximalPolicyOptimization, PPOReplayBuffer).learn() (preprocess + clipped-surrogate
+    actor steps + critic steps) with the sampled indices recorded."""
+    from pearl.policy_learners.sequential_decision_making.ppo import PPOReplayBuffer, ProximalPolicyOptimization
+    torch.manual_seed(53)
+    random.seed(53)
+    torch.set_num_threads(1)
+    obs, n_act, n, B, rounds = 10, 5, 400, 48, 6
+    space = DiscreteActionSpace(actions=list(torch.arange(n_act).view(-1, 1)))
+    hp = dict(actor_lr=3e-4, critic_lr=1e-3, epsilon=0.2, gamma=0.97, lam=0.9, beta=0.02)
+    pl = ProximalPolicyOptimization(state_dim=obs, action_space=space, actor_hidden_dims=[32, 32], critic_hidden_dims=[32, 32],
+                                    training_rounds=rounds, batch_size=B, epsilon=hp["epsilon"], discount_factor=hp["gamma"],
+                                    trace_decay_param=hp["lam"], entropy_bonus_scaling=hp["beta"],
+                                    actor_learning_rate=hp["actor_lr"], critic_learning_rate=hp["critic_lr"],
+                                    action_representation_module=OneHotActionTensorRepresentationModule(n_act))
+    buf = PPOReplayBuffer(n)
+    agent = PearlAgent(policy_learner=pl, replay_buffer=buf, device_id=-1)
+    rng = np.random.Generator(np.random.PCG64(15))
+    q8 = lambda x: (np.rint(x * 256) / 256).astype(np.float32)
+    states = q8(rng.standard_normal((n + 1, obs)))
+    rewards = q8(rng.standard_normal(n))
+    actions = rng.integers(0, n_act, size=n).astype(np.int64)
+    terminated = np.zeros(n, dtype=bool); truncated = np.zeros(n, dtype=bool)
+    terminated[39::40] = True
+    truncated[[100, 333]] = True
+    for i in range(n):
+        buf.push(state=torch.from_numpy(states[i]), action=torch.tensor(int(actions[i])), reward=float(rewards[i]),
+                 terminated=bool(terminated[i]), truncated=bool(truncated[i]), curr_available_actions=space,
+                 next_state=torch.from_numpy(states[i + 1]), next_available_actions=space, max_number_actions=n_act)
+    fl = lambda m: np.concatenate([p.detach().numpy().ravel() for p in m.parameters()])
+    init_actor, init_critic = fl(pl._actor), fl(pl._critic)
+    idxs, pre = [], {}
+    orig_sample = buf.sample
+
+    def sample_spy(k):
+        if not pre:     # the agent clears an on-policy buffer after learning: record the preprocessing results now
+            pre["gae"] = np.asarray([float(t.gae) for t in buf.memory], dtype=np.float32)
+            pre["lam"] = np.asarray([float(t.lam_return) for t in buf.memory], dtype=np.float32)
+            pre["apo"] = np.asarray([float(t.action_probs) for t in buf.memory], dtype=np.float32)
+        pos = {id(t): j for j, t in enumerate(buf.memory)}
+        stt = random.getstate()
+        idxs.append([pos[id(t)] for t in random.sample(buf.memory, k)])
+        random.setstate(stt)
+        return orig_sample(k)
+    buf.sample = sample_spy
+    rep = agent.learn()
+    gae, lam, apo = pre["gae"], pre["lam"], pre["apo"]
+    assert gae.shape == (n,)
+    np.savez_compressed(os.path.join(GOLDEN, "ppo_small.npz"), obs=obs, n_act=n_act, n=n, batch=B, rounds=rounds, **hp,
+                        states=states, action=actions, reward=rewards, terminated=terminated, truncated=truncated,
+                        idx=np.asarray(idxs, dtype=np.int32), gae=gae, lam_return=lam, action_probs=apo,
+                        actor_loss=np.asarray(rep["actor_loss"]), critic_loss=np.asarray(rep["critic_loss"]),
+                        init_actor=init_actor, init_critic=init_critic, actor_after=fl(pl._actor), critic_after=fl(pl._critic))
+    print("ppo_small.npz: actor_loss", rep["actor_loss"][:2], "critic_loss", rep["critic_loss"][:2])
+
+
 def gen_sac_golden():
     """Continuous SAC: PearlAgent(ContinuousSoftActorCritic, BasicReplayBuffer).learn() with the two
     Normal.rsample noise draws per step recorded (torch.distributions.normal._standard_normal)."""
@@ -339,9 +395,11 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ppo":
         gen_ppo_gae_golden()
+        gen_ppo_learn_golden()
         sys.exit(0)
     gen_random_sample_vectors()
     gen_ppo_gae_golden()
+    gen_ppo_learn_golden()
     gen_sac_golden()
     # small everything; ring wraps (n_push > capacity); pool branch (n=48 <= 85)
     run_dqn_case("dqn_tiny", obs=8, n_act=4, hidden=(16, 16), capacity=48, n_push=70, batch=16,

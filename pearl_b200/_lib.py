@@ -41,6 +41,14 @@ class SacCfg(C.Structure):
                 ("tau", C.c_double)]
 
 
+class PpoCfg(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("n_actions", C.c_int32), ("actor_h1", C.c_int32), ("actor_h2", C.c_int32),
+                ("critic_h1", C.c_int32), ("critic_h2", C.c_int32), ("max_batch", C.c_int32), ("max_rounds", C.c_int32),
+                ("max_rollout", C.c_int64), ("actor_lr", C.c_double), ("critic_lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double), ("gamma", C.c_double),
+                ("lam", C.c_double), ("epsilon", C.c_double), ("entropy_bonus", C.c_double)]
+
+
 class DqnCfg(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("n_actions", C.c_int32), ("hidden1", C.c_int32),
                 ("hidden2", C.c_int32), ("double_dqn", C.c_int32), ("target_update_freq", C.c_int32),
@@ -103,7 +111,19 @@ _SIGNATURES = {
     "prl_sac_create": (C.c_int, [C.POINTER(_P), C.POINTER(SacCfg)] + [_P] * 13 + [C.c_int64, _P]),
     "prl_sac_destroy": (C.c_int, [_P]),
     "prl_sac_adam_step": (C.c_int64, [_P]),
+    "prl_sac_set_graph": (C.c_int, [_P, C.c_int]),
+    "prl_sac_last_launches": (C.c_int64, [_P]),
     "prl_sac_learn": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "prl_ppo_actor_param_count": (C.c_int64, [C.POINTER(PpoCfg)]),
+    "prl_ppo_critic_param_count": (C.c_int64, [C.POINTER(PpoCfg)]),
+    "prl_ppo_workspace_bytes": (C.c_int64, [C.POINTER(PpoCfg)]),
+    "prl_ppo_create": (C.c_int, [C.POINTER(_P), C.POINTER(PpoCfg)] + [_P] * 8 + [C.c_int64, _P]),
+    "prl_ppo_destroy": (C.c_int, [_P]),
+    "prl_ppo_adam_step": (C.c_int64, [_P]),
+    "prl_ppo_set_graph": (C.c_int, [_P, C.c_int]),
+    "prl_ppo_last_launches": (C.c_int64, [_P]),
+    "prl_ppo_preprocess": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "prl_ppo_learn": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "prl_dqn_set_timing": (C.c_int, [_P, C.c_int]),
     "prl_dqn_set_profile": (C.c_int, [_P, _P]),
     "prl_dqn_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),

@@ -18,115 +18,27 @@
 #include <new>
 
 #include "common.cuh"
-#include "sampler.cuh"
+#include "gemm.cuh"
 
 using namespace prl;
 
 namespace {
 
-constexpr int TB = 64;   // output tile (both dimensions)
-constexpr int TK = 16;   // contraction chunk
-constexpr int GT = 256;  // threads
-
-// A matrix of `rows` x features; features [0, split) come from p1, [split, ..) from p2 (state || action),
-// and feature index == ones_at reads as 1.0 (bias column for weight gradients).
-struct Mat {
-    const float *p1; int ld1; int split;
-    const float *p2; int ld2;
-    int ones_at;
-    long long net_stride1, net_stride2;   // added per blockIdx.z
-    __device__ __forceinline__ float at(int row, int f, int z) const {
-        if (f == ones_at) return 1.f;
-        if (f < split) return __ldg(p1 + z * net_stride1 + (size_t)row * ld1 + f);
-        return __ldg(p2 + z * net_stride2 + (size_t)row * ld2 + (f - split));
-    }
+// per-call pointers the captured round reads through (the graph itself never changes between calls)
+struct SacCall {
+    const float *noise;      // [rounds][2][B][A]
+    const int32_t *slots;    // [rounds][B]
+    float *out_actor, *out_critic, *out_entropy;
 };
-__host__ inline Mat mat(const float *p, int ld, long long net_stride = 0) {
-    Mat m; m.p1 = p; m.ld1 = ld; m.split = 1 << 30; m.p2 = nullptr; m.ld2 = 0; m.ones_at = -1; m.net_stride1 = net_stride; m.net_stride2 = 0;
-    return m;
-}
-__host__ inline Mat mat2(const float *p1, int ld1, int split, const float *p2, int ld2, long long s1 = 0, long long s2 = 0) {
-    Mat m = mat(p1, ld1, s1); m.split = split; m.p2 = p2; m.ld2 = ld2; m.net_stride2 = s2;
-    return m;
-}
-
-struct GemmArgs {
-    Mat A, B;            // operand (out index, contraction index): a_rows_are_out ? A.at(out, c) : A.at(c, out)
-    int a_rows_are_out, b_rows_are_out;
-    int Mo, No, Kc;      // C[Mo x No] = sum_c A(i, c) * B(j, c)
-    float *C; int ldc; long long c_net_stride;
-    float *C_tail; int tail_col; long long tail_net_stride;   // column `tail_col` of C goes to C_tail[row] (bias gradient)
-    const float *bias; long long bias_net_stride;             // + bias[j]
-    int relu;                                                   // max(., 0)
-    const float *mask; int ldm; long long mask_net_stride;     // *= (mask[i][j] > 0)
-    int accumulate;                                             // C += (before mask)
-};
-
-__global__ void __launch_bounds__(GT) k_gemm(const GemmArgs g) {
-    __shared__ float As[TK][TB + 4], Bs[TK][TB + 4];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, z = blockIdx.z;
-    const int i0 = blockIdx.x * TB, j0 = blockIdx.y * TB;
-    float acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
-    for (int c0 = 0; c0 < g.Kc; c0 += TK) {
-        // stage A(i0.., c0..) and B(j0.., c0..) as [contraction][out]
-        for (int e = tid; e < TB * TK; e += GT) {
-            int o, c;
-            if (g.a_rows_are_out) { o = e / TK; c = e - o * TK; } else { c = e / TB; o = e - c * TB; }
-            float v = 0.f;
-            if (i0 + o < g.Mo && c0 + c < g.Kc) v = g.a_rows_are_out ? g.A.at(i0 + o, c0 + c, z) : g.A.at(c0 + c, i0 + o, z);
-            As[c][o] = v;
-        }
-        for (int e = tid; e < TB * TK; e += GT) {
-            int o, c;
-            if (g.b_rows_are_out) { o = e / TK; c = e - o * TK; } else { c = e / TB; o = e - c * TB; }
-            float v = 0.f;
-            if (j0 + o < g.No && c0 + c < g.Kc) v = g.b_rows_are_out ? g.B.at(j0 + o, c0 + c, z) : g.B.at(c0 + c, j0 + o, z);
-            Bs[c][o] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < TK; c++) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[c][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[c][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const int i = i0 + ty * 4 + p;
-        if (i >= g.Mo) continue;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int j = j0 + tx * 4 + q;
-            if (j >= g.No) continue;
-            float v = acc[p][q];
-            if (g.C_tail && j == g.tail_col) { g.C_tail[z * g.tail_net_stride + i] = v; continue; }
-            float *dst = g.C + z * g.c_net_stride + (size_t)i * g.ldc + j;
-            if (g.bias) v += __ldg(g.bias + z * g.bias_net_stride + j);
-            if (g.accumulate) v += *dst;
-            if (g.relu) v = fmaxf(v, 0.f);
-            if (g.mask && !(__ldg(g.mask + z * g.mask_net_stride + (size_t)i * g.ldm + j) > 0.f)) v = 0.f;
-            *dst = v;
-        }
-    }
-}
 
 // ------------------------------------------------------------------ elementwise pieces
 // batch rows of one round from the replay ring
-__global__ void k_sac_gather(const uint32_t *__restrict__ records, prl_buf_layout L, int obs, int act, const int32_t *__restrict__ slots,
-                             int B, float *__restrict__ S, float *__restrict__ A, float *__restrict__ R, float *__restrict__ S2,
-                             float *__restrict__ T) {
+__global__ void k_sac_gather(const uint32_t *__restrict__ records, prl_buf_layout L, int obs, int act, const SacCall *__restrict__ call,
+                             const int *__restrict__ round_idx, int B, float *__restrict__ S, float *__restrict__ A, float *__restrict__ R,
+                             float *__restrict__ S2, float *__restrict__ T) {
     const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= B) return;
+    const int32_t *slots = call->slots + (size_t)(*round_idx) * B;
     const uint32_t *r = records + (size_t)slots[w] * L.record_words;
     for (int p = lane; p < obs; p += 32) {
         S[(size_t)w * obs + p] = __uint_as_float(r[L.off_state + p]);
@@ -137,11 +49,12 @@ __global__ void k_sac_gather(const uint32_t *__restrict__ records, prl_buf_layou
 }
 
 // GaussianActorNetwork.sample_action (actor_networks.py:551-591) with the rsample noise given
-__global__ void k_sac_sample(int B, int A, const float *__restrict__ mean, const float *__restrict__ z, const float *__restrict__ noise,
-                             const float *__restrict__ low, const float *__restrict__ high, float *__restrict__ action,
-                             float *__restrict__ na_out, float *__restrict__ std_out, float *__restrict__ logp) {
+__global__ void k_sac_sample(int B, int A, const float *__restrict__ mean, const float *__restrict__ z, const SacCall *__restrict__ call,
+                             const int *__restrict__ round_idx, int which, const float *__restrict__ low, const float *__restrict__ high,
+                             float *__restrict__ action, float *__restrict__ na_out, float *__restrict__ std_out, float *__restrict__ logp) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const float *noise = call->noise + (size_t)(2 * (*round_idx) + which) * B * A;
     float lp = 0.f;
     for (int d = 0; d < A; d++) {
         const size_t o = (size_t)b * A + d;
@@ -162,7 +75,7 @@ __global__ void k_sac_sample(int B, int A, const float *__restrict__ mean, const
 
 // actor loss = mean(alpha * logp - min(q1, q2)); routes -1/B to the smaller critic
 __global__ void k_sac_actor_loss(int B, const float *__restrict__ q, const float *__restrict__ logp, const float *__restrict__ alpha,
-                                 float *__restrict__ dq, float *__restrict__ out_loss) {
+                                 float *__restrict__ dq, const SacCall *__restrict__ call, const int *__restrict__ round_idx) {
     __shared__ float red[256];
     float s = 0.f;
     const float al = *alpha, ib = 1.f / (float)B;
@@ -176,27 +89,18 @@ __global__ void k_sac_actor_loss(int B, const float *__restrict__ q, const float
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) *out_loss = red[0] * ib;
-}
-
-// dC2[z][m][j] = dq[z][m] * W3[z][j] * (c2 > 0)      (backward through the scalar head)
-__global__ void k_head_bwd(int B, int H, const float *__restrict__ dq, const float *__restrict__ w3, long long w_net_stride,
-                           const float *__restrict__ c2, float *__restrict__ dc2) {
-    const int z = blockIdx.z;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B * H) return;
-    const int m = e / H, j = e - m * H;
-    const size_t o = (size_t)z * B * H + e;
-    dc2[o] = (c2[o] > 0.f) ? dq[z * B + m] * __ldg(w3 + z * w_net_stride + j) : 0.f;
+    if (threadIdx.x == 0) call->out_actor[*round_idx] = red[0] * ib;
 }
 
 // gradients of the actor loss w.r.t. the two heads (mean, pre-tanh log-std z)
 __global__ void k_sac_head_grads(int B, int A, const float *__restrict__ da /* [2][B][A] from both critics */,
-                                 const float *__restrict__ na, const float *__restrict__ sd, const float *__restrict__ noise,
-                                 const float *__restrict__ z, const float *__restrict__ low, const float *__restrict__ high,
-                                 const float *__restrict__ alpha, float *__restrict__ dmean, float *__restrict__ dz) {
+                                 const float *__restrict__ na, const float *__restrict__ sd, const SacCall *__restrict__ call,
+                                 const int *__restrict__ round_idx, const float *__restrict__ z, const float *__restrict__ low,
+                                 const float *__restrict__ high, const float *__restrict__ alpha, float *__restrict__ dmean,
+                                 float *__restrict__ dz) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B * A) return;
+    const float *noise = call->noise + (size_t)(2 * (*round_idx)) * B * A;
     const int d = e % A;
     const float al_b = *alpha / (float)B;
     const float lo = low[d], hi = high[d], bound = (hi - lo) * 0.5f;
@@ -220,7 +124,7 @@ __global__ void k_sac_target(int B, const float *__restrict__ qt, const float *_
     y[b] = __fadd_rn(__fmul_rn(__fmul_rn(nq, gamma), 1.f - term[b]), rew[b]);
 }
 __global__ void k_sac_critic_loss(int B, const float *__restrict__ q, const float *__restrict__ y, float *__restrict__ dq,
-                                  float *__restrict__ out_loss) {
+                                  const SacCall *__restrict__ call, const int *__restrict__ round_idx) {
     __shared__ float red[256];
     float s = 0.f;
     const float ib = 1.f / (float)B;
@@ -233,35 +137,18 @@ __global__ void k_sac_critic_loss(int B, const float *__restrict__ q, const floa
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
-    if (threadIdx.x == 0) *out_loss = red[0] * ib * 0.5f;
+    if (threadIdx.x == 0) call->out_critic[*round_idx] = red[0] * ib * 0.5f;
 }
 
-struct AdamHp { float decay, omb1, beta2, omb2, eps; };
-__device__ __forceinline__ float adamw1(float w, float &m, float &v, float &x, float g, const AdamHp &h, float step_size, float bc2s) {
-    float p = __fmul_rn(w, h.decay);
-    m = fmaf(h.omb1, g - m, m);
-    v = __fadd_rn(__fmul_rn(v, h.beta2), __fmul_rn(__fmul_rn(h.omb2, g), g));
-    x = fmaxf(x, v);
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(x), bc2s), h.eps);
-    return __fadd_rn(p, __fdiv_rn(__fmul_rn(-step_size, m), denom));
-}
-// AdamW(amsgrad) over a flat vector; optional soft update of a target vector with the NEW parameters
-__global__ void k_adamw(int n, float *__restrict__ w, float *__restrict__ m, float *__restrict__ v, float *__restrict__ vmax,
-                        const float *__restrict__ grad, AdamHp h, const float2 *__restrict__ scal, const int *__restrict__ round_idx,
-                        float *__restrict__ target, float tau, float omtau) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float2 sc = scal[*round_idx];
-    float mm = m[i], vv = v[i], xx = vmax[i];
-    const float p = adamw1(w[i], mm, vv, xx, grad[i], h, sc.x, sc.y);
-    w[i] = p; m[i] = mm; v[i] = vv; vmax[i] = xx;
-    if (target) target[i] = __fadd_rn(__fmul_rn(tau, p), __fmul_rn(omtau, target[i]));
-}
 // entropy coefficient: loss = mean(-exp(log_alpha) * (logp + target_entropy)); AdamW on the scalar; alpha = exp(log_alpha)
 __global__ void k_sac_alpha(int B, const float *__restrict__ logp, float target_entropy, float *__restrict__ log_alpha /* [4]: w m v vmax */,
                             float *__restrict__ alpha, AdamHp h, const float2 *__restrict__ scal, const int *__restrict__ round_idx,
-                            float *__restrict__ out_loss) {
+                            const SacCall *__restrict__ call, int autotune) {
     __shared__ float red[256];
+    if (!autotune) {                       // fixed entropy coefficient: only the round counter advances
+        if (threadIdx.x == 0) *const_cast<int *>(round_idx) += 1;
+        return;
+    }
     float s = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) s += logp[b] + target_entropy;
     red[threadIdx.x] = s;
@@ -269,18 +156,16 @@ __global__ void k_sac_alpha(int B, const float *__restrict__ logp, float target_
     for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
     if (threadIdx.x == 0) {
         const float mean = red[0] / (float)B, ea = expf(log_alpha[0]);
-        *out_loss = -ea * mean;
+        call->out_entropy[*round_idx] = -ea * mean;
         const float g = -ea * mean;                 // d/dlog_alpha
         const float2 sc = scal[*round_idx];
         float mm = log_alpha[1], vv = log_alpha[2], xx = log_alpha[3];
         const float p = adamw1(log_alpha[0], mm, vv, xx, g, h, sc.x, sc.y);
         log_alpha[0] = p; log_alpha[1] = mm; log_alpha[2] = vv; log_alpha[3] = xx;
         *alpha = expf(p);
+        *const_cast<int *>(round_idx) += 1;
     }
 }
-__global__ void k_bump(int *round_idx) { *round_idx += 1; }
-__global__ void k_set(int *p, int v) { *p = v; }
-// Philox-free fallback noise is not provided: the caller passes the noise (device) explicitly.
 
 }  // namespace
 
@@ -301,11 +186,17 @@ struct prl_sac {
         *dh2, *dh1, *y, *g_actor, *g_critic;
     int32_t *slots, *logical;
     float2 *scal_a, *scal_c;
+    SacCall *call;
     int *round_idx;
+    bool use_graph;
+    cudaGraphExec_t graph_exec;
+    int graph_batch;
+    const uint32_t *graph_buf;
+    int launches_per_round;
     float2 *scal_host[2];
     cudaEvent_t scal_done[2];
     int scal_next;
-    int last_launches;
+    int64_t last_launches;
 };
 
 static int64_t al64(int64_t x) { return (x + 255) / 256 * 256; }
@@ -358,7 +249,7 @@ static SacWs sac_ws(const prl_sac_cfg *c, int Pa, int Pc) {
     add(B * A); add(B * A); add(B * c->actor_h2); add(B * c->actor_h1); add(B);          // dmean dz dh2 dh1 y
     add(Pa); add(2 * (int64_t)Pc);                                                        // g_actor g_critic
     add((int64_t)c->max_rounds * B); add((int64_t)c->max_rounds * B);                    // slots logical (int32)
-    add(2 * (int64_t)c->max_rounds); add(2 * (int64_t)c->max_rounds); add(64);           // scal_a scal_c round_idx
+    add(4 * (int64_t)c->max_rounds + 64);                                                 // scal_a | scal_c | call | round_idx
     w.total = o;
     return w;
 }
@@ -392,11 +283,13 @@ extern "C" int prl_sac_create(prl_sac **out, const prl_sac_cfg *cfg, float *acto
     int k = 0;
     for (auto p : f) *p = (float *)(b + w.off[k++]);
     s->slots = (int32_t *)(b + w.off[k++]); s->logical = (int32_t *)(b + w.off[k++]);
-    s->scal_a = (float2 *)(b + w.off[k++]); s->scal_c = (float2 *)(b + w.off[k++]); s->round_idx = (int *)(b + w.off[k++]);
-    s->scal_next = 0;
+    s->scal_a = (float2 *)(b + w.off[k++]); s->scal_c = s->scal_a + cfg->max_rounds;
+    s->call = (SacCall *)(s->scal_c + cfg->max_rounds); s->round_idx = (int *)(s->call + 1);
+    s->scal_next = 0; s->use_graph = true; s->graph_exec = nullptr; s->graph_batch = 0; s->graph_buf = nullptr; s->last_launches = 0;
+    static_assert(sizeof(SacCall) + 4 <= 64 * 4, "call block fits the reserved tail");
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-        e = cudaHostAlloc((void **)&s->scal_host[i], (size_t)cfg->max_rounds * 16, cudaHostAllocDefault);
+        e = cudaHostAlloc((void **)&s->scal_host[i], (size_t)cfg->max_rounds * 16 + 256, cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->scal_done[i], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) { delete s; return fail(PRL_ECUDA, "prl_sac_create: %s", cudaGetErrorString(e)); }
@@ -406,60 +299,87 @@ extern "C" int prl_sac_create(prl_sac **out, const prl_sac_cfg *cfg, float *acto
 extern "C" int prl_sac_destroy(prl_sac *s) {
     if (!s) return PRL_OK;
     for (int i = 0; i < 2; i++) { cudaEventSynchronize(s->scal_done[i]); cudaEventDestroy(s->scal_done[i]); cudaFreeHost(s->scal_host[i]); }
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     delete s;
     return PRL_OK;
 }
 extern "C" int64_t prl_sac_adam_step(const prl_sac *s) { return s ? s->adam_step : -1; }
 
-namespace {
-
-struct Launcher {
-    cudaStream_t st;
-    int count = 0;
-    void gemm(GemmArgs g, int nets = 1) {
-        dim3 grid((g.Mo + TB - 1) / TB, (g.No + TB - 1) / TB, nets);
-        k_gemm<<<grid, GT, 0, st>>>(g);
-        count++;
+// one learner round, launched (or captured) on `st`; everything round-dependent is read on the device through
+// s->call / s->round_idx
+static int sac_round(prl_sac *s, prl_buf *buf, int B, cudaStream_t st) {
+    const prl_sac_cfg &c = s->cfg;
+    const int O = c.obs_dim, A = c.act_dim, D = O + A;
+    const int H1 = c.actor_h1, H2 = c.actor_h2, C1 = c.critic_h1, C2 = c.critic_h2;
+    const long long Pc = s->Pc;
+    AdamHp ha{(float)(1.0 - c.actor_lr * c.weight_decay), (float)(1.0 - c.beta1), (float)c.beta2, (float)(1.0 - c.beta2), (float)c.eps};
+    AdamHp hc{(float)(1.0 - c.critic_lr * c.weight_decay), (float)(1.0 - c.beta1), (float)c.beta2, (float)(1.0 - c.beta2), (float)c.eps};
+    GemmLauncher L; L.st = st;
+    const float *aw = s->actor, *cw = s->critic, *ct = s->critic_t;
+    const long long sC1 = (long long)B * C1, sC2 = (long long)B * C2;
+    auto actor_forward = [&](const float *X) {
+        L.fwd(mat(X, O), B, aw + s->aW1, O, 0, aw + s->ab1, 0, H1, O, true, s->h1, H1, 0);
+        L.fwd(mat(s->h1, H1), B, aw + s->aW2, H1, 0, aw + s->ab2, 0, H2, H1, true, s->h2, H2, 0);
+        L.fwd(mat(s->h2, H2), B, aw + s->aWmu, H2, 0, aw + s->abmu, 0, A, H2, false, s->mean, A, 0);
+        L.fwd(mat(s->h2, H2), B, aw + s->aWsd, H2, 0, aw + s->absd, 0, A, H2, false, s->z, A, 0);
+    };
+    auto critic_forward = [&](const float *net, const float *X, const float *Act, float *qout) {   // both critics (blockIdx.z)
+        L.fwd(mat2(X, O, O, Act, A), B, net + s->cW1, D, Pc, net + s->cb1, Pc, C1, D, true, s->c1, C1, sC1, 2);
+        L.fwd(mat(s->c1, C1, sC1), B, net + s->cW2, C1, Pc, net + s->cb2, Pc, C2, C1, true, s->c2, C2, sC2, 2);
+        L.fwd(mat(s->c2, C2, sC2), B, net + s->cW3, C2, Pc, net + s->cb3, Pc, 1, C2, false, qout, 1, B, 2);
+    };
+    const int eb = 256;
+    int small = 0;
+    k_sac_gather<<<(B * 32 + eb - 1) / eb, eb, 0, st>>>(buf->records, buf->lay, O, A, s->call, s->round_idx, B, s->S, s->A, s->R, s->S2, s->T);
+    // ---------------- actor step (actor_critic_base.py:333-343)
+    actor_forward(s->S);
+    k_sac_sample<<<(B + 127) / 128, 128, 0, st>>>(B, A, s->mean, s->z, s->call, s->round_idx, 0, s->low, s->high, s->act_s, s->na, s->sd, s->logp);
+    critic_forward(cw, s->S, s->act_s, s->q);
+    k_sac_actor_loss<<<1, 256, 0, st>>>(B, s->q, s->logp, s->alpha, s->dq, s->call, s->round_idx);
+    {   // dQ/d(action) through both critics
+        dim3 g2((B * C2 + eb - 1) / eb, 1, 2);
+        k_head_bwd<<<g2, eb, 0, st>>>(B, C2, s->dq, cw + s->cW3, Pc, s->c2, s->dc2);
+        L.bwd_x(s->dc2, C2, sC2, B, C2, cw + s->cW2, C1, Pc, 0, C1, s->dc1, C1, sC1, s->c1, C1, sC1, false, 2);
+        L.bwd_x(s->dc1, C1, sC1, B, C1, cw + s->cW1, D, Pc, O, A, s->da, A, (long long)B * A, nullptr, 0, 0, false, 2);
     }
-};
-GemmArgs base_args() {
-    GemmArgs g;
-    memset(&g, 0, sizeof(g));
-    g.tail_col = -1;
-    return g;
+    k_sac_head_grads<<<(B * A + eb - 1) / eb, eb, 0, st>>>(B, A, s->da, s->na, s->sd, s->call, s->round_idx, s->z, s->low, s->high, s->alpha,
+                                                         s->dmean, s->dz);
+    {   // actor backward
+        float *ga = s->g_actor;
+        L.bwd_w(s->dmean, A, 0, B, A, mat(s->h2, H2), H2, ga + s->aWmu, H2, 0, ga + s->abmu, 0);
+        L.bwd_w(s->dz, A, 0, B, A, mat(s->h2, H2), H2, ga + s->aWsd, H2, 0, ga + s->absd, 0);
+        L.bwd_x(s->dmean, A, 0, B, A, aw + s->aWmu, H2, 0, 0, H2, s->dh2, H2, 0, nullptr, 0, 0, false);
+        L.bwd_x(s->dz, A, 0, B, A, aw + s->aWsd, H2, 0, 0, H2, s->dh2, H2, 0, s->h2, H2, 0, true);
+        L.bwd_w(s->dh2, H2, 0, B, H2, mat(s->h1, H1), H1, ga + s->aW2, H1, 0, ga + s->ab2, 0);
+        L.bwd_x(s->dh2, H2, 0, B, H2, aw + s->aW2, H1, 0, 0, H1, s->dh1, H1, 0, s->h1, H1, 0, false);
+        L.bwd_w(s->dh1, H1, 0, B, H1, mat(s->S, O), O, ga + s->aW1, O, 0, ga + s->ab1, 0);
+        k_adamw<<<(s->Pa + eb - 1) / eb, eb, 0, st>>>(s->Pa, s->actor, s->actor_m, s->actor_v, s->actor_x, ga, ha, s->scal_a, s->round_idx, nullptr, 0.f, 0.f);
+    }
+    // ---------------- critic step with the UPDATED actor (:345-349; soft_actor_critic_continuous.py:155-205)
+    actor_forward(s->S2);
+    k_sac_sample<<<(B + 127) / 128, 128, 0, st>>>(B, A, s->mean, s->z, s->call, s->round_idx, 1, s->low, s->high, s->act_s, s->na, s->sd, s->logp2);
+    critic_forward(ct, s->S2, s->act_s, s->qt);
+    k_sac_target<<<(B + eb - 1) / eb, eb, 0, st>>>(B, s->qt, s->logp2, s->alpha, (float)c.gamma, s->T, s->R, s->y);
+    critic_forward(cw, s->S, s->A, s->q);
+    k_sac_critic_loss<<<1, 256, 0, st>>>(B, s->q, s->y, s->dq, s->call, s->round_idx);
+    {
+        float *gc = s->g_critic;
+        L.bwd_w(s->dq, 1, B, B, 1, mat(s->c2, C2, sC2), C2, gc + s->cW3, C2, Pc, gc + s->cb3, Pc, 2);
+        dim3 g2((B * C2 + eb - 1) / eb, 1, 2);
+        k_head_bwd<<<g2, eb, 0, st>>>(B, C2, s->dq, cw + s->cW3, Pc, s->c2, s->dc2);
+        L.bwd_w(s->dc2, C2, sC2, B, C2, mat(s->c1, C1, sC1), C1, gc + s->cW2, C1, Pc, gc + s->cb2, Pc, 2);
+        L.bwd_x(s->dc2, C2, sC2, B, C2, cw + s->cW2, C1, Pc, 0, C1, s->dc1, C1, sC1, s->c1, C1, sC1, false, 2);
+        L.bwd_w(s->dc1, C1, sC1, B, C1, mat2(s->S, O, O, s->A, A), D, gc + s->cW1, D, Pc, gc + s->cb1, Pc, 2);
+        const int n2p = 2 * s->Pc;
+        k_adamw<<<(n2p + eb - 1) / eb, eb, 0, st>>>(n2p, s->critic, s->critic_m, s->critic_v, s->critic_x, gc, hc, s->scal_c, s->round_idx,
+                                                  s->critic_t, (float)c.tau, (float)(1.0 - c.tau));
+    }
+    small = 12;
+    // ---------------- entropy coefficient (soft_actor_critic_continuous.py:134-147); also advances the round counter
+    k_sac_alpha<<<1, 256, 0, st>>>(B, s->logp, -(float)A, s->log_alpha, s->alpha, hc, s->scal_c, s->round_idx, s->call, c.autotune);
+    s->launches_per_round = L.count + small;
+    return PRL_OK;
 }
-// y[M x N] = act(x W^T + b)
-void fwd(Launcher &L, Mat X, int M, const float *W, int ldw, long long w_ns, const float *b, long long b_ns, int N, int K, bool relu,
-         float *Y, int ldy, long long y_ns, int nets = 1) {
-    GemmArgs g = base_args();
-    g.A = X; g.a_rows_are_out = 1;
-    g.B = mat(W, ldw, w_ns); g.b_rows_are_out = 1;
-    g.Mo = M; g.No = N; g.Kc = K; g.C = Y; g.ldc = ldy; g.c_net_stride = y_ns; g.bias = b; g.bias_net_stride = b_ns; g.relu = relu;
-    L.gemm(g, nets);
-}
-// dx[M x Kx] (+)= dy[M x N] W[:, col0 : col0 + Kx]  (* (mask > 0))
-void bwd_x(Launcher &L, const float *dY, int ldy, long long dy_ns, int M, int N, const float *W, int ldw, long long w_ns, int col0, int Kx,
-           float *dX, int ldx, long long dx_ns, const float *mask, int ldm, long long m_ns, bool accumulate, int nets = 1) {
-    GemmArgs g = base_args();
-    g.A = mat(dY, ldy, dy_ns); g.a_rows_are_out = 1;
-    g.B = mat(W + col0, ldw, w_ns); g.b_rows_are_out = 0;       // B(out = k, c = n) = W[n][col0 + k]
-    g.Mo = M; g.No = Kx; g.Kc = N; g.C = dX; g.ldc = ldx; g.c_net_stride = dx_ns;
-    g.mask = mask; g.ldm = ldm; g.mask_net_stride = m_ns; g.accumulate = accumulate;
-    L.gemm(g, nets);
-}
-// dW[N x K] = dy^T x ; db[N] = column sums of dy (x extended with a ones column)
-void bwd_w(Launcher &L, const float *dY, int ldy, long long dy_ns, int M, int N, Mat X, int K, float *dW, int ldw, long long dw_ns, float *db,
-           long long db_ns, int nets = 1) {
-    GemmArgs g = base_args();
-    g.A = mat(dY, ldy, dy_ns); g.a_rows_are_out = 0;            // A(out = n, c = m) = dy[m][n]
-    X.ones_at = K;
-    g.B = X; g.b_rows_are_out = 0;                              // B(out = k, c = m) = x[m][k]
-    g.Mo = N; g.No = K + 1; g.Kc = M; g.C = dW; g.ldc = ldw; g.c_net_stride = dw_ns;
-    g.C_tail = db; g.tail_col = K; g.tail_net_stride = db_ns;
-    L.gemm(g, nets);
-}
-
-}  // namespace
 
 extern "C" int prl_sac_learn(prl_sac *s, prl_buf *buf, int rounds, int batch, const float *noise_dev, float *out_actor_loss,
                              float *out_critic_loss, float *out_entropy_loss, int32_t *out_logical, void *stream_) {
@@ -471,91 +391,56 @@ extern "C" int prl_sac_learn(prl_sac *s, prl_buf *buf, int rounds, int batch, co
     cudaStream_t st = (cudaStream_t)stream_;
     int rc = prl_buf_sample_indices(buf, rounds, batch, out_logical ? out_logical : s->logical, s->slots, stream_);
     if (rc) return rc;
-    // per-round AdamW scalars (actor lr / critic lr), as torch evaluates them
+    // per-call block: AdamW scalars of every round (actor lr / critic lr, as torch evaluates them in double) + pointers
     const int sb = s->scal_next; s->scal_next ^= 1;
     PRL_CUDA(cudaEventSynchronize(s->scal_done[sb]));
+    float2 *hs = s->scal_host[sb];
     for (int r = 0; r < rounds; r++) {
         const double step = (double)(s->adam_step + r + 1);
         const double bc1 = 1.0 - pow(c.beta1, step), bc2 = 1.0 - pow(c.beta2, step);
-        s->scal_host[sb][r] = make_float2((float)(c.actor_lr / bc1), (float)sqrt(bc2));
-        s->scal_host[sb][rounds + r] = make_float2((float)(c.critic_lr / bc1), (float)sqrt(bc2));
+        hs[r] = make_float2((float)(c.actor_lr / bc1), (float)sqrt(bc2));
+        hs[c.max_rounds + r] = make_float2((float)(c.critic_lr / bc1), (float)sqrt(bc2));
     }
-    PRL_CUDA(cudaMemcpyAsync(s->scal_a, s->scal_host[sb], (size_t)rounds * 8, cudaMemcpyHostToDevice, st));
-    PRL_CUDA(cudaMemcpyAsync(s->scal_c, s->scal_host[sb] + rounds, (size_t)rounds * 8, cudaMemcpyHostToDevice, st));
+    SacCall *hc = reinterpret_cast<SacCall *>(hs + 2 * (size_t)c.max_rounds);
+    hc->noise = noise_dev; hc->slots = s->slots; hc->out_actor = out_actor_loss; hc->out_critic = out_critic_loss; hc->out_entropy = out_entropy_loss;
+    int *hround = reinterpret_cast<int *>(hc + 1);
+    *hround = 0;
+    // scal_a | scal_c | call | round_idx are contiguous on the device in the same order
+    PRL_CUDA(cudaMemcpyAsync(s->scal_a, hs, 2 * (size_t)c.max_rounds * 8 + sizeof(SacCall) + 4, cudaMemcpyHostToDevice, st));
     PRL_CUDA(cudaEventRecord(s->scal_done[sb], st));
-    k_set<<<1, 1, 0, st>>>(s->round_idx, 0);
 
-    const int B = batch, O = c.obs_dim, A = c.act_dim, D = O + A;
-    const int H1 = c.actor_h1, H2 = c.actor_h2, C1 = c.critic_h1, C2 = c.critic_h2;
-    const long long Pc = s->Pc;
-    AdamHp ha{(float)(1.0 - c.actor_lr * c.weight_decay), (float)(1.0 - c.beta1), (float)c.beta2, (float)(1.0 - c.beta2), (float)c.eps};
-    AdamHp hc{(float)(1.0 - c.critic_lr * c.weight_decay), (float)(1.0 - c.beta1), (float)c.beta2, (float)(1.0 - c.beta2), (float)c.eps};
-    Launcher L; L.st = st;
-    const float *aw = s->actor, *cw = s->critic, *ct = s->critic_t;
-    auto actor_forward = [&](const float *X) {
-        fwd(L, mat(X, O), B, aw + s->aW1, O, 0, aw + s->ab1, 0, H1, O, true, s->h1, H1, 0);
-        fwd(L, mat(s->h1, H1), B, aw + s->aW2, H1, 0, aw + s->ab2, 0, H2, H1, true, s->h2, H2, 0);
-        fwd(L, mat(s->h2, H2), B, aw + s->aWmu, H2, 0, aw + s->abmu, 0, A, H2, false, s->mean, A, 0);
-        fwd(L, mat(s->h2, H2), B, aw + s->aWsd, H2, 0, aw + s->absd, 0, A, H2, false, s->z, A, 0);
-    };
-    auto critic_forward = [&](const float *net, const float *X, const float *Act, float *qout) {   // both critics (blockIdx.z)
-        fwd(L, mat2(X, O, O, Act, A), B, net + s->cW1, D, Pc, net + s->cb1, Pc, C1, D, true, s->c1, C1, (long long)B * C1, 2);
-        fwd(L, mat(s->c1, C1, (long long)B * C1), B, net + s->cW2, C1, Pc, net + s->cb2, Pc, C2, C1, true, s->c2, C2, (long long)B * C2, 2);
-        fwd(L, mat(s->c2, C2, (long long)B * C2), B, net + s->cW3, C2, Pc, net + s->cb3, Pc, 1, C2, false, qout, 1, B, 2);
-    };
-    const int eb = 256;
-    for (int r = 0; r < rounds; r++) {
-        const float *n1 = noise_dev + (size_t)(2 * r) * B * A, *n2 = n1 + (size_t)B * A;
-        k_sac_gather<<<(B * 32 + eb - 1) / eb, eb, 0, st>>>(buf->records, buf->lay, O, A, s->slots + (size_t)r * B, B, s->S, s->A, s->R, s->S2, s->T);
-        // ---------------- actor step (actor_critic_base.py:333-343)
-        actor_forward(s->S);
-        k_sac_sample<<<(B + eb - 1) / eb, eb, 0, st>>>(B, A, s->mean, s->z, n1, s->low, s->high, s->act_s, s->na, s->sd, s->logp);
-        critic_forward(cw, s->S, s->act_s, s->q);
-        k_sac_actor_loss<<<1, 256, 0, st>>>(B, s->q, s->logp, s->alpha, s->dq, out_actor_loss + r);
-        {   // dQ/d(action) through both critics
-            dim3 g2((B * C2 + eb - 1) / eb, 1, 2);
-            k_head_bwd<<<g2, eb, 0, st>>>(B, C2, s->dq, cw + s->cW3, Pc, s->c2, s->dc2);
-            bwd_x(L, s->dc2, C2, (long long)B * C2, B, C2, cw + s->cW2, C1, Pc, 0, C1, s->dc1, C1, (long long)B * C1, s->c1, C1, (long long)B * C1, false, 2);
-            bwd_x(L, s->dc1, C1, (long long)B * C1, B, C1, cw + s->cW1, D, Pc, O, A, s->da, A, (long long)B * A, nullptr, 0, 0, false, 2);
+    if (s->use_graph) {
+        if (!s->graph_exec || s->graph_batch != batch || s->graph_buf != buf->records) {
+            if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+            cudaStream_t cs;
+            PRL_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                sac_round(s, buf, batch, cs);
+                e = cudaStreamEndCapture(cs, &graph);
+            }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cs);
+            if (e != cudaSuccess) { s->graph_exec = nullptr; return fail(PRL_ECUDA, "prl_sac_learn: graph capture failed: %s", cudaGetErrorString(e)); }
+            s->graph_batch = batch; s->graph_buf = buf->records;
         }
-        k_sac_head_grads<<<(B * A + eb - 1) / eb, eb, 0, st>>>(B, A, s->da, s->na, s->sd, n1, s->z, s->low, s->high, s->alpha, s->dmean, s->dz);
-        {   // actor backward
-            float *ga = s->g_actor;
-            bwd_w(L, s->dmean, A, 0, B, A, mat(s->h2, H2), H2, ga + s->aWmu, H2, 0, ga + s->abmu, 0);
-            bwd_w(L, s->dz, A, 0, B, A, mat(s->h2, H2), H2, ga + s->aWsd, H2, 0, ga + s->absd, 0);
-            bwd_x(L, s->dmean, A, 0, B, A, aw + s->aWmu, H2, 0, 0, H2, s->dh2, H2, 0, nullptr, 0, 0, false);
-            bwd_x(L, s->dz, A, 0, B, A, aw + s->aWsd, H2, 0, 0, H2, s->dh2, H2, 0, s->h2, H2, 0, true);
-            bwd_w(L, s->dh2, H2, 0, B, H2, mat(s->h1, H1), H1, ga + s->aW2, H1, 0, ga + s->ab2, 0);
-            bwd_x(L, s->dh2, H2, 0, B, H2, aw + s->aW2, H1, 0, 0, H1, s->dh1, H1, 0, s->h1, H1, 0, false);
-            bwd_w(L, s->dh1, H1, 0, B, H1, mat(s->S, O), O, ga + s->aW1, O, 0, ga + s->ab1, 0);
-            k_adamw<<<(s->Pa + eb - 1) / eb, eb, 0, st>>>(s->Pa, s->actor, s->actor_m, s->actor_v, s->actor_x, ga, ha, s->scal_a, s->round_idx, nullptr, 0.f, 0.f);
+        for (int r = 0; r < rounds; r++) PRL_CUDA(cudaGraphLaunch(s->graph_exec, st));
+    } else {
+        for (int r = 0; r < rounds; r++) {
+            rc = sac_round(s, buf, batch, st);
+            if (rc) return rc;
         }
-        // ---------------- critic step with the UPDATED actor (:345-349; soft_actor_critic_continuous.py:155-205)
-        actor_forward(s->S2);
-        k_sac_sample<<<(B + eb - 1) / eb, eb, 0, st>>>(B, A, s->mean, s->z, n2, s->low, s->high, s->act_s, s->na, s->sd, s->logp2);
-        critic_forward(ct, s->S2, s->act_s, s->qt);
-        k_sac_target<<<(B + eb - 1) / eb, eb, 0, st>>>(B, s->qt, s->logp2, s->alpha, (float)c.gamma, s->T, s->R, s->y);
-        critic_forward(cw, s->S, s->A, s->q);
-        k_sac_critic_loss<<<1, 256, 0, st>>>(B, s->q, s->y, s->dq, out_critic_loss + r);
-        {
-            float *gc = s->g_critic;
-            bwd_w(L, s->dq, 1, B, B, 1, mat(s->c2, C2, (long long)B * C2), C2, gc + s->cW3, C2, Pc, gc + s->cb3, Pc, 2);
-            dim3 g2((B * C2 + eb - 1) / eb, 1, 2);
-            k_head_bwd<<<g2, eb, 0, st>>>(B, C2, s->dq, cw + s->cW3, Pc, s->c2, s->dc2);
-            bwd_w(L, s->dc2, C2, (long long)B * C2, B, C2, mat(s->c1, C1, (long long)B * C1), C1, gc + s->cW2, C1, Pc, gc + s->cb2, Pc, 2);
-            bwd_x(L, s->dc2, C2, (long long)B * C2, B, C2, cw + s->cW2, C1, Pc, 0, C1, s->dc1, C1, (long long)B * C1, s->c1, C1, (long long)B * C1, false, 2);
-            bwd_w(L, s->dc1, C1, (long long)B * C1, B, C1, mat2(s->S, O, O, s->A, A), D, gc + s->cW1, D, Pc, gc + s->cb1, Pc, 2);
-            const int n2p = 2 * s->Pc;
-            k_adamw<<<(n2p + eb - 1) / eb, eb, 0, st>>>(n2p, s->critic, s->critic_m, s->critic_v, s->critic_x, gc, hc, s->scal_c, s->round_idx,
-                                                      s->critic_t, (float)c.tau, (float)(1.0 - c.tau));
-        }
-        // ---------------- entropy coefficient (soft_actor_critic_continuous.py:134-147)
-        if (c.autotune)
-            k_sac_alpha<<<1, 256, 0, st>>>(B, s->logp, -(float)A, s->log_alpha, s->alpha, hc, s->scal_c, s->round_idx, out_entropy_loss + r);
-        k_bump<<<1, 1, 0, st>>>(s->round_idx);
     }
     PRL_CUDA(cudaGetLastError());
     s->adam_step += rounds;
-    s->last_launches = L.count;
+    s->last_launches = s->launches_per_round * rounds;
     return PRL_OK;
 }
+extern "C" int prl_sac_set_graph(prl_sac *s, int enable) {
+    PRL_REQUIRE(s, "null handle");
+    s->use_graph = enable != 0;
+    return PRL_OK;
+}
+extern "C" int64_t prl_sac_last_launches(const prl_sac *s) { return s ? s->last_launches : -1; }

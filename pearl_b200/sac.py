@@ -53,6 +53,7 @@ class B200ContinuousSoftActorCritic:
         self._entropy_autotune = bool(entropy_autotune)
         self._max_rounds = max(int(max_rounds_per_call), 1)
         self._training_steps = 0
+        self.use_cuda_graph = True       # False: plain stream launches (profilers)
         self._handle = C.c_void_p(0)
         self._bound_batch = 0
         self._gen = torch.Generator(device=self._device)
@@ -185,6 +186,7 @@ class B200ContinuousSoftActorCritic:
             idx = torch.empty((r, B), dtype=torch.int32, device=dev) if trace is not None else None
             replay_buffer._rng_push()
             with torch.cuda.device(dev):
+                _lib.check(self._lib.prl_sac_set_graph(self._handle, int(self.use_cuda_graph)))
                 _lib.check(self._lib.prl_sac_learn(self._handle, replay_buffer.handle, r, B, _lib.ptr(nz), _lib.ptr(out[0]),
                                                    _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(idx) if idx is not None else None,
                                                    _stream_ptr(dev)))

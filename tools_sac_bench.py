@@ -6,7 +6,8 @@ import torch
 
 import pearl_b200
 
-obs, act, n, B = 17, 6, 100000, 256
+import os
+obs, act, n, B = [int(x) for x in os.environ.get("SAC_SHAPE", "17,6,100000,256").split(",")]
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 buf = pearl_b200.B200ReplayBuffer(n, rng="device")
 buf.is_action_continuous = True
@@ -17,6 +18,7 @@ buf.push_batch(rn(n, obs), rn(n, act).clamp(-1, 1), rn(n), rn(n, obs), torch.zer
 buf.seed(1)
 pl = pearl_b200.B200ContinuousSoftActorCritic(state_dim=obs, low=[-1.0] * act, high=[1.0] * act, actor_hidden_dims=[256, 256],
                                               critic_hidden_dims=[256, 256], training_rounds=R, batch_size=B, seed=3)
+pl.use_cuda_graph = os.environ.get('SAC_GRAPH', '1') == '1'
 pl.learn(buf)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
