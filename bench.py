@@ -339,9 +339,147 @@ def run_b200(args) -> None:
         }
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1)
+        if world == 1 and not args.no_extras:
+            del group, learners, bufs
+            if single is not None:
+                del sl
+            torch.cuda.empty_cache()
+            try:
+                line["other_paths"] = other_paths(dev, args)
+            except Exception as exc:   # the headline line must survive a failure in the side measurements
+                line["other_paths"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_paths(dev, args) -> dict:
+    """The remaining BASELINE configs on ONE GPU (rank 0, N = 1): SAC configs[2], PPO configs[3] (one GPU's rollout),
+    prioritized DoubleDQN configs[4] (one GPU's shard).  Each: device-resident synthetic data, CUDA-event timing after a
+    warm-up call, and the oracle port timed on the host cores on a bounded sample."""
+    import time
+
+    import torch
+    import pearl_b200
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(777)
+    rn = lambda *shape: torch.randn(*shape, device=dev, generator=gen)
+    cores = os.cpu_count() or 1
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / reps
+
+    def cpu_rate(step):
+        """steps/s of `step` on the host, best of a few intra-op thread counts (eager PyTorch at these batch sizes does
+        not scale to all cores; the best setting is what a user of the reference would run)."""
+        best = (0.0, 1)
+        for nt in sorted({1, min(8, cores), min(32, cores)}):
+            torch.set_num_threads(nt)
+            step()
+            t0, k = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 1.5:
+                step()
+                k += 1
+            best = max(best, (k / (time.perf_counter() - t0), nt))
+        return best
+
+    def section(fn):
+        try:
+            fn()
+        except Exception as exc:   # one failing side measurement must not take the others (or the headline) with it
+            out[fn.__name__] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+
+    # ---- SAC, Humanoid-shaped (configs[2]): obs 376, act 17, 1M replay, batch 512, [256, 256] networks
+    def sac():
+        obs, act, cap, B, R = 376, 17, 1_000_000, 512, 200
+        buf = pearl_b200.B200ReplayBuffer(cap, device=dev, rng="device")
+        buf.is_action_continuous = True
+        for s0 in range(0, cap, 1 << 17):
+            m = min(1 << 17, cap - s0)
+            buf.push_batch(rn(m, obs), rn(m, act).clamp(-1, 1), rn(m), rn(m, obs), torch.rand(m, device=dev, generator=gen) < 0.01,
+                           torch.zeros(m, dtype=torch.bool, device=dev))
+        buf.seed(5)
+        pl = pearl_b200.B200ContinuousSoftActorCritic(state_dim=obs, low=[-1.0] * act, high=[1.0] * act, actor_hidden_dims=[256, 256],
+                                                       critic_hidden_dims=[256, 256], training_rounds=R, batch_size=B, device=dev, seed=1)
+        sec = timed(lambda: pl.learn(buf), 3)
+        out["sac"] = {"workload": "SAC continuous obs_dim=376 act_dim=17, 1M replay, batch=512 (configs[2])", "value": R / sec,
+                      "unit": "gradient-steps/s (actor + twin-critic + entropy steps)", "us_per_step": sec / R * 1e6,
+                      "kernels_per_step": int(pl._lib.prl_sac_last_launches(pl._handle)) // R, "engine": "fp32 SIMT tiled contractions, CUDA-graph replay"}
+        del pl, buf
+        if not args.no_cpu:
+            from oracle.sac_oracle import OracleSAC
+            orc = OracleSAC(obs, act, (256, 256), (256, 256), [-1.0] * act, [1.0] * act)
+            b = dict(state=torch.randn(B, obs), action=torch.rand(B, act) * 2 - 1, reward=torch.randn(B), next_state=torch.randn(B, obs),
+                     terminated=torch.zeros(B, dtype=torch.bool))
+            n1, n2 = torch.randn(B, act), torch.randn(B, act)
+            rate, nt = cpu_rate(lambda: orc.learn_batch(b, n1, n2))
+            out["sac"]["cpu_baseline"] = {"value": rate, "unit": "gradient-steps/s", "cores": nt, "host_cores": cores, "kind": "port",
+                                          "sample": "1.5 s of learn_batch calls of oracle/sac_oracle.py on one fixed batch (no sampling cost), "
+                                                    "best of 1 / 8 / 32 intra-op threads"}
+
+    # ---- PPO (configs[3], one GPU's rollout): 64k-step rollout, obs 210, [256, 256] networks, batch 256
+    def ppo():
+        obs, A, n, B, R = 210, 8, 65536, 256, 100
+        buf = pearl_b200.B200ReplayBuffer(n, device=dev, rng="device")
+        buf.push_batch(rn(n, obs), torch.randint(0, A, (n,), device=dev, generator=gen).to(torch.int32), rn(n), rn(n, obs),
+                       torch.rand(n, device=dev, generator=gen) < 0.002, torch.rand(n, device=dev, generator=gen) < 0.001, max_number_actions=A)
+        buf.seed(6)
+        pl = pearl_b200.B200ProximalPolicyOptimization(state_dim=obs, n_actions=A, actor_hidden_dims=[256, 256], critic_hidden_dims=[256, 256],
+                                                        training_rounds=R, batch_size=B, epsilon=0.2, device=dev, seed=2)
+        pre_sec = timed(lambda: pl.preprocess_replay_buffer(buf), 5)
+        sec = timed(lambda: pl.learn(buf), 3)
+        out["ppo"] = {"workload": "PPO 64k-step rollout obs_dim=210, GAE + clipped surrogate, batch=256 (configs[3], one GPU)",
+                      "preprocess_ms": pre_sec * 1e3, "preprocess_transitions_per_s": n / pre_sec,
+                      "value": R / (sec - pre_sec), "unit": "gradient-steps/s (actor + critic steps, preprocessing excluded)",
+                      "learn_ms": sec * 1e3, "training_rounds": R}
+        del pl, buf
+        if not args.no_cpu:
+            from oracle.ppo_oracle import OraclePPO
+            orc = OraclePPO(obs, A, (256, 256), (256, 256), epsilon=0.2, batch_size=B, training_rounds=1)
+            ns = 4096
+            st, ac = torch.randn(ns + 1, obs), torch.randint(0, A, (ns,))
+            torch.set_num_threads(min(8, cores))
+            t0 = time.perf_counter()
+            pre = orc.preprocess(st[:ns], ac, torch.randn(ns), torch.zeros(ns, dtype=torch.bool), torch.zeros(ns, dtype=torch.bool), st[ns])
+            t_pre = time.perf_counter() - t0
+            idx = torch.arange(B)
+            rate, nt = cpu_rate(lambda: orc.learn_batch(st[idx], ac[idx], pre["gae"][idx], pre["lam_return"][idx], pre["action_probs"][idx]))
+            out["ppo"]["cpu_baseline"] = {"value": rate, "unit": "gradient-steps/s", "cores": nt, "host_cores": cores, "kind": "port",
+                                          "preprocess_transitions_per_s": ns / t_pre,
+                                          "sample": f"preprocess of a {ns}-step rollout (8 threads) + 1.5 s of learn_batch calls of "
+                                                    "oracle/ppo_oracle.py, best of 1 / 8 / 32 intra-op threads"}
+
+    # ---- prioritized DoubleDQN (configs[4], one GPU's shard): obs 512, 16 actions, batch 256, sum / min trees in HBM
+    def prioritized_ddqn():
+        obs, A, B, R = 512, 16, 256, 200
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        cap = 4_000_000 if free_b > (40 << 30) else 500_000
+        buf = pearl_b200.B200PrioritizedReplayBuffer(cap, device=dev, seed=11)
+        for s0 in range(0, cap, 1 << 17):
+            m = min(1 << 17, cap - s0)
+            buf.push_batch(rn(m, obs), (torch.arange(s0, s0 + m, device=dev) % A).to(torch.int32), rn(m), rn(m, obs),
+                           torch.rand(m, device=dev, generator=gen) < 0.02, torch.zeros(m, dtype=torch.bool, device=dev), max_number_actions=A)
+        ddqn = pearl_b200.B200DoubleDQN(state_dim=obs, action_space=Space(A), hidden_dims=[128, 128], training_rounds=R, batch_size=B,
+                                        target_update_freq=10, soft_update_tau=0.75,
+                                        action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(A),
+                                        max_rounds_per_call=R).to(dev)
+        sec = timed(lambda: ddqn.learn(buf), 3)
+        out["prioritized_ddqn"] = {"workload": f"prioritized segment-tree replay {cap} x obs_dim=512, DoubleDQN, batch=256 (configs[4], one GPU's shard)",
+                                   "value": R / sec, "unit": "gradient-steps/s (stratified tree draw + weighted step + priority update)",
+                                   "us_per_step": sec / R * 1e6, "replay_bytes": cap * buf.record_bytes}
+        del ddqn, buf
+    for fn in (sac, ppo, prioritized_ddqn):
+        section(fn)
+    return out
 
 
 def main() -> None:
@@ -359,9 +497,16 @@ def main() -> None:
     ap.add_argument("--ref-rounds", type=int, default=100)
     ap.add_argument("--ref-capacity", type=int, default=20_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the SAC / PPO / prioritized-replay side measurements")
     ap.add_argument("--multi", default="dp", choices=["dp", "replicas"],
                     help="N>1: data-parallel learner with in-kernel gradient exchange, or independent replicas")
+    ap.add_argument("--extras-only", action="store_true", help="developer: run only the side measurements on cuda:0")
     args = ap.parse_args()
+    if args.extras_only:
+        import torch
+        torch.cuda.set_device(0)
+        print(json.dumps({"other_paths": other_paths(torch.device("cuda", 0), args)}), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:
