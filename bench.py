@@ -251,20 +251,19 @@ def run_b200(args) -> None:
     ms_max = float(t.item())
     value = args.steps * rounds * R * world / (ms_max / 1e3)
 
-    # ---- e2e: host data through the plugin API (every learner pushes `rounds` fresh transitions per step
-    #      from pinned host memory, CPython-RNG hand-off on, loss reports read back)
-    import random
-    random.seed(1234 + rank)
-    for b in bufs:
-        b._rng_mode = "python"
+    # ---- e2e: host data through the plugin API (every learner pushes `rounds` fresh transitions per step from pinned
+    #      host memory; loss reports read back).  Every learner keeps its OWN device-resident MT19937 stream
+    #      (rng="device"), like the reference's replicas, which are separate processes with their own `random` state
+    #      (utils/scripts/benchmark.py:80-116); the CPython-global-stream hand-off of a single learner is measured in
+    #      `single_learner_e2e`.
     n_new = rounds
     pin = lambda x: x.pin_memory()
     hg = torch.Generator().manual_seed(99 + rank)
     host = dict(state=pin(torch.randn((n_new, OBS), generator=hg)), next_state=pin(torch.randn((n_new, OBS), generator=hg)),
                 reward=pin(torch.randn(n_new, generator=hg)), action=pin((torch.arange(n_new) % N_ACT).to(torch.int32)),
                 term=pin(torch.rand(n_new, generator=hg) < 0.02), trunc=pin(torch.zeros(n_new, dtype=torch.bool)))
-    h2d = R * (n_new * (2 * OBS * 4 + 4 + 4 + 1 + 1) + 625 * 4)
-    d2h = R * (rounds * 4 + 625 * 4)
+    h2d = R * n_new * (2 * OBS * 4 + 4 + 4 + 1 + 1)
+    d2h = R * rounds * 4
 
     def e2e_step():
         for b in bufs:
@@ -304,6 +303,23 @@ def run_b200(args) -> None:
         info = sl.launch_info()
         single = {"value": 5 * rounds / (s0.elapsed_time(s1) / 1e3), "unit": "gradient-steps/s",
                   "engine": f"k_dqn_learn: {info['ctas']} learner CTAs x {info['rows_per_cta']} rows + 1 index-producer CTA, fp32 SIMT"}
+        # the same learner end to end as PearlAgent drives it: push from pinned host memory, CPython's global MT19937
+        # stream handed to the device and back around learn(), loss report read back
+        import random
+        random.seed(1234)
+        bufs[0]._rng_mode = "python"
+
+        def single_e2e():
+            bufs[0].push_batch(host["state"], host["action"], host["reward"], host["next_state"], host["term"], host["trunc"])
+            return sl.learn(bufs[0])["loss"][-1]
+        single_e2e()
+        s0.record()
+        for _ in range(5):
+            single_e2e()
+        s1.record()
+        torch.cuda.synchronize()
+        single["e2e"] = {"value": 5 * rounds / (s0.elapsed_time(s1) / 1e3), "unit": "gradient-steps/s",
+                         "what": f"push_batch({n_new} from pinned host) + learn() incl. CPython RNG hand-off (2 x 2500 B) and loss report"}
 
     if rank == 0:
         pk = peaks()
@@ -325,7 +341,7 @@ def run_b200(args) -> None:
                                     "(the data-parallel single learner with in-kernel NVLink gradient exchange is `--single-dp`)",
                        "loss_last": last_loss},
             "e2e": {"value": e2e_value, "unit": "gradient-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": f"per learner push_batch({n_new} transitions from pinned host) + group.learn() incl. CPython RNG hand-off and loss reports"},
+                    "what": f"per learner push_batch({n_new} transitions from pinned host) + group.learn() with the loss reports read back; device-resident RNG streams"},
             "gpu_launches": args.steps * 2,
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "k_dqn_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
