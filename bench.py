@@ -40,6 +40,9 @@ OBS, N_ACT, HIDDEN, BATCH = 128, 16, (64, 64), 256
 METRIC = "learner gradient-steps/sec (batch=256, 1e6 replay)"
 
 
+TC_DRAM_BYTES_PER_STEP = 796e3   # measured under ncu, see profiles/r1_k_dqn_tc_summary.md
+
+
 def flops_per_step(obs=OBS, A=N_ACT, H1=HIDDEN[0], H2=HIDDEN[1], B=BATCH, double=False):
     """Algorithmic FLOPs of one DQN gradient step."""
     D = obs + A
@@ -345,7 +348,10 @@ def run_b200(args) -> None:
             "gpu_launches": args.steps * 2,
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "k_dqn_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": TC_DRAM_BYTES_PER_STEP * rounds * R,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full` capture of k_dqn_tc in "
+                                           "profiles/r1_k_dqn_tc_summary.md (796 KB per gradient step; algorithmic gather 266 KB), "
+                                           "scaled to the gradient steps of one bench launch",
                          "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
                          "flops_per_gradient_step_factored": fact, "flops_per_gradient_step_as_written": as_written,
                          "kernel_ms_per_launch": k_ms, "gradient_steps_per_launch": rounds * R,
