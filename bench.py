@@ -262,15 +262,14 @@ def run_b200(args) -> None:
     n_new = rounds
     pin = lambda x: x.pin_memory()
     hg = torch.Generator().manual_seed(99 + rank)
-    host = dict(state=pin(torch.randn((n_new, OBS), generator=hg)), next_state=pin(torch.randn((n_new, OBS), generator=hg)),
-                reward=pin(torch.randn(n_new, generator=hg)), action=pin((torch.arange(n_new) % N_ACT).to(torch.int32)),
-                term=pin(torch.rand(n_new, generator=hg) < 0.02), trunc=pin(torch.zeros(n_new, dtype=torch.bool)))
+    host = dict(state=pin(torch.randn((R, n_new, OBS), generator=hg)), next_state=pin(torch.randn((R, n_new, OBS), generator=hg)),
+                reward=pin(torch.randn((R, n_new), generator=hg)), action=pin((torch.arange(R * n_new) % N_ACT).to(torch.int32).view(R, n_new)),
+                term=pin((torch.rand((R, n_new), generator=hg) < 0.02).to(torch.uint8)), trunc=pin(torch.zeros((R, n_new), dtype=torch.uint8)))
     h2d = R * n_new * (2 * OBS * 4 + 4 + 4 + 1 + 1)
     d2h = R * rounds * 4
 
     def e2e_step():
-        for b in bufs:
-            b.push_batch(host["state"], host["action"], host["reward"], host["next_state"], host["term"], host["trunc"])
+        group.push_batch(host["state"], host["action"], host["reward"], host["next_state"], host["term"], host["trunc"])
         return group.learn()[0]["loss"][-1]
 
     for _ in range(2):
@@ -313,7 +312,7 @@ def run_b200(args) -> None:
         bufs[0]._rng_mode = "python"
 
         def single_e2e():
-            bufs[0].push_batch(host["state"], host["action"], host["reward"], host["next_state"], host["term"], host["trunc"])
+            bufs[0].push_batch(host["state"][0], host["action"][0], host["reward"][0], host["next_state"][0], host["term"][0], host["trunc"][0])
             return sl.learn(bufs[0])["loss"][-1]
         single_e2e()
         s0.record()
@@ -344,7 +343,8 @@ def run_b200(args) -> None:
                                     "(the data-parallel single learner with in-kernel NVLink gradient exchange is `--single-dp`)",
                        "loss_last": last_loss},
             "e2e": {"value": e2e_value, "unit": "gradient-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": f"per learner push_batch({n_new} transitions from pinned host) + group.learn() with the loss reports read back; device-resident RNG streams"},
+                    "what": f"group.push_batch({n_new} fresh transitions per learner from pinned host memory, one library call) + group.learn() with the "
+                            "loss reports read back; device-resident RNG streams"},
             "gpu_launches": args.steps * 2,
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "k_dqn_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

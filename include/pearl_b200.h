@@ -101,6 +101,13 @@ int prl_buf_clear(prl_buf *buf);                  /* clear()  (:287-288) */
  * (checkpoint load): `len` valid records, oldest at physical slot `head`. */
 int prl_buf_set_occupancy(prl_buf *buf, int64_t len, int64_t head);
 
+/* The same host push for `count` buffers of one record layout in ONE call (a vectorised environment feeding
+ * a learner group): every source is a [count][n][...] host array; no per-transition action sets.  Records
+ * are packed by a few worker threads and copied with one cudaMemcpyAsync per buffer. */
+int prl_buf_push_host_multi(prl_buf *const *bufs, int count, int64_t n, const float *state, const void *action,
+                            const float *reward, const float *next_state, const uint8_t *terminated,
+                            const uint8_t *truncated, void *stream);
+
 /* push n transitions given as HOST arrays (struct-of-arrays, C order):
  * state/next_state f32[n][obs_dim]; action int32[n] or f32[n][act_dim];
  * reward f32[n]; terminated/truncated u8[n]; next_avail_ids u8[n][n_actions]

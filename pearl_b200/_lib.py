@@ -72,6 +72,7 @@ _SIGNATURES = {
     "prl_buf_clear": (C.c_int, [_P]),
     "prl_buf_set_occupancy": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "prl_buf_push_host": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "prl_buf_push_host_multi": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "prl_buf_push_device": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "prl_rng_set_state": (C.c_int, [_P, _P, _P]),
     "prl_rng_get_state": (C.c_int, [_P, _P, _P]),

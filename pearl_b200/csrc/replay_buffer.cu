@@ -5,6 +5,10 @@
 
 #include <new>
 
+#include <algorithm>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 #include "sampler.cuh"
 
@@ -169,6 +173,41 @@ static int check_push_args(const prl_buf *b, int64_t n, const void *state, const
     return PRL_OK;
 }
 
+// pack transitions [i0, i0 + m) of struct-of-arrays host sources into m consecutive records at `st` (pure CPU)
+static void pack_records_host(const prl_buf *b, uint32_t *st, int64_t i0, int64_t m, const float *state, const void *action,
+                              const float *reward, const float *next_state, const uint8_t *terminated, const uint8_t *truncated,
+                              const uint8_t *next_avail_ids, const int32_t *next_avail_cnt) {
+    const prl_buf_layout &L = b->lay;
+    const int obs = b->desc.obs_dim, A = b->desc.n_actions, W = L.record_words;
+    for (int64_t i = 0; i < m; i++) {
+        const int64_t s = i0 + i;
+        uint32_t *r = st + i * W;
+        memcpy(r + L.off_state, state + s * obs, 4 * obs);
+        for (int p = obs; p < L.off_next_state; p++) r[p] = 0;
+        if (next_state)
+            memcpy(r + L.off_next_state, next_state + s * obs, 4 * obs);
+        else
+            memset(r + L.off_next_state, 0, 4 * obs);
+        for (int p = L.off_next_state + obs; p < L.off_action; p++) r[p] = 0;
+        if (b->desc.flags & PRL_BUF_DISCRETE)
+            r[L.off_action] = (uint32_t)((const int32_t *)action)[s];
+        else
+            memcpy(r + L.off_action, (const float *)action + s * L.act_words, 4 * L.act_words);
+        r[L.off_reward] = f2u(reward[s]);
+        uint32_t cnt = (b->desc.flags & PRL_BUF_DISCRETE) ? (uint32_t)A : 0u;
+        if (next_avail_cnt) cnt = (uint32_t)next_avail_cnt[s];
+        r[L.off_flags] = (terminated[s] ? 1u : 0u) | (truncated[s] ? 2u : 0u) | (cnt << 8);
+        for (int p = L.off_avail; p < W; p++) r[p] = 0;
+        if (b->desc.flags & PRL_BUF_DYNAMIC_ACTIONS) {
+            uint8_t *ids = (uint8_t *)(r + L.off_avail);
+            if (next_avail_ids)
+                for (uint32_t a = 0; a < cnt && a < (uint32_t)A; a++) ids[a] = next_avail_ids[s * A + a];
+            else
+                for (int a = 0; a < A; a++) ids[a] = (uint8_t)a;
+        }
+    }
+}
+
 extern "C" int prl_buf_push_host(prl_buf *b, int64_t n, const float *state, const void *action,
                                  const float *reward, const float *next_state,
                                  const uint8_t *terminated, const uint8_t *truncated,
@@ -180,8 +219,7 @@ extern "C" int prl_buf_push_host(prl_buf *b, int64_t n, const float *state, cons
     cudaStream_t stream = (cudaStream_t)stream_;
     rc = ensure_staging(b);
     if (rc) return rc;
-    const prl_buf_layout &L = b->lay;
-    const int obs = b->desc.obs_dim, A = b->desc.n_actions, W = L.record_words;
+    const int W = b->lay.record_words;
     const int64_t C = b->desc.capacity;
     // only the last `capacity` transitions of an oversized push can survive
     int64_t skip = n > C ? n - C : 0;
@@ -197,39 +235,85 @@ extern "C" int prl_buf_push_host(prl_buf *b, int64_t n, const float *state, cons
         b->stage_next ^= 1;
         PRL_CUDA(cudaEventSynchronize(b->stage_done[sb]));
         uint32_t *st = b->stage[sb];
-        for (int64_t i = 0; i < m; i++) {
-            const int64_t s = i0 + i;
-            uint32_t *r = st + i * W;
-            memcpy(r + L.off_state, state + s * obs, 4 * obs);
-            for (int p = obs; p < L.off_next_state; p++) r[p] = 0;
-            if (next_state)
-                memcpy(r + L.off_next_state, next_state + s * obs, 4 * obs);
-            else
-                memset(r + L.off_next_state, 0, 4 * obs);
-            for (int p = L.off_next_state + obs; p < L.off_action; p++) r[p] = 0;
-            if (b->desc.flags & PRL_BUF_DISCRETE)
-                r[L.off_action] = (uint32_t)((const int32_t *)action)[s];
-            else
-                memcpy(r + L.off_action, (const float *)action + s * L.act_words, 4 * L.act_words);
-            r[L.off_reward] = f2u(reward[s]);
-            uint32_t cnt = (b->desc.flags & PRL_BUF_DISCRETE) ? (uint32_t)A : 0u;
-            if (next_avail_cnt) cnt = (uint32_t)next_avail_cnt[s];
-            r[L.off_flags] = (terminated[s] ? 1u : 0u) | (truncated[s] ? 2u : 0u) | (cnt << 8);
-            for (int p = L.off_avail; p < W; p++) r[p] = 0;
-            if (b->desc.flags & PRL_BUF_DYNAMIC_ACTIONS) {
-                uint8_t *ids = (uint8_t *)(r + L.off_avail);
-                if (next_avail_ids)
-                    for (uint32_t a = 0; a < cnt && a < (uint32_t)A; a++) ids[a] = next_avail_ids[s * A + a];
-                else
-                    for (int a = 0; a < A; a++) ids[a] = (uint8_t)a;
-            }
-        }
+        pack_records_host(b, st, i0, m, state, action, reward, next_state, terminated, truncated, next_avail_ids, next_avail_cnt);
         PRL_CUDA(cudaMemcpyAsync(b->records + b->write_pos * W, st, m * (int64_t)W * 4,
                                  cudaMemcpyHostToDevice, stream));
         PRL_CUDA(cudaEventRecord(b->stage_done[sb], stream));
         b->write_pos = (b->write_pos + m) % C;
         b->len = b->len + m > C ? C : b->len + m;
         i0 += m;
+    }
+    return PRL_OK;
+}
+
+// The same push for `count` buffers of one layout at once (a vectorised environment feeding a learner group):
+// sources are [count][n][...] host arrays.  Records are packed by a few worker threads (pure CPU work), the copies are
+// enqueued by the calling thread.  Buffers whose push would wrap the ring or exceed the staging area take the
+// single-buffer path.
+extern "C" int prl_buf_push_host_multi(prl_buf *const *bufs, int count, int64_t n, const float *state, const void *action,
+                                       const float *reward, const float *next_state, const uint8_t *terminated,
+                                       const uint8_t *truncated, void *stream_) {
+    PRL_REQUIRE(bufs && count > 0, "null / empty buffer list");
+    PRL_REQUIRE(n >= 0, "negative count");
+    if (n == 0) return PRL_OK;
+    PRL_REQUIRE(state && action && reward && terminated && truncated, "null field array");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    struct Job { prl_buf *b; uint32_t *st; int sb; int idx; };
+    std::vector<Job> fast;
+    std::vector<int> slow;
+    for (int i = 0; i < count; i++) {
+        prl_buf *b = bufs[i];
+        PRL_REQUIRE(b, "null buffer %d", i);
+        PRL_REQUIRE(b->lay.record_words == bufs[0]->lay.record_words && b->desc.obs_dim == bufs[0]->desc.obs_dim &&
+                        b->desc.flags == bufs[0]->desc.flags && b->lay.act_words == bufs[0]->lay.act_words,
+                    "buffers of one multi-push must share one record layout");
+        int rc = ensure_staging(b);
+        if (rc) return rc;
+        if (n <= b->stage_records && n <= b->desc.capacity - b->write_pos) {
+            const int sb = b->stage_next;
+            b->stage_next ^= 1;
+            PRL_CUDA(cudaEventSynchronize(b->stage_done[sb]));
+            fast.push_back(Job{b, b->stage[sb], sb, i});
+        } else {
+            slow.push_back(i);
+        }
+    }
+    const int obs = bufs[0]->desc.obs_dim, aw = bufs[0]->lay.act_words;
+    auto src = [&](int i, const float *&s, const void *&a, const float *&r, const float *&ns, const uint8_t *&te, const uint8_t *&tr) {
+        s = state + (size_t)i * n * obs;
+        a = (bufs[0]->desc.flags & PRL_BUF_DISCRETE) ? (const void *)((const int32_t *)action + (size_t)i * n)
+                                                     : (const void *)((const float *)action + (size_t)i * n * aw);
+        r = reward + (size_t)i * n;
+        ns = next_state ? next_state + (size_t)i * n * obs : nullptr;
+        te = terminated + (size_t)i * n;
+        tr = truncated + (size_t)i * n;
+    };
+    const int T = (int)std::min<size_t>(8, fast.size());
+    auto work = [&](int t) {
+        for (size_t j = t; j < fast.size(); j += T) {
+            const float *s, *r, *ns; const void *a; const uint8_t *te, *tr;
+            src(fast[j].idx, s, a, r, ns, te, tr);
+            pack_records_host(fast[j].b, fast[j].st, 0, n, s, a, r, ns, te, tr, nullptr, nullptr);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+    if (T > 0) work(0);
+    for (auto &th : pool) th.join();
+    for (const Job &j : fast) {
+        prl_buf *b = j.b;
+        const int W = b->lay.record_words;
+        const int64_t C = b->desc.capacity;
+        PRL_CUDA(cudaMemcpyAsync(b->records + b->write_pos * W, j.st, n * (int64_t)W * 4, cudaMemcpyHostToDevice, stream));
+        PRL_CUDA(cudaEventRecord(b->stage_done[j.sb], stream));
+        b->write_pos = (b->write_pos + n) % C;
+        b->len = b->len + n > C ? C : b->len + n;
+    }
+    for (int i : slow) {
+        const float *s, *r, *ns; const void *a; const uint8_t *te, *tr;
+        src(i, s, a, r, ns, te, tr);
+        int rc = prl_buf_push_host(bufs[i], n, s, a, r, ns, te, tr, nullptr, nullptr, stream_);
+        if (rc) return rc;
     }
     return PRL_OK;
 }
@@ -380,6 +464,8 @@ int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *
     } else {
         uint32_t cap = 64;
         while (cap < (uint32_t)(2 * k)) cap <<= 1;
+        // a sparser table (load <= 1/8 while it stays under 32 KB) keeps the probe sequences of a 32-lane chunk short
+        for (int g = 0; g < 2 && (size_t)cap * 2 * 8 <= 32 * 1024; g++) cap <<= 1;
         sp->table_cap = cap;
         *smem_bytes = (size_t)cap * 8;
     }

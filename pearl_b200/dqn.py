@@ -413,6 +413,40 @@ class B200LearnerGroup:
             l._sync_step_tensors()
         return [{"loss": host[i].tolist()} for i in range(n)]
 
+    def push_batch(self, state, action, reward, next_state, terminated, truncated) -> None:
+        """One push for the whole group (a vectorised environment): HOST tensors with a leading learner axis,
+        state / next_state [R, n, obs], action [R, n] ints, reward [R, n], terminated / truncated [R, n] bool.
+        Equivalent to `buffers[i].push_batch(state[i], ...)` for every i, in one library call
+        (`prl_buf_push_host_multi`: records packed by a few threads, one copy per buffer)."""
+        R = len(self.buffers)
+        b0 = self.buffers[0]
+        state = torch.as_tensor(state)
+        if state.is_cuda:
+            raise ValueError("group push_batch takes host tensors; push device data per buffer")
+        if state.dim() != 3 or state.shape[0] != R:
+            raise ValueError(f"state must be [{R}, n, obs]")
+        n = state.shape[1]
+        if n == 0:
+            return
+        if any(not b._handle.value for b in self.buffers) or b0._is_action_continuous:
+            for i, b in enumerate(self.buffers):     # first push allocates; continuous actions: per-buffer path
+                b.push_batch(state[i], action[i], reward[i], next_state[i], terminated[i], truncated[i],
+                             max_number_actions=self.learners[i]._n_actions)
+            return
+        prep = lambda x, dt, shape: torch.as_tensor(x).to(dtype=dt).reshape(shape).contiguous()
+        st = prep(state, torch.float32, (R, n, -1))
+        if st.shape[2] != b0.obs_dim:
+            raise ValueError(f"state has {st.shape[2]} features, buffers store {b0.obs_dim}")
+        ns = prep(next_state, torch.float32, (R, n, b0.obs_dim))
+        ac = prep(action, torch.int32, (R, n))
+        rw = prep(reward, torch.float32, (R, n))
+        te, tr = prep(terminated, torch.uint8, (R, n)), prep(truncated, torch.uint8, (R, n))
+        dev = b0._device
+        with torch.cuda.device(dev):
+            _lib.check(b0._lib.prl_buf_push_host_multi((C.c_void_p * R)(*[b.handle.value for b in self.buffers]), R, n, _lib.ptr(st),
+                                                       _lib.ptr(ac), _lib.ptr(rw), _lib.ptr(ns), _lib.ptr(te), _lib.ptr(tr),
+                                                       _stream_ptr(dev)))
+
     def set_kernel_timing(self, enable: bool = True) -> None:
         self.learners[0].set_kernel_timing(enable)
 

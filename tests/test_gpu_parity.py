@@ -412,3 +412,30 @@ def test_learner_group_equals_individual_simt_learners():
         assert_close(np.asarray(groups["tc"][2][i]["loss"]), np.asarray(groups["simt"][2][i]["loss"]), f"group loss {i}")
         assert_close(lt.flat_parameters.cpu().numpy(), ls.flat_parameters.cpu().numpy(), f"group params {i}")
         assert_close(lt.flat_target_parameters.cpu().numpy(), ls.flat_target_parameters.cpu().numpy(), f"group target {i}")
+
+
+@pytest.mark.gpu
+def test_group_push_matches_per_buffer_push():
+    """B200LearnerGroup.push_batch (one library call, threaded packing) writes the same ring contents as per-buffer pushes,
+    including the buffers that take the wrap-around path."""
+    import pearl_b200
+    from oracle.synth import make_transitions
+    R, obs, A, cap = 5, 8, 4, 300
+    bufs_a = [pearl_b200.B200ReplayBuffer(cap) for _ in range(R)]
+    bufs_b = [pearl_b200.B200ReplayBuffer(cap) for _ in range(R)]
+
+    class _L:   # the group only needs the learners for learn(); push goes through the buffers
+        _n_actions = A
+    group = pearl_b200.B200LearnerGroup([_L() for _ in range(R)], bufs_a)
+    t = torch.from_numpy
+    for step, n in enumerate((120, 130, 100, 7)):          # the third push wraps the ring
+        d = [make_transitions(n, obs, A, seed=100 * step + i) for i in range(R)]
+        stack = lambda k: torch.stack([t(d[i][k]) for i in range(R)])
+        group.push_batch(stack("state"), stack("action"), stack("reward"), stack("next_state"), stack("terminated"), stack("truncated"))
+        for i in range(R):
+            bufs_b[i].push_batch(*(t(d[i][k]) for k in ("state", "action", "reward", "next_state", "terminated", "truncated")),
+                                 max_number_actions=A)
+    for a, b in zip(bufs_a, bufs_b):
+        assert len(a) == len(b) == cap
+        assert torch.equal(a._storage, b._storage)
+        assert int(a._lib.prl_buf_head(a._handle)) == int(b._lib.prl_buf_head(b._handle))

@@ -1,5 +1,9 @@
 """Developer tool: a few SAC (configs[2] shape) and PPO (configs[3] shape) rounds with plain stream launches, for
 `ncu --metrics gpu__time_duration.sum` launch lists (profiles/r1_launches_sac_ppo.csv)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import pearl_b200

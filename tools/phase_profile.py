@@ -1,7 +1,7 @@
 """Developer tool: per-phase SM-clock breakdown of the persistent learner kernel
 (CTA 0), printed in microseconds at the measured SM clock."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, ctypes as C
 import pearl_b200
 from pearl_b200 import _lib

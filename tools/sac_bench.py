@@ -1,4 +1,8 @@
 """Developer tool: time the SAC learner (cfg3 shape) on one GPU."""
+import os as _os
+import sys as _sys
+
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import sys
 import time
 

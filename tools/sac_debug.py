@@ -1,4 +1,8 @@
 """Developer tool: per-parameter-block error of the SAC learner vs the oracle after R rounds."""
+import os as _os
+import sys as _sys
+
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 import random
 import sys
 

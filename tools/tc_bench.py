@@ -1,6 +1,6 @@
 """Developer tool: throughput of the tensor-core learner group for several group sizes."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import pearl_b200
 from bench import Space, OBS, N_ACT, HIDDEN, BATCH

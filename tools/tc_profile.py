@@ -1,6 +1,6 @@
 """Developer tool: phase breakdown (SM clocks of CTA 0) of the tensor-core learner kernel."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, ctypes as C
 import pearl_b200
 from pearl_b200 import _lib

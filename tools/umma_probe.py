@@ -1,5 +1,5 @@
-import sys, ctypes as C, torch
-sys.path.insert(0, "/root/repo")
+import os, sys, ctypes as C, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pearl_b200 import _lib
 lib = _lib.init(0)
 g = torch.Generator(device="cuda").manual_seed(3)
