@@ -345,7 +345,7 @@ def run_b200(args) -> None:
             "e2e": {"value": e2e_value, "unit": "gradient-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": f"group.push_batch({n_new} fresh transitions per learner from pinned host memory, one library call) + group.learn() with the "
                             "loss reports read back; device-resident RNG streams"},
-            "gpu_launches": args.steps * 2,
+            "gpu_launches": args.steps * learners[0].launch_info()["launches"],
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "k_dqn_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": TC_DRAM_BYTES_PER_STEP * rounds * R,

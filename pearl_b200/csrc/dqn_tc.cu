@@ -66,6 +66,7 @@ struct TcArgs {
     prl_buf_layout lay;
     Dims d;
     int B, rounds, freq;
+    int round0;        // this launch runs rounds [round0, round0 + rounds) of the call (chunked launches)
     float decay, omb1, beta2, omb2, eps, gamma, tau, omtau, inv_b2;
     long long *prof;   // optional [rounds][16] SM-clock stamps of CTA 0
 };
@@ -329,7 +330,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     extern __shared__ __align__(1024) char smem[];
     Misc &mi = *reinterpret_cast<Misc *>(smem + MISC_OFF);
-    const TcLearner L = a.learners[blockIdx.x];
+    TcLearner L = a.learners[blockIdx.x];
+    if (a.round0) {   // a later chunk of the same call: shift every per-round array once
+        L.slots += (size_t)a.round0 * a.B;
+        L.scal += a.round0;
+        L.out_mae += a.round0;
+        if (L.out_q) L.out_q += (size_t)a.round0 * a.B;
+        if (L.out_y) L.out_y += (size_t)a.round0 * a.B;
+        L.steps0 += a.round0;
+    }
     const Dims &d = a.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = tid & 127, h = tid >> 7;
@@ -747,15 +756,24 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     if (warp == 0) umma::tmem_dealloc(tm, 512);
 }
 
+// a few microseconds of nothing: lets the learner CTAs of the main stream take their SMs before the next chunk's
+// index producers (side stream) become ready
+__global__ void k_delay(unsigned ns) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)ns * 2) __nanosleep(200);
+}
+
 // all learners' index streams in one launch: CTA i draws `rounds` samples for learner i
 struct MultiSampler {
     uint32_t *mt_state;
     SamplerParams sp;
 };
-__global__ void __launch_bounds__(kSamplerThreads, 1) k_sample_indices_multi(const MultiSampler *items, int rounds) {
+__global__ void __launch_bounds__(kSamplerThreads, 1) k_sample_indices_multi(const MultiSampler *items, int rounds, int round0) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ SamplerState S;
-    const MultiSampler it = items[blockIdx.x];
+    MultiSampler it = items[blockIdx.x];
+    if (it.sp.out_slot) it.sp.out_slot += (size_t)round0 * it.sp.k;
+    if (it.sp.out_logical) it.sp.out_logical += (size_t)round0 * it.sp.k;
     sampler_init(S, it.mt_state, dyn, it.sp);
     sampler_advance(S, dyn, it.sp, rounds);
     __syncthreads();
@@ -836,14 +854,12 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
     PRL_CUDA(cudaEventRecord(h_done, stream));
 
     PRL_CUDA(cudaFuncSetAttribute(k_sample_indices_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_sample_indices_multi<<<count, kSamplerThreads, samp_smem, stream>>>(d_samp, rounds);
-    PRL_CUDA(cudaGetLastError());
 
     TcArgs a;
     a.learners = d_learn;
     a.lay = bufs[0]->lay;
     a.d = q0->d;
-    a.B = batch; a.rounds = rounds; a.freq = c.target_update_freq;
+    a.B = batch; a.rounds = rounds; a.freq = c.target_update_freq; a.round0 = 0;
     a.decay = (float)(1.0 - c.lr * c.weight_decay);
     a.omb1 = (float)(1.0 - c.beta1);
     a.beta2 = (float)c.beta2;
@@ -857,13 +873,46 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
     const size_t smem = MISC_OFF + sizeof(Misc);
     PRL_REQUIRE(smem <= (size_t)q0->max_smem, "tensor-core learner needs %zu B of shared memory", smem);
     PRL_CUDA(cudaFuncSetAttribute(k_dqn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (q0->timing) PRL_CUDA(cudaEventRecord(q0->t0, stream));
-    k_dqn_tc<<<count, NTH, smem, stream>>>(a);
+
+    // The index streams are produced in chunks of rounds: chunk 0 ahead of the first learner launch, chunk c + 1 on a
+    // side stream WHILE the learners run chunk c (one learner CTA fills an SM, so the producers of the next chunk run
+    // on the SMs the group leaves free; with no spare SM they simply run between the learner launches).
+    const int spare = q0->sm_count - count;
+    int nchunks = 1;
+    if (!q0->prof && spare >= 2 && rounds >= 64) nchunks = rounds >= 256 ? 4 : 2;
+    static thread_local cudaStream_t side = nullptr;
+    static thread_local cudaEvent_t ev_idx[8], ev_fork = nullptr;
+    if (nchunks > 1 && !side) {
+        PRL_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        for (auto &e : ev_idx) PRL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        PRL_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    }
+    auto chunk_begin = [&](int cix) { return (int)((long long)rounds * cix / nchunks); };
+    k_sample_indices_multi<<<count, kSamplerThreads, samp_smem, stream>>>(d_samp, chunk_begin(1), 0);
     PRL_CUDA(cudaGetLastError());
+    if (nchunks > 1) {
+        PRL_CUDA(cudaEventRecord(ev_fork, stream));
+        PRL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    }
+    if (q0->timing) PRL_CUDA(cudaEventRecord(q0->t0, stream));
+    for (int cix = 0; cix < nchunks; cix++) {
+        const int r0 = chunk_begin(cix), r1 = chunk_begin(cix + 1);
+        if (cix > 0) PRL_CUDA(cudaStreamWaitEvent(stream, ev_idx[cix], 0));
+        a.round0 = r0; a.rounds = r1 - r0;
+        k_dqn_tc<<<count, NTH, smem, stream>>>(a);
+        PRL_CUDA(cudaGetLastError());
+        if (cix + 1 < nchunks) {
+            const int n0 = r1, n1 = chunk_begin(cix + 2);
+            k_delay<<<1, 1, 0, side>>>(30000u);
+            k_sample_indices_multi<<<count, kSamplerThreads, samp_smem, side>>>(d_samp, n1 - n0, n0);
+            PRL_CUDA(cudaGetLastError());
+            PRL_CUDA(cudaEventRecord(ev_idx[cix + 1], side));
+        }
+    }
     if (q0->timing) PRL_CUDA(cudaEventRecord(q0->t1, stream));
     for (int i = 0; i < count; i++) {
         dqns[i]->adam_step += rounds;
-        dqns[i]->last_launches = 2;
+        dqns[i]->last_launches = 3 * nchunks - 1;   // index producers + learner launches + the side-stream delays
         dqns[i]->last_ctas = 1;
         dqns[i]->last_rows = batch;
     }

@@ -408,9 +408,9 @@ class B200LearnerGroup:
                 done += r
             for b in self.buffers:
                 b._rng_pull()
-        host = mae.cpu()
-        for l in self.learners:
+        for l in self.learners:          # host-side bookkeeping while the GPU works
             l._sync_step_tensors()
+        host = mae.cpu()                 # the one device->host read of the call
         return [{"loss": host[i].tolist()} for i in range(n)]
 
     def push_batch(self, state, action, reward, next_state, terminated, truncated) -> None:
