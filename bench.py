@@ -427,10 +427,11 @@ def other_paths(dev, args) -> dict:
         buf.is_action_continuous = True
         for s0 in range(0, cap, 1 << 17):
             m = min(1 << 17, cap - s0)
-            buf.push_batch(rn(m, obs), rn(m, act).clamp(-1, 1), rn(m), rn(m, obs), torch.rand(m, device=dev, generator=gen) < 0.01,
+            buf.push_batch(rn(m, obs), (torch.rand(m, act, device=dev, generator=gen) * 0.8 - 0.4), rn(m), rn(m, obs),
+                           torch.rand(m, device=dev, generator=gen) < 0.01,
                            torch.zeros(m, dtype=torch.bool, device=dev))
         buf.seed(5)
-        pl = pearl_b200.B200ContinuousSoftActorCritic(state_dim=obs, low=[-1.0] * act, high=[1.0] * act, actor_hidden_dims=[256, 256],
+        pl = pearl_b200.B200ContinuousSoftActorCritic(state_dim=obs, low=[-0.4] * act, high=[0.4] * act, actor_hidden_dims=[256, 256],
                                                        critic_hidden_dims=[256, 256], training_rounds=R, batch_size=B, device=dev, seed=1)
         sec = timed(lambda: pl.learn(buf), 3)
         out["sac"] = {"workload": "SAC continuous obs_dim=376 act_dim=17, 1M replay, batch=512 (configs[2])", "value": R / sec,
@@ -439,8 +440,8 @@ def other_paths(dev, args) -> dict:
         del pl, buf
         if not args.no_cpu:
             from oracle.sac_oracle import OracleSAC
-            orc = OracleSAC(obs, act, (256, 256), (256, 256), [-1.0] * act, [1.0] * act)
-            b = dict(state=torch.randn(B, obs), action=torch.rand(B, act) * 2 - 1, reward=torch.randn(B), next_state=torch.randn(B, obs),
+            orc = OracleSAC(obs, act, (256, 256), (256, 256), [-0.4] * act, [0.4] * act)
+            b = dict(state=torch.randn(B, obs), action=torch.rand(B, act) * 0.8 - 0.4, reward=torch.randn(B), next_state=torch.randn(B, obs),
                      terminated=torch.zeros(B, dtype=torch.bool))
             n1, n2 = torch.randn(B, act), torch.randn(B, act)
             rate, nt = cpu_rate(lambda: orc.learn_batch(b, n1, n2))
@@ -450,23 +451,25 @@ def other_paths(dev, args) -> dict:
 
     # ---- PPO (configs[3], one GPU's rollout): 64k-step rollout, obs 210, [256, 256] networks, batch 256
     def ppo():
-        obs, A, n, B, R = 210, 8, 65536, 256, 100
+        obs, A, n, B, R, hid = 210, 16, 65536, 256, 100, [64, 64]
         buf = pearl_b200.B200ReplayBuffer(n, device=dev, rng="device")
         buf.push_batch(rn(n, obs), torch.randint(0, A, (n,), device=dev, generator=gen).to(torch.int32), rn(n), rn(n, obs),
-                       torch.rand(n, device=dev, generator=gen) < 0.002, torch.rand(n, device=dev, generator=gen) < 0.001, max_number_actions=A)
+                       (torch.arange(n, device=dev) % 500) == 499, torch.zeros(n, dtype=torch.bool, device=dev), max_number_actions=A)
         buf.seed(6)
-        pl = pearl_b200.B200ProximalPolicyOptimization(state_dim=obs, n_actions=A, actor_hidden_dims=[256, 256], critic_hidden_dims=[256, 256],
-                                                        training_rounds=R, batch_size=B, epsilon=0.2, device=dev, seed=2)
+        pl = pearl_b200.B200ProximalPolicyOptimization(state_dim=obs, n_actions=A, actor_hidden_dims=hid, critic_hidden_dims=hid,
+                                                        training_rounds=R, batch_size=B, epsilon=0.1, discount_factor=0.99,
+                                                        trace_decay_param=0.95, device=dev, seed=2)
         pre_sec = timed(lambda: pl.preprocess_replay_buffer(buf), 5)
         sec = timed(lambda: pl.learn(buf), 3)
-        out["ppo"] = {"workload": "PPO 64k-step rollout obs_dim=210, GAE + clipped surrogate, batch=256 (configs[3], one GPU)",
+        out["ppo"] = {"workload": "PPO 64k-step rollout obs_dim=210, 16 actions, [64,64] networks, GAE + clipped surrogate, batch=256 "
+                                  "(configs[3] / SURVEY cfg4, one GPU)",
                       "preprocess_ms": pre_sec * 1e3, "preprocess_transitions_per_s": n / pre_sec,
                       "value": R / (sec - pre_sec), "unit": "gradient-steps/s (actor + critic steps, preprocessing excluded)",
                       "learn_ms": sec * 1e3, "training_rounds": R}
         del pl, buf
         if not args.no_cpu:
             from oracle.ppo_oracle import OraclePPO
-            orc = OraclePPO(obs, A, (256, 256), (256, 256), epsilon=0.2, batch_size=B, training_rounds=1)
+            orc = OraclePPO(obs, A, tuple(hid), tuple(hid), epsilon=0.1, batch_size=B, training_rounds=1)
             ns = 4096
             st, ac = torch.randn(ns + 1, obs), torch.randint(0, A, (ns,))
             torch.set_num_threads(min(8, cores))
@@ -490,12 +493,12 @@ def other_paths(dev, args) -> dict:
             m = min(1 << 17, cap - s0)
             buf.push_batch(rn(m, obs), (torch.arange(s0, s0 + m, device=dev) % A).to(torch.int32), rn(m), rn(m, obs),
                            torch.rand(m, device=dev, generator=gen) < 0.02, torch.zeros(m, dtype=torch.bool, device=dev), max_number_actions=A)
-        ddqn = pearl_b200.B200DoubleDQN(state_dim=obs, action_space=Space(A), hidden_dims=[128, 128], training_rounds=R, batch_size=B,
+        ddqn = pearl_b200.B200DoubleDQN(state_dim=obs, action_space=Space(A), hidden_dims=[64, 64], training_rounds=R, batch_size=B,
                                         target_update_freq=10, soft_update_tau=0.75,
                                         action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(A),
                                         max_rounds_per_call=R).to(dev)
         sec = timed(lambda: ddqn.learn(buf), 3)
-        out["prioritized_ddqn"] = {"workload": f"prioritized segment-tree replay {cap} x obs_dim=512, DoubleDQN, batch=256 (configs[4], one GPU's shard)",
+        out["prioritized_ddqn"] = {"workload": f"prioritized segment-tree replay {cap} x obs_dim=512, DoubleDQN [64,64], batch=256 (configs[4] / SURVEY cfg5 on one GPU)",
                                    "value": R / sec, "unit": "gradient-steps/s (stratified tree draw + weighted step + priority update)",
                                    "us_per_step": sec / R * 1e6, "replay_bytes": cap * buf.record_bytes}
         del ddqn, buf

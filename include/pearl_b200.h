@@ -385,9 +385,16 @@ int prl_ppo_destroy(prl_ppo *ppo);
 int64_t prl_ppo_adam_step(const prl_ppo *ppo);
 int prl_ppo_set_graph(prl_ppo *ppo, int enable);
 int64_t prl_ppo_last_launches(const prl_ppo *ppo);
-/* outputs: device f32[len(buf)] each, index 0 = oldest stored transition */
+/* outputs: device f32[len(buf)] each, index 0 = oldest stored transition; out_cut_dev (optional) u8[len]:
+ * 1 where the transition is terminated or truncated (ends a GAE chain) */
 int prl_ppo_preprocess(prl_ppo *ppo, prl_buf *buf, float *out_values_dev, float *out_action_probs_dev,
-                       float *out_gae_dev, float *out_lam_return_dev, void *stream);
+                       float *out_gae_dev, float *out_lam_return_dev, uint8_t *out_cut_dev, void *stream);
+/* Rollout sharded over ranks by contiguous time chunks: re-run this chunk's GAE chains with V(next) of its newest
+ * transition = `next_value` (first state value of the next, newer chunk) and the chain entering from there =
+ * `incoming_gae` (that chunk's first gae).  Uses the rewards / flags staged by the last prl_ppo_preprocess.
+ * Bit-identical to the unsharded computation. */
+int prl_ppo_gae_redo(prl_ppo *ppo, const float *values_dev, float next_value, float incoming_gae,
+                     float *out_gae_dev, float *out_lam_return_dev, void *stream);
 /* gae / lam_return / action_probs: the arrays prl_ppo_preprocess produced; out_*_loss: device f32[rounds] */
 int prl_ppo_learn(prl_ppo *ppo, prl_buf *buf, int rounds, int batch, const float *gae_dev,
                   const float *lam_return_dev, const float *action_probs_dev, float *out_actor_loss_dev,

@@ -21,12 +21,15 @@ import torch
 from .pearl_oracle import _mlp, flat, load_flat  # noqa: F401
 
 
-def gae_reference_loop(values, last_next_value, reward, terminated, truncated, discount_factor, trace_decay_param):
+def gae_reference_loop(values, last_next_value, reward, terminated, truncated, discount_factor, trace_decay_param,
+                       incoming_gae=0.0):
+    """`incoming_gae`: the chain entering from newer transitions held elsewhere (0.0 = the reference's start value);
+    used to check the sharded rollout protocol (pearl_b200/dist.py: sharded_gae_fixup)."""
     n = values.shape[0]
     gae_out = torch.empty(n, dtype=torch.float32)
     lam_out = torch.empty(n, dtype=torch.float32)
     next_value = torch.as_tensor(last_next_value, dtype=torch.float32).reshape(1)
-    gae = torch.tensor([0.0])
+    gae = torch.tensor([float(incoming_gae)])
     for t in range(n - 1, -1, -1):
         term, trunc = terminated[t].reshape(1), truncated[t].reshape(1)
         td_error = reward[t].reshape(1) + discount_factor * next_value * (~term) - values[t].reshape(1)

@@ -123,7 +123,8 @@ _SIGNATURES = {
     "prl_ppo_adam_step": (C.c_int64, [_P]),
     "prl_ppo_set_graph": (C.c_int, [_P, C.c_int]),
     "prl_ppo_last_launches": (C.c_int64, [_P]),
-    "prl_ppo_preprocess": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "prl_ppo_preprocess": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "prl_ppo_gae_redo": (C.c_int, [_P, _P, C.c_float, C.c_float, _P, _P, _P]),
     "prl_ppo_learn": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "prl_dqn_set_timing": (C.c_int, [_P, C.c_int]),
     "prl_dqn_set_profile": (C.c_int, [_P, _P]),

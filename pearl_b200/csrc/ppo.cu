@@ -24,7 +24,7 @@ namespace {
 
 // arrays are in TIME order (index 0 = oldest stored transition)
 __global__ void k_ppo_gae(int n, const float *__restrict__ values, float last_next_value_host,
-                          const float *__restrict__ last_next_value_dev, const float *__restrict__ reward, const uint8_t *__restrict__ terminated,
+                          const float *__restrict__ last_next_value_dev, float incoming_gae, const float *__restrict__ reward, const uint8_t *__restrict__ terminated,
                           const uint8_t *__restrict__ truncated, float gamma, float c_live,
                           float *__restrict__ out_gae, float *__restrict__ out_lam_return) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,7 +32,9 @@ __global__ void k_ppo_gae(int n, const float *__restrict__ values, float last_ne
     const bool head = (t == n - 1) || terminated[t] || truncated[t];   // newest element of its chain
     if (!head) return;
     const float last_next_value = last_next_value_dev ? *last_next_value_dev : last_next_value_host;
-    float gae = 0.f;
+    // the chain headed by the newest element continues a chain of NEWER transitions held elsewhere (a later time
+    // shard): it starts from that chain's gae instead of 0 (multiplied by 0 below if the newest element ends an episode)
+    float gae = (t == n - 1) ? incoming_gae : 0.f;
     for (int s = t; s >= 0; s--) {
         const bool term = terminated[s] != 0, cut = term || truncated[s] != 0;
         if (s != t && cut) break;                                       // the next chain's head
@@ -58,7 +60,7 @@ extern "C" int prl_ppo_gae(int n, const float *values_dev, float last_next_value
                 "null argument");
     const int threads = 256;
     k_ppo_gae<<<(n + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-        n, values_dev, last_next_value, nullptr, reward_dev, terminated_dev, truncated_dev, (float)gamma, (float)(gamma * lam),
+        n, values_dev, last_next_value, nullptr, 0.f, reward_dev, terminated_dev, truncated_dev, (float)gamma, (float)(gamma * lam),
         out_gae_dev, out_lam_return_dev);
     PRL_CUDA(cudaGetLastError());
     return PRL_OK;
@@ -194,6 +196,10 @@ __global__ void k_ppo_critic_loss(int B, const float *__restrict__ v, const floa
     if (threadIdx.x == 0) call->out_critic[*round_idx] = red[0] * ib;
 }
 __global__ void k_ppo_bump(int *round_idx) { *round_idx += 1; }
+__global__ void k_ppo_cuts(int n, const uint8_t *__restrict__ term, const uint8_t *__restrict__ trunc, uint8_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (term[i] | trunc[i]) ? 1 : 0;
+}
 
 }  // namespace
 
@@ -219,6 +225,7 @@ struct prl_ppo {
     const uint32_t *graph_buf;
     int launches_per_round;
     int64_t last_launches;
+    int64_t pre_n;      // rollout length of the last prl_ppo_preprocess
 };
 
 static const int kPpoChunk = 8192;   // rollout rows evaluated per pass of the preprocessing
@@ -299,6 +306,7 @@ extern "C" int prl_ppo_create(prl_ppo **out, const prl_ppo_cfg *cfg, float *acto
     s->call = (PpoCall *)(s->scal_c + cfg->max_rounds); s->round_idx = (int *)(s->call + 1);
     static_assert(sizeof(PpoCall) + 4 <= 256, "call block fits the reserved tail");
     s->scal_next = 0; s->use_graph = true; s->graph_exec = nullptr; s->graph_batch = 0; s->graph_buf = nullptr; s->last_launches = 0;
+    s->pre_n = 0;
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
         e = cudaHostAlloc((void **)&s->scal_host[i], (size_t)cfg->max_rounds * 16 + 256, cudaHostAllocDefault);
@@ -341,7 +349,7 @@ static void ppo_critic_forward(prl_ppo *s, GemmLauncher &L, int rows, float *vou
 // preprocess_replay_buffer (ppo.py:201-293): state values, taken-action probabilities, GAE and lambda returns of the whole
 // rollout, in time order (index 0 = oldest stored transition)
 extern "C" int prl_ppo_preprocess(prl_ppo *s, prl_buf *buf, float *out_values, float *out_action_probs, float *out_gae,
-                                  float *out_lam_return, void *stream_) {
+                                  float *out_lam_return, uint8_t *out_cut, void *stream_) {
     PRL_REQUIRE(s && buf && out_values && out_action_probs && out_gae && out_lam_return, "null argument");
     const prl_ppo_cfg &c = s->cfg;
     PRL_REQUIRE((buf->desc.flags & PRL_BUF_DISCRETE) && buf->desc.obs_dim == c.obs_dim && buf->desc.n_actions == c.n_actions,
@@ -362,8 +370,26 @@ extern "C" int prl_ppo_preprocess(prl_ppo *s, prl_buf *buf, float *out_values, f
     }
     k_ppo_last_next_state<<<1, 128, 0, st>>>(buf->records, buf->lay, c.obs_dim, (head + n - 1) % cap, s->S);
     ppo_critic_forward(s, L, 1, s->last_value);
-    k_ppo_gae<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, out_values, 0.f, s->last_value, s->reward, s->term, s->trunc, (float)c.gamma,
+    k_ppo_gae<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, out_values, 0.f, s->last_value, 0.f, s->reward, s->term, s->trunc, (float)c.gamma,
                                                       (float)(c.gamma * c.lam), out_gae, out_lam_return);
+    if (out_cut) k_ppo_cuts<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, s->term, s->trunc, out_cut);
+    PRL_CUDA(cudaGetLastError());
+    s->pre_n = n;
+    return PRL_OK;
+}
+
+// A rollout sharded over ranks by contiguous time chunks: the GAE recurrence of this chunk continues into
+// the next (newer) chunk.  Re-run the chunk's chains with V(next) of its newest transition = the first state value of the
+// next chunk and the chain entering from there = that chunk's first gae.  Same fp32 operation order as the unsharded
+// kernel, so the sharded result is bit-identical to the whole rollout on one GPU.
+extern "C" int prl_ppo_gae_redo(prl_ppo *s, const float *values_dev, float next_value, float incoming_gae, float *out_gae,
+                                float *out_lam_return, void *stream_) {
+    PRL_REQUIRE(s && values_dev && out_gae && out_lam_return, "null argument");
+    PRL_REQUIRE(s->pre_n > 0, "prl_ppo_preprocess has not run on this handle");
+    const prl_ppo_cfg &c = s->cfg;
+    const int64_t n = s->pre_n;
+    k_ppo_gae<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((int)n, values_dev, next_value, nullptr, incoming_gae, s->reward, s->term,
+                                                                      s->trunc, (float)c.gamma, (float)(c.gamma * c.lam), out_gae, out_lam_return);
     PRL_CUDA(cudaGetLastError());
     return PRL_OK;
 }

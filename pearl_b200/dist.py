@@ -38,6 +38,37 @@ def shard_owner(global_write_index: int, world: int) -> tuple:
     return global_write_index % world, global_write_index // world
 
 
+def sharded_gae_fixup(v0: float, g0: float, has_cut: bool, redo, group=None, device: Optional[torch.device] = None) -> int:
+    """GAE over a rollout sharded by contiguous time chunks, rank r holding chunk r (the recurrence of
+    ppo.py:271-293 runs newest -> oldest, so chunk r continues into chunk r + 1).
+
+    After its local pass every rank knows `v0` (state value of its oldest transition), `g0` (gae of its oldest
+    transition) and `has_cut` (the chunk contains a terminated / truncated transition, which makes g0 independent of
+    newer chunks).  One all-gather of 4 floats per rank and round; a rank whose successor's g0 is final calls
+    `redo(next_value, incoming_gae)` once (it recomputes the chunk's chains and returns the new g0).  Chunks without an
+    episode end propagate sequentially, one round per such chunk; otherwise two rounds.  Returns the number of rounds."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    if dev is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    final = bool(has_cut) or rank == world - 1     # g0 no longer depends on newer chunks
+    done = rank == world - 1                       # every element of the chunk is final
+    rounds = 0
+    while True:
+        mine = torch.tensor([v0, g0, float(final), float(done)], dtype=torch.float32, device=dev)
+        table = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(table, mine, group=group)
+        table = [t.cpu() for t in table]
+        rounds += 1
+        if all(bool(t[3]) for t in table):
+            return rounds
+        if not done and bool(table[rank + 1][2]):
+            g0 = float(redo(float(table[rank + 1][0]), float(table[rank + 1][1])))
+            final = done = True
+        if rounds > world + 1:
+            raise RuntimeError("sharded GAE did not converge (inconsistent shards?)")
+
+
 class B200Communicator:
     """NVLink peer-memory communicator for B200DeepQLearning / B200DoubleDQN."""
 

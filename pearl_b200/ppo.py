@@ -152,7 +152,11 @@ class B200ProximalPolicyOptimization:
                 p(self._critic_state[2]), self._adam_step, p(self._workspace)))
         self._handle, self._bound_batch = h, cfg.max_batch
 
-    def preprocess_replay_buffer(self, replay_buffer) -> dict:
+    def preprocess_replay_buffer(self, replay_buffer, process_group=None) -> dict:
+        """`process_group`: the rollout is sharded over the ranks of that torch.distributed group by contiguous time
+        chunks (rank r holds chunk r, rank world-1 the newest transitions).  The network passes are row-parallel; the
+        GAE chains are stitched with `pearl_b200.dist.sharded_gae_fixup` (4 floats per rank and round) and come out
+        bit-identical to the unsharded rollout.  The training rounds of `learn()` stay local to each shard."""
         n = len(replay_buffer)
         if n == 0:
             raise AssertionError("preprocess_replay_buffer needs a non-empty rollout")
@@ -162,14 +166,24 @@ class B200ProximalPolicyOptimization:
         self._bind(B)
         dev = self._device
         out = {k: torch.empty(n, dtype=torch.float32, device=dev) for k in ("values", "action_probs", "gae", "lam_return")}
+        cut = torch.empty(n, dtype=torch.uint8, device=dev) if process_group is not None else None
         with torch.cuda.device(dev):
             _lib.check(self._lib.prl_ppo_preprocess(self._handle, replay_buffer.handle, _lib.ptr(out["values"]),
                                                     _lib.ptr(out["action_probs"]), _lib.ptr(out["gae"]), _lib.ptr(out["lam_return"]),
-                                                    _stream_ptr(dev)))
+                                                    _lib.ptr(cut), _stream_ptr(dev)))
+            if process_group is not None:
+                from .dist import sharded_gae_fixup
+
+                def redo(next_value: float, incoming_gae: float) -> float:
+                    _lib.check(self._lib.prl_ppo_gae_redo(self._handle, _lib.ptr(out["values"]), next_value, incoming_gae,
+                                                          _lib.ptr(out["gae"]), _lib.ptr(out["lam_return"]), _stream_ptr(dev)))
+                    return float(out["gae"][0].item())
+                self.last_shard_rounds = sharded_gae_fixup(float(out["values"][0].item()), float(out["gae"][0].item()),
+                                                           bool(cut.any().item()), redo, group=process_group, device=dev)
         self.last_preprocess = out
         return out
 
-    def learn(self, replay_buffer, trace: dict | None = None) -> dict:
+    def learn(self, replay_buffer, trace: dict | None = None, process_group=None) -> dict:
         from .replay_buffer import B200ReplayBuffer
         if not isinstance(replay_buffer, B200ReplayBuffer):
             raise TypeError("B200ProximalPolicyOptimization learns from a B200ReplayBuffer (GPU-resident rollout)")
@@ -178,7 +192,7 @@ class B200ProximalPolicyOptimization:
             return {}
         if replay_buffer.is_action_continuous:
             raise ValueError("the PPO learner supports discrete actions (as the reference's `_actor_loss` does)")
-        pre = self.preprocess_replay_buffer(replay_buffer)
+        pre = self.preprocess_replay_buffer(replay_buffer, process_group=process_group)
         B = n if (self._batch_size == -1 or n < self._batch_size) else self._batch_size
         R, dev = self._training_rounds, self._device
         report = {"actor_loss": [], "critic_loss": []}
