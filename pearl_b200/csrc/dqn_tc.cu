@@ -829,7 +829,10 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
                     "buffer %d does not match the learner", i);
         PRL_REQUIRE(b->lay.record_words == bufs[0]->lay.record_words && b->lay.off_avail == bufs[0]->lay.off_avail,
                     "buffers must share one record layout");
-        int rc = prl_dqn_stage_scalars(q, rounds, stream);
+        // the per-round AdamW scalars (two double pow() per round, as torch evaluates them) depend only on the shared
+        // configuration and the step count: learners at the same step read learner 0's copy
+        const bool shared_scal = i > 0 && q->adam_step == q0->adam_step;
+        int rc = shared_scal ? PRL_OK : prl_dqn_stage_scalars(q, rounds, stream);
         if (rc) return rc;
         size_t sbytes = 0;
         rc = prl_sampler_params(b, batch, &h_samp[i].sp, &sbytes);
@@ -841,7 +844,7 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
         TcLearner &L = h_learn[i];
         L.records = b->records; L.slots = q->slots;
         L.w = q->w; L.wt = q->wt; L.m = q->m; L.v = q->v; L.vmax = q->vmax;
-        L.scal = q->scal_dev;
+        L.scal = shared_scal ? q0->scal_dev : q->scal_dev;
         L.out_mae = out_mae[i]; L.out_q = out_q ? out_q[i] : nullptr; L.out_y = out_y ? out_y[i] : nullptr;
         L.steps0 = training_steps0[i];
         L.buf_flags = b->desc.flags;
