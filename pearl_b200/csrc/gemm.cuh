@@ -50,15 +50,16 @@ struct GemmArgs {
 constexpr int GK = 32;   // contraction chunk
 
 // AO / BO: true = the Mat's ROW index is the output index (features are contracted); false = rows are contracted
-template <int TM, int TN, bool AO, bool BO>
-__global__ void __launch_bounds__((TM / 4) * (TN / 4)) k_gemm(const GemmArgs g) {
-    constexpr int NT = (TM / 4) * (TN / 4), LA = TM * GK / NT, LB = TN * GK / NT;
+// MR x 4 outputs per thread: MR = 4 for the big tiles, MR = 2 doubles the warps of the small (latency-bound) tiles
+template <int TM, int TN, int MR, bool AO, bool BO>
+__global__ void __launch_bounds__((TM / MR) * (TN / 4)) k_gemm(const GemmArgs g) {
+    constexpr int NT = (TM / MR) * (TN / 4), LA = TM * GK / NT, LB = TN * GK / NT;
     __shared__ __align__(16) float As[GK][TM + 4], Bs[GK][TN + 4];
     const int tid = threadIdx.x, tx = tid % (TN / 4), ty = tid / (TN / 4), z = blockIdx.z;
     const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
-    float acc[4][4];
+    float acc[MR][4];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < MR; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
     float ra[LA], rb[LB];
@@ -112,19 +113,26 @@ __global__ void __launch_bounds__((TM / 4) * (TN / 4)) k_gemm(const GemmArgs g) 
         if (c0 + GK < g.Kc) fetch(c0 + GK);
 #pragma unroll
         for (int c = 0; c < GK; c++) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[c][ty * 4]);
+            float av[MR];
+            if constexpr (MR == 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(&As[c][ty * 4]);
+                av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+            } else {
+                const float2 a = *reinterpret_cast<const float2 *>(&As[c][ty * 2]);
+                av[0] = a.x; av[1] = a.y;
+            }
             const float4 b = *reinterpret_cast<const float4 *>(&Bs[c][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int p = 0; p < 4; p++)
+            for (int p = 0; p < MR; p++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const int i = i0 + ty * 4 + p;
+    for (int p = 0; p < MR; p++) {
+        const int i = i0 + ty * MR + p;
         if (i >= g.Mo) continue;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -150,10 +158,10 @@ struct GemmLauncher {
         const long long big = (long long)((g.Mo + 63) / 64) * ((g.No + 63) / 64) * nets;
         if (big >= 96) {       // enough 64x64 tiles to occupy the chip
             dim3 grid((g.Mo + 63) / 64, (g.No + 63) / 64, nets);
-            k_gemm<64, 64, AO, BO><<<grid, 256, 0, st>>>(g);
-        } else {               // small problem: 4x the CTAs, 2 warps each
+            k_gemm<64, 64, 4, AO, BO><<<grid, 256, 0, st>>>(g);
+        } else {               // small problem: 4x the CTAs, 4 warps each (2 x 4 outputs per thread)
             dim3 grid((g.Mo + 31) / 32, (g.No + 31) / 32, nets);
-            k_gemm<32, 32, AO, BO><<<grid, 64, 0, st>>>(g);
+            k_gemm<32, 32, 2, AO, BO><<<grid, 128, 0, st>>>(g);
         }
         count++;
     }
