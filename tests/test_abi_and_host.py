@@ -106,3 +106,34 @@ def test_plugins_subclass_pearl_when_available():
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_ctypes_signatures_match_the_header_arity():
+    """Every ctypes binding takes exactly as many arguments as the C declaration (a mismatch would corrupt the call
+    silently); pointer / integer / floating classes are compared as well."""
+    from pearl_b200 import _lib
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef struct[^;{]*\{.*?\}[^;]*;", "", src, flags=re.S)
+    decls = dict(re.findall(r"\b(prl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(decls) == set(_lib.EXPORTS)
+
+    def kind(c_param: str) -> str:
+        p = " ".join(c_param.split())
+        if "*" in p or "[" in p:          # arrays decay to pointers
+            return "ptr"
+        base = p.rsplit(" ", 1)[0] if " " in p else p
+        return "float" if base in ("float", "double") else "int"
+
+    def ckind(t) -> str:
+        if t in (ctypes.c_float, ctypes.c_double):
+            return "float"
+        if t in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint):
+            return "int"
+        return "ptr"
+    for name, params in decls.items():
+        plist = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        _, argtypes = _lib._SIGNATURES[name]
+        assert len(plist) == len(argtypes), f"{name}: header has {len(plist)} parameters, ctypes table {len(argtypes)}"
+        for i, (cp, at) in enumerate(zip(plist, argtypes)):
+            assert kind(cp) == ckind(at), f"{name} argument {i}: `{' '.join(cp.split())}` bound as {at}"
