@@ -770,7 +770,7 @@ extern "C" int64_t prl_dqn_param_count(const prl_dqn_cfg *c) {
     return make_dims(c->obs_dim, c->n_actions, c->hidden1, c->hidden2).P;
 }
 
-struct WsPlan { int64_t gpart, slots, logical, scal, tmp_rec, tmp_slots, multi, is_w, td, total; };
+struct WsPlan { int64_t gpart, slots, logical, scal, tmp_rec, tmp_slots, multi, is_w, td, tc_tiles, total; };
 static WsPlan ws_plan(const prl_dqn_cfg *c) {
     Dims d = make_dims(c->obs_dim, c->n_actions, c->hidden1, c->hidden2);
     WsPlan w;
@@ -784,6 +784,7 @@ static WsPlan ws_plan(const prl_dqn_cfg *c) {
     w.multi = o; o = align_up64(o + 64 * 1024, 256);
     w.is_w = o; o = align_up64(o + (int64_t)c->max_rounds * c->max_batch * 4, 256);
     w.td = o; o = align_up64(o + (int64_t)c->max_batch * 4, 256);
+    w.tc_tiles = o; o = align_up64(o + prl_tc_tile_floats(c) * 4, 256);
     w.total = o;
     return w;
 }
@@ -816,6 +817,7 @@ extern "C" int prl_dqn_create(prl_dqn **out, const prl_dqn_cfg *cfg, float *w, f
     q->multi_dev = (void *)(base + ws.multi);
     q->is_w = (float *)(base + ws.is_w);
     q->td = (float *)(base + ws.td);
+    q->tc_tiles = prl_tc_tile_floats(cfg) ? (float *)(base + ws.tc_tiles) : nullptr;
     q->tmp_lay = tmp_layout(cfg);
     q->scal_next = 0;
     q->scal_host[0] = q->scal_host[1] = nullptr;

@@ -59,6 +59,7 @@ struct prl_dqn {
     uint32_t *tmp_rec;
     float *is_w, *td;         // prioritized replay: importance weights [rounds][B], |q-y| [B]
     void *multi_dev;          // 64 KB: per-learner descriptors of a multi-learner launch
+    float *tc_tiles;          // operand-layout weight tiles of the tensor-core learner (dqn_tc.cu), or null
     int32_t *tmp_slots;
     prl_buf_layout tmp_lay;
     // pinned per-round optimizer scalars, double buffered
@@ -76,3 +77,10 @@ struct prl_dqn {
 
 
 int prl_dqn_stage_scalars(prl_dqn *q, int rounds, cudaStream_t stream);
+
+// floats of the tensor-core learner's operand-layout weight tiles (online W1s | W2 | W2^T, target W1s | W2, each
+// stacked [hi ; lo] = 128 rows), 0 for shapes outside its class
+inline int64_t prl_tc_tile_floats(const prl_dqn_cfg *c) {
+    if (c->hidden1 != 64 || c->hidden2 != 64 || c->obs_dim > 128 || c->obs_dim % 8) return 0;
+    return 2ll * 128 * c->obs_dim + 3ll * 128 * 64;
+}

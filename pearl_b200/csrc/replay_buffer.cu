@@ -99,6 +99,12 @@ extern "C" int prl_buf_create(prl_buf **out, const prl_buf_desc *desc, void *sto
     b->stage_records = 0;
     b->stage_next = 0;
     cudaGetDevice(&b->device);
+    // never leave the MT19937 stream all-zero (it twists to zeros for ever: the set-branch sampler would then
+    // spin on duplicates): a distinct default stream per buffer until the caller seeds / hands over a state
+    static uint32_t created = 0;
+    const uint32_t key[2] = {0x9e3779b9u, ++created};
+    rc = prl_rng_seed(b, key, 2, nullptr);
+    if (rc) { delete b; return rc; }
     *out = b;
     return PRL_OK;
 }
@@ -397,6 +403,9 @@ extern "C" int prl_buf_push_device(prl_buf *b, int64_t n, const float *state, co
 extern "C" int prl_rng_set_state(prl_buf *b, const uint32_t *st, void *stream) {
     PRL_REQUIRE(b && st, "null argument");
     PRL_REQUIRE(st[624] <= 624, "MT19937 position must be in [0,624]");
+    uint32_t any = 0;
+    for (int i = 0; i < 624; i++) any |= st[i];
+    PRL_REQUIRE(any != 0, "all-zero MT19937 state (not a state random.getstate() can return; it never leaves zero)");
     PRL_CUDA(cudaMemcpyAsync(b->mt_state, st, 625 * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     PRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // `st` may be a temporary
     return PRL_OK;

@@ -107,11 +107,15 @@ class _B200DQNMixin:
                 "(PearlAgent(device_id=0) does this); pearl_b200 has no CPU path" % device)
         if (self._handle.value and self._bound_ptr == params[0].data_ptr()
                 and need_batch <= self._bound_batch):
+            self._refresh_optimizer_binding(params)
             return
         old_state = None
         if self._handle.value:
-            old_state = {k: v.clone() for k, v in self._flat.items() if k in ("m", "v", "vmax")}
-            old_step = int(self._libh.prl_dqn_adam_step(self._handle))
+            st0 = self._optimizer.state.get(params[0], {})
+            if "exp_avg" not in st0 or st0["exp_avg"].data_ptr() == self._flat["m"].data_ptr():
+                # the optimizer still shows our flat vectors (no load_state_dict in between): carry them over
+                old_state = {k: v.clone() for k, v in self._flat.items() if k in ("m", "v", "vmax")}
+                old_step = int(self._libh.prl_dqn_adam_step(self._handle))
             self._libh.prl_dqn_destroy(self._handle)
             self._handle = C.c_void_p(0)
         self._libh = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
@@ -129,17 +133,6 @@ class _B200DQNMixin:
             step = int(float(opt_state[params[0]]["step"]))
         else:
             m, v, vmax = (torch.zeros(P, dtype=torch.float32, device=device) for _ in range(3))
-        # expose the flat AdamW state through the torch optimizer (views, no copies)
-        off = 0
-        self._step_tensors = []
-        for p in params:
-            n = p.numel()
-            st = torch.tensor(float(step), dtype=torch.float32)
-            self._step_tensors.append(st)
-            opt_state[p] = dict(step=st, exp_avg=m[off:off + n].view(p.shape),
-                                exp_avg_sq=v[off:off + n].view(p.shape),
-                                max_exp_avg_sq=vmax[off:off + n].view(p.shape))
-            off += n
         self._bound_batch = max(int(need_batch), int(self._batch_size) if self._batch_size > 0 else 0, 1)
         cfg = _lib.DqnCfg(
             obs_dim=self._obs_dim, n_actions=self._n_actions, hidden1=self._hidden[0], hidden2=self._hidden[1],
@@ -160,8 +153,59 @@ class _B200DQNMixin:
         if getattr(self, "_comm", None) is not None:
             _lib.check(self._libh.prl_dqn_set_comm(self._handle, self._comm.handle))
         self._flat = dict(w=w, wt=wt, m=m, v=v, vmax=vmax, ws=ws)
+        self._expose_state(params, step)   # the flat AdamW state seen through the torch optimizer (views, no copies)
+        self._bound_hp = hp
         self._bound_ptr = params[0].data_ptr()
         self._device = device
+
+    def _refresh_optimizer_binding(self, params) -> None:
+        """The kernels read the flat AdamW vectors and the hyper-parameters captured at bind time.  A checkpoint
+        resume (`optimizer.load_state_dict`) replaces `optimizer.state[p]` with fresh tensors, and a scheduler or
+        the user may change `param_groups[0]`: pick both up on every learn() (a few pointer / float compares)."""
+        hp = self._adam_hparams()
+        if hp != self._bound_hp:
+            if {k: v for k, v in hp.items() if k != "lr"} != {k: v for k, v in self._bound_hp.items() if k != "lr"}:
+                self._bound_ptr = None          # betas / eps / weight decay changed: full re-bind with the new config
+                self._bind(self._bound_batch)
+                return
+            _lib.check(self._libh.prl_dqn_set_lr(self._handle, hp["lr"]))
+            self._bound_hp = hp
+        st = self._optimizer.state
+        m = self._flat["m"]
+        p0 = params[0]
+        if p0 in st and "exp_avg" in st[p0] and st[p0]["exp_avg"].data_ptr() == m.data_ptr():
+            return
+        if not all(p in st and "exp_avg" in st[p] for p in params):
+            if len(st) == 0:                    # state dropped (fresh optimizer): restart the moments
+                for k in ("m", "v", "vmax"):
+                    self._flat[k].zero_()
+                _lib.check(self._libh.prl_dqn_set_adam_step(self._handle, 0))
+                self._expose_state(params, 0)
+            return
+        dev = m.device
+        cat = lambda key: torch.cat([st[p][key].detach().reshape(-1).to(dev, torch.float32) for p in params])
+        has_max = all("max_exp_avg_sq" in st[p] for p in params)
+        self._flat["m"].copy_(cat("exp_avg"))
+        self._flat["v"].copy_(cat("exp_avg_sq"))
+        self._flat["vmax"].copy_(cat("max_exp_avg_sq") if has_max else cat("exp_avg_sq"))
+        step = int(float(st[p0]["step"]))
+        _lib.check(self._libh.prl_dqn_set_adam_step(self._handle, step))
+        self._expose_state(params, step)
+
+    def _expose_state(self, params, step: int) -> None:
+        """Make `optimizer.state` a set of views into the flat AdamW vectors (no copies for state_dict())."""
+        m, v, vmax = self._flat["m"], self._flat["v"], self._flat["vmax"]
+        opt_state = self._optimizer.state
+        off = 0
+        self._step_tensors = []
+        for p in params:
+            n = p.numel()
+            st = torch.tensor(float(step), dtype=torch.float32)
+            self._step_tensors.append(st)
+            opt_state[p] = dict(step=st, exp_avg=m[off:off + n].view(p.shape),
+                                exp_avg_sq=v[off:off + n].view(p.shape),
+                                max_exp_avg_sq=vmax[off:off + n].view(p.shape))
+            off += n
 
     def _sync_step_tensors(self) -> None:
         step = float(self._libh.prl_dqn_adam_step(self._handle))
@@ -384,6 +428,11 @@ class B200LearnerGroup:
         if min(sizes) == 0 or len(set(bs)) != 1:
             raise ValueError("all buffers of a group must be non-empty and give the same batch size")
         bs = bs[0]
+        if n > 1 and any(b._rng_mode != "device" for b in self.buffers):
+            # with rng="python" every buffer would be handed the SAME global `random` state: identical index streams in
+            # all learners and a global stream advanced by one learner's consumption only
+            raise ValueError('B200LearnerGroup needs buffers with rng="device" (one private MT19937 stream per learner, '
+                             'like the separate processes the reference runs its replicas in)')
         for l in self.learners:
             l._bind(bs)
         dev = l0._device

@@ -54,11 +54,13 @@ class B200PrioritizedReplayBuffer(B200ReplayBuffer):
 
     def push_batch(self, state, *args, **kwargs) -> None:
         n = torch.as_tensor(state).shape[0]
-        first = 0
-        if self._handle.value:
-            first = (int(self._lib.prl_buf_head(self._handle)) + len(self)) % self.capacity
         super().push_batch(state, *args, **kwargs)
         if n:
+            # the slot of the first new row, derived AFTER the push: a push that upgrades the storage to dynamic
+            # action sets re-creates the trees and re-pushes the old content from slot 0 (at max priority; learned
+            # priorities do not survive the upgrade), so a position taken before the push would be stale
+            first = (int(self._lib.prl_buf_head(self._handle)) + len(self) - min(n, self.capacity)) % self.capacity
+            n = min(n, self.capacity)
             with torch.cuda.device(self._device):
                 _lib.check(self._lib.prl_per_push(self.per_handle, first, n, _stream_ptr(self._device)))
 

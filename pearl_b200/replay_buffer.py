@@ -16,6 +16,7 @@ unit test asserts it, test_replay_buffer.py:46-82 — a deliberate difference).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import random
 from typing import Optional
 
@@ -69,7 +70,9 @@ class B200ReplayBuffer(ReplayBuffer):
         self._layout = None
         self._desc = None
         self.obs_dim = self.n_actions = self.act_dim = None
-        self._pending_seed = None
+        # rng="device": never leave the private MT19937 stream uninitialised (an all-zero state twists to zeros for
+        # ever and the set-branch sampler would spin on duplicates); a distinct stream per buffer until seed() is called
+        self._pending_seed = int.from_bytes(os.urandom(8), "little") if rng == "device" else None
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -168,7 +171,8 @@ class B200ReplayBuffer(ReplayBuffer):
     def _rng_pull(self) -> None:
         if self._rng_mode == "python":
             st = self.get_rng_state()
-            random.setstate((3, tuple(int(x) for x in st), None))
+            ver, _, gauss_next = random.getstate()   # random.sample never touches the cached Gaussian: keep it
+            random.setstate((ver, tuple(int(x) for x in st), gauss_next))
 
     # ------------------------------------------------------------------ write side
     def push(self, state, action, reward, terminated, truncated, curr_available_actions=None,

@@ -1,0 +1,133 @@
+"""Host-contract tests on the GPU box: RNG stream hygiene, learner-group preconditions, optimizer / checkpoint
+hand-over.  These pin the behaviours the round-1 code review flagged."""
+import copy
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class _Space:
+    def __init__(self, n):
+        self.n = n
+        self.actions = [torch.tensor([i]) for i in range(n)]
+
+    @property
+    def actions_batch(self):
+        return torch.stack(self.actions)
+
+
+def _buffer(n, obs, A, rng="device", seed=None):
+    import pearl_b200
+    from oracle.synth import make_transitions
+    d = make_transitions(n, obs, A, seed=7)
+    buf = pearl_b200.B200ReplayBuffer(n, rng=rng)
+    buf.push_batch(*(torch.from_numpy(d[k]) for k in ("state", "action", "reward", "next_state", "terminated", "truncated")),
+                   max_number_actions=A)
+    if seed is not None:
+        buf.seed(seed)
+    return buf
+
+
+def _learner(obs, A, rounds=6, B=32, **kw):
+    import pearl_b200
+    return pearl_b200.B200DeepQLearning(
+        state_dim=obs, action_space=_Space(A), hidden_dims=[64, 64], training_rounds=rounds, batch_size=B,
+        target_update_freq=4, soft_update_tau=0.5,
+        action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(A), **kw).to("cuda")
+
+
+def test_unseeded_device_rng_buffer_samples_and_streams_differ():
+    """rng="device" without seed(): the private MT19937 stream is initialised (never all-zero, which would hang the
+    set-branch sampler), distinct per buffer, and sample() returns distinct in-range indices."""
+    n, k = 5000, 64                        # n > setsize(64) = 277: set branch
+    a, b = _buffer(n, 4, 2), _buffer(n, 4, 2)
+    sa, sb = a.get_rng_state(), b.get_rng_state()
+    assert sa[:624].any() and sb[:624].any() and not np.array_equal(sa, sb)
+    la, _ = a.sample_indices(k, rounds=3)
+    la = la.cpu().numpy()
+    assert la.min() >= 0 and la.max() < n
+    for row in la:
+        assert len(set(row.tolist())) == k
+    assert len(a.sample(k)) == k
+
+
+def test_all_zero_mt_state_is_rejected():
+    buf = _buffer(100, 4, 2)
+    with pytest.raises(ValueError):
+        buf.set_rng_state(np.zeros(625, dtype=np.uint32))
+
+
+def test_rng_pull_keeps_gauss_next():
+    """The reference's random.sample never touches the cached second Gaussian of random.gauss()."""
+    buf = _buffer(2000, 4, 2, rng="python")
+    random.seed(5)
+    random.gauss(0.0, 1.0)                 # leaves gauss_next cached
+    g = random.getstate()[2]
+    assert g is not None
+    buf.sample(16)
+    assert random.getstate()[2] == g
+
+
+def test_group_rejects_python_rng_buffers():
+    import pearl_b200
+    bufs = [_buffer(2000, 8, 4, rng="python") for _ in range(2)]
+    ls = [_learner(8, 4, B=128, engine="tc") for _ in range(2)]
+    with pytest.raises(ValueError):
+        pearl_b200.B200LearnerGroup(ls, bufs).learn()
+
+
+def test_optimizer_load_state_dict_and_lr_change_are_picked_up():
+    """Checkpoint resume: learner A trains, its optimizer state_dict is loaded into learner B (same weights); both
+    then take identical further steps.  A later change of param_groups[0]['lr'] takes effect."""
+    obs, A = 8, 4
+    torch.manual_seed(3)
+    la = _learner(obs, A)
+    lb = _learner(obs, A)
+    buf_a, buf_b = _buffer(3000, obs, A, seed=11), _buffer(3000, obs, A, seed=11)
+    la.learn(buf_a)
+    lb.learn(buf_b)                        # binds B (its own moments), then diverge B's state on purpose
+    lb.learn(buf_b)
+    # resume B from A's checkpoint: parameters, target, optimizer
+    sd = copy.deepcopy(la.state_dict())
+    osd = copy.deepcopy(la.optimizer.state_dict())
+    lb.load_state_dict(sd)
+    lb.optimizer.load_state_dict(osd)
+    lb._training_steps = la._training_steps
+    buf_b.set_rng_state(buf_a.get_rng_state())
+    ra, rb = la.learn(buf_a), lb.learn(buf_b)
+    np.testing.assert_allclose(rb["loss"], ra["loss"], rtol=1e-6)
+    assert torch.equal(lb.flat_parameters, la.flat_parameters)
+    assert lb.adam_state()["step"] == la.adam_state()["step"]
+    assert torch.equal(lb.adam_state()["exp_avg_sq"], la.adam_state()["exp_avg_sq"])
+    # the optimizer state exposed through torch is again a view of the flat vectors
+    p0 = next(iter(lb._Q.parameters()))
+    assert lb.optimizer.state[p0]["exp_avg"].data_ptr() == lb.adam_state()["exp_avg"].data_ptr()
+    # lr = 0: AdamW only applies the (now also zero) decoupled decay -> parameters frozen
+    before = lb.flat_parameters.clone()
+    lb.optimizer.param_groups[0]["lr"] = 0.0
+    lb.learn(buf_b)
+    assert torch.equal(lb.flat_parameters, before)
+
+
+def test_prioritized_push_after_dynamic_upgrade_gets_priorities():
+    """A push that upgrades the storage to dynamic action sets on a wrapped ring: the new rows' leaves carry the
+    max priority (they can be sampled), at the slots the rows were written to."""
+    import pearl_b200
+    from oracle.synth import make_transitions
+    cap, obs, A = 64, 4, 4
+    buf = pearl_b200.B200PrioritizedReplayBuffer(cap, seed=1)
+    t = torch.from_numpy
+    d = make_transitions(100, obs, A, seed=1)     # wraps: 100 > 64
+    buf.push_batch(*(t(d[k]) for k in ("state", "action", "reward", "next_state", "terminated", "truncated")), max_number_actions=A)
+    d2 = make_transitions(10, obs, A, seed=2, dynamic=True)
+    buf.push_batch(*(t(d2[k]) for k in ("state", "action", "reward", "next_state", "terminated", "truncated")), max_number_actions=A,
+                   next_available_ids=t(d2["next_avail_ids"].astype(np.uint8)), next_available_count=t(d2["next_avail_n"].astype(np.int32)))
+    assert len(buf) == cap
+    C2 = buf.sum_tree.numel() // 2
+    leaves = buf.sum_tree[C2:C2 + cap].cpu().numpy()
+    assert (leaves > 0).all()                     # every stored row, old and new, can be drawn
+    np.testing.assert_allclose(float(buf.sum_tree[1]), leaves.astype(np.float64).sum(), rtol=1e-5)
