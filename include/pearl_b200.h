@@ -101,6 +101,17 @@ int prl_buf_clear(prl_buf *buf);                  /* clear()  (:287-288) */
  * (checkpoint load): `len` valid records, oldest at physical slot `head`. */
 int prl_buf_set_occupancy(prl_buf *buf, int64_t len, int64_t head);
 
+/* Multi-GPU: `buf` is rank `rank`'s shard of ONE logical replay buffer of `world * capacity` transitions
+ * (the reference has no sharded buffer — its BasicReplayBuffer is the world == 1 case,
+ * basic_replay_buffer.py:21-48).  The transition with global write counter g lives on rank g mod world at
+ * local slot (g div world) mod capacity, so FIFO eviction and age-uniform sampling stay balanced.
+ * `global_pushed` = pushes to the logical buffer so far; the shard must hold exactly its share.  A sharded
+ * buffer samples from the LOGICAL population: every rank runs the same MT19937 stream and draws the same
+ * `batch` global indices as one GPU would (random.sample over the whole deque,
+ * tensor_based_replay_buffer.py:276); prl_dqn_learn then works on the rows the rank owns. */
+int prl_buf_set_shard(prl_buf *buf, int rank, int world, int64_t global_pushed);
+int64_t prl_buf_global_len(const prl_buf *buf);
+
 /* The same host push for `count` buffers of one record layout in ONE call (a vectorised environment feeding
  * a learner group): every source is a [count][n][...] host array; no per-transition action sets.  Records
  * are packed by a few worker threads and copied with one cudaMemcpyAsync per buffer. */

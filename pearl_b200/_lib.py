@@ -71,6 +71,8 @@ _SIGNATURES = {
     "prl_buf_head": (C.c_int64, [_P]),
     "prl_buf_clear": (C.c_int, [_P]),
     "prl_buf_set_occupancy": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "prl_buf_set_shard": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64]),
+    "prl_buf_global_len": (C.c_int64, [_P]),
     "prl_buf_push_host": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "prl_buf_push_host_multi": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "prl_buf_push_device": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

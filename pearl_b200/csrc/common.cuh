@@ -65,6 +65,9 @@ struct prl_buf {
     int64_t stage_records;  // records per staging buffer
     int stage_next;
     int device;
+    // shard of a replay distributed over `shard_world` ranks (prl_buf_set_shard; 0 / 1 = not sharded)
+    int shard_rank, shard_world;
+    int64_t g_pushed;      // transitions pushed to the LOGICAL buffer so far (global write counter)
 };
 
 // multi-GPU communicator (see include/pearl_b200.h)

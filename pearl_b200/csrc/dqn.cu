@@ -44,7 +44,7 @@ constexpr int RED_FLOATS = NT * 16;
 
 // shared-memory plan, offsets in floats (all multiples of 4)
 struct Plan {
-    int rec, T1o, H1o, H2o, T1t, T1d, dZ2, dZ1, Hc, H2c, WaO, WaT, qa, scal, stage, red, total;
+    int rec, T1o, H1o, H2o, T1t, T1d, dZ2, dZ1, Hc, H2c, WaO, WaT, qa, scal, stage, red, own, total;
     int zero_begin, zero_end;  // activation region zero-initialised once
 };
 
@@ -69,6 +69,7 @@ __host__ __device__ inline Plan make_plan(const Dims &d, int R, int W, int mch) 
     p.zero_end = o;
     p.stage = o; o += STAGE_FLOATS;
     p.red = o; o += RED_FLOATS;
+    p.own = o; o += round_up(2 * (R + 1) + 16, 4);   // sharded replay: per round parity [count, batch index of each owned row], scan scratch
     p.total = o;
     return p;
 }
@@ -101,6 +102,10 @@ struct LearnArgs {
     long long comm_slot;      // floats per inbox slot
     unsigned long long exch0; // exchanges completed before this launch
     float inv_world;
+    // replay sharded over the ranks: every rank draws the SAME B global indices; transition number g
+    // (global write counter) lives on rank g mod W at local slot (g div W) mod local_cap; a rank works on the rows it owns
+    int shard_world, shard_rank;
+    long long g_oldest, local_cap;
     long long *prof;          // optional [rounds][16] SM-clock stamps of CTA 0 (developer profiling)
     long long steps0;         // learner._training_steps before the call
     float decay, omb1, beta2, omb2, eps, gamma, tau, omtau, inv_b2;  // fp32 images of the scalars
@@ -370,15 +375,50 @@ __device__ __noinline__ void all_actions_q(const float *__restrict__ net, const 
     __syncthreads();
 }
 
-__device__ void prefetch_records(const LearnArgs &a, float *sm, int round, int Rv, int r0) {
+// rows of `round` this CTA works on: r0 .. r0 + Rv - 1 of the batch, or — sharded replay — the owned rows whose
+// position k in the rank's compacted list has k mod G == blockIdx.x
+__device__ int prefetch_records(const LearnArgs &a, float *sm, int round, int Rv, int r0) {
     const int W = a.lay.record_words, W4 = W >> 2;
     uint32_t *dst = reinterpret_cast<uint32_t *>(sm + a.plan.rec) + (size_t)(round & 1) * a.R * W;
-    const int32_t *sl = a.slots + (size_t)round * a.B + r0;
+    const int32_t *sl = a.slots + (size_t)round * a.B;
+    if (a.shard_world > 1) {
+        int *own = reinterpret_cast<int *>(sm + a.plan.own) + (round & 1) * (a.R + 1);
+        int *wsum = reinterpret_cast<int *>(sm + a.plan.own) + 2 * (a.R + 1);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int base = 0;
+        for (int i0 = 0; i0 < a.B; i0 += NT) {
+            const int i = i0 + threadIdx.x;
+            bool mine = false;
+            if (i < a.B) mine = (int)((a.g_oldest + (long long)__ldcg(sl + i)) % a.shard_world) == a.shard_rank;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (lane == 0) wsum[warp] = __popc(bal);
+            __syncthreads();
+            int off = base, total = 0;
+            for (int w8 = 0; w8 < NT / 32; w8++) { if (w8 < warp) off += wsum[w8]; total += wsum[w8]; }
+            const int k = off + __popc(bal & ((1u << lane) - 1u));
+            if (mine && k % a.G == (int)blockIdx.x) own[1 + k / a.G] = i;
+            base += total;
+            __syncthreads();
+        }
+        Rv = base > (int)blockIdx.x ? (base - (int)blockIdx.x + a.G - 1) / a.G : 0;
+        if (threadIdx.x == 0) own[0] = Rv;
+        __syncthreads();
+        for (int e = threadIdx.x; e < Rv * W4; e += NT) {
+            const int r = e / W4, c = e - r * W4;
+            const long long g = a.g_oldest + (long long)__ldcg(sl + own[1 + r]);
+            const long long slot = (g / a.shard_world) % a.local_cap;
+            cp_async16(dst + (size_t)r * W + c * 4, a.records + (size_t)slot * W + c * 4);
+        }
+        cp_async_commit();
+        return Rv;
+    }
+    sl += r0;
     for (int e = threadIdx.x; e < Rv * W4; e += NT) {
         const int r = e / W4, c = e - r * W4;
         cp_async16(dst + (size_t)r * W + c * 4, a.records + (size_t)__ldcg(sl + r) * W + c * 4);
     }
     cp_async_commit();
+    return Rv;
 }
 
 // ---------------------------------------------------------------------------
@@ -393,7 +433,11 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
     const Dims &d = a.d;
     const Plan &pl = a.plan;
     const int tid = threadIdx.x, R = a.R, W = a.lay.record_words;
-    const int r0 = blockIdx.x * R, Rv = min(R, a.B - r0);
+    const int r0 = blockIdx.x * R;
+    int Rv = min(R, a.B - r0);
+    const int *own = reinterpret_cast<const int *>(sm + pl.own) + (round & 1) * (R + 1);
+    const bool shard = a.shard_world > 1;
+    if (shard) Rv = own[0];                       // written (and barrier-published) by prefetch_records of this round
     PRL_STAMP(0);
     cp_async_wait<0>();
     __syncthreads();
@@ -480,11 +524,12 @@ __device__ void phase_rows(const LearnArgs &a, float *sm, int round) {
         const float q = sc.q[tid];
         sc.y[tid] = y;
         float dqv = (q - y) * a.inv_b2;  // d/dq mean((q-y)^2) = 2 (q-y) / B
-        if (a.is_weight) dqv *= __ldg(a.is_weight + (size_t)round * a.B + r0 + tid);   // d/dq mean(w (q-y)^2)
+        const int bi = shard ? own[1 + tid] : r0 + tid;   // position of this row in the sampled batch
+        if (a.is_weight) dqv *= __ldg(a.is_weight + (size_t)round * a.B + bi);   // d/dq mean(w (q-y)^2)
         sc.dq[tid] = dqv;
-        if (a.out_td) a.out_td[(size_t)round * a.B + r0 + tid] = fabsf(q - y);
-        if (a.out_q) a.out_q[(size_t)round * a.B + r0 + tid] = q;
-        if (a.out_y) a.out_y[(size_t)round * a.B + r0 + tid] = y;
+        if (a.out_td) a.out_td[(size_t)round * a.B + bi] = fabsf(q - y);
+        if (a.out_q) a.out_q[(size_t)round * a.B + bi] = q;
+        if (a.out_y) a.out_y[(size_t)round * a.B + bi] = y;
     }
     __syncthreads();
 
@@ -589,11 +634,12 @@ __device__ void phase_update(const LearnArgs &a, int round) {
     const bool upd_next = (round + 1 < a.rounds) && ((t_next + 1) % a.freq == 0);
     const int parity = (int)((a.exch0 + (unsigned long long)round) & 1ull);
     const unsigned int seq = (unsigned int)(a.exch0 + (unsigned long long)round + 1ull);
+    const int nx = d.P + (a.shard_world > 1 ? 1 : 0);   // sharded replay: sum |q - y| travels with the gradient
     if (a.world > 1) {
         // ---- fused gradient exchange (NVLink peer memory, one-way latency only): every rank
         // pushes (value, round sequence number) as ONE 8-byte store into every peer's inbox;
         // readers poll the sequence half of each element, so there is no fence / flag round trip.
-        for (int i = blockIdx.x * NT + threadIdx.x; i < d.P; i += G * NT) {
+        for (int i = blockIdx.x * NT + threadIdx.x; i < nx; i += G * NT) {
             const float g = reduce_partials(a, i);
             const size_t off = ((size_t)parity * a.world + a.rank) * a.comm_slot + i;
             for (int p = 0; p < a.world; p++) st_volatile_v2(a.peer_inbox[p] + 2 * off, g, seq);
@@ -601,7 +647,7 @@ __device__ void phase_update(const LearnArgs &a, int round) {
     }
     for (int i = blockIdx.x * NT + threadIdx.x; i <= d.P; i += G * NT) {
         float g;
-        if (a.world > 1 && i < d.P) {
+        if (a.world > 1 && i < nx) {
             float sum = 0.f;  // rank order: identical on every rank
             for (int q = 0; q < a.world; q++) {
                 const float *src = a.inbox + 2 * (((size_t)parity * a.world + q) * a.comm_slot + i);
@@ -1043,6 +1089,7 @@ static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layou
     a.mt_state = nullptr;
     a.prof = q->prof;
     a.rank = 0; a.world = 1; a.inbox = nullptr; a.flags = nullptr; a.comm_slot = 0; a.exch0 = 0; a.inv_world = 1.f;
+    a.shard_world = 1; a.shard_rank = 0; a.g_oldest = 0; a.local_cap = 0;
     for (int p = 0; p < 16; p++) { a.peer_inbox[p] = nullptr; a.peer_flags[p] = nullptr; }
     if (q->comm && sample_from) {  // data-parallel learn(): exchange inside the kernel
         prl_comm *c = q->comm;
@@ -1053,6 +1100,21 @@ static int launch_learn(prl_dqn *q, const uint32_t *records, const prl_buf_layou
         a.comm_slot = c->slot_floats; a.exch0 = c->exchanges; a.inv_world = 1.0f / (float)c->world;
         for (int p = 0; p < c->world; p++) { a.peer_inbox[p] = c->peer_inbox[p]; a.peer_flags[p] = c->peer_flags[p]; }
         c->exchanges += (unsigned long long)rounds;
+        if (sample_from->shard_world > 1) {
+            // replay sharded over the ranks: same B indices everywhere, each rank contributes the UNNORMALISED partial
+            // gradient of the rows it owns (every row already carries 2 / B), the exchange sums them
+            PRL_REQUIRE(sample_from->shard_world == c->world && sample_from->shard_rank == c->rank,
+                        "replay shard (%d of %d) does not match the communicator (%d of %d)", sample_from->shard_rank,
+                        sample_from->shard_world, c->rank, c->world);
+            PRL_REQUIRE(c->slot_floats >= q->d.P + 1, "communicator slots must hold the parameter vector + 1");
+            PRL_REQUIRE(!is_weight, "prioritized replay is not sharded here");
+            a.shard_world = c->world; a.shard_rank = c->rank;
+            a.g_oldest = sample_from->g_pushed - prl_buf_global_len(sample_from);
+            a.local_cap = sample_from->desc.capacity;
+            a.inv_world = 1.f;
+        }
+    } else if (sample_from && sample_from->shard_world > 1) {
+        return fail(PRL_EINVAL, "a sharded replay buffer needs a learner with a communicator (set_communicator)");
     }
     if (sample_from) {  // the index stream is produced inside the kernel by CTA number G
         size_t sbytes = 0;

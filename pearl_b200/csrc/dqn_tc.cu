@@ -76,9 +76,11 @@ constexpr int TM_A0 = 0, TM_S0 = 256;          // group g: A operand at 128 g (h
 constexpr int TM_G1 = 0, TM_G2 = 128;          // weight-gradient accumulators (the A regions are free by then)
 
 // mbarrier indices
-enum {
+enum {   // (B_SFULL: spare)
     B_W1 = 0, B_W2, B_W2T, B_MMA /*2*/ = 3, B_W1FREE = 5, B_ACTDONE, B_RFULL /*2*/ = 7, B_RFREE /*2*/ = 9,
-    B_H1FREE = 11, B_H2FREE, B_SFULL /*16*/ = 13, B_COUNT = 29
+    // one barrier PER PASS for the two arena chains: a parity wait only tells adjacent phases apart, and pass p + 2 may
+    // reach its wait before pass p has even committed
+    B_H1FREE /*8*/ = 11, B_H2FREE /*8*/ = 19, B_SFULL /*16*/ = 27, B_COUNT = 43
 };
 
 struct TcLearner {            // one per CTA, in global memory
@@ -117,7 +119,8 @@ struct Misc {
     Smalls t, o;
     float redw[8][HID];
     float redmae[8], reddb3[8];
-    unsigned long long bar[B_COUNT + 3];
+    unsigned long long rowptr[8][32];   // this round's record row of every row thread (the warp's lanes copy each other's rows)
+    unsigned long long bar[B_COUNT + 1];
     uint32_t tmem_base;
 };
 
@@ -221,6 +224,7 @@ struct RowCtx {
     uint32_t tm, tlane;            // TMEM base, this warp's lane window
     uint32_t a_col, s_col;         // the group's A-operand and accumulator columns
     uint32_t n_chunk;              // staged row chunks consumed so far by this warp (running, all phases and rounds)
+    uint32_t n_issued;             // staged row chunks requested so far
     uint32_t n_mma;                // MMA batches committed so far on the group's barrier
     bool elected;                  // issues the group's MMAs
     float *sbuf;                   // this warp's two staging buffers
@@ -228,13 +232,28 @@ struct RowCtx {
     char *smem;
 };
 
-// TMA copies of this warp's 32 rows, chunk `cc` (32 columns) of the field at `field_off`, into buffer (n & 1)
-__device__ __forceinline__ void issue_chunk(const RowCtx &c, uint32_t n, const float *row_base, int field_off, int cc, int obs) {
+// Chunk `cc` (32 columns) of the field at `field_off` of this warp's 32 rows -> buffer (n & 1): 16-byte cp.async, 8 lanes
+// per row (one full 128-byte line), 4 rows per instruction; one cp.async group per chunk.  (Per-row TMA bulk copies were
+// measured first: ~2300 128-byte operations per round serialise in the SM's TMA unit and tripled the round time; TMA is
+// kept for what it is good at here, the 16 - 64 KB weight tiles.)
+__device__ __forceinline__ void issue_chunk(RowCtx &c, uint32_t n, const unsigned long long *rowptr, int field_off, int cc, int obs) {
     const int kc = min(32, obs - 32 * cc);
-    uint64_t *full = c.bar + B_SFULL + c.warp * 2 + (n & 1);
-    if (c.lane == 0) mbar_expect_tx(full, 32u * kc * 4);
+    float *dst = c.sbuf + (n & 1) * (SBUF / 4);
+    const int c16 = c.lane & 7, rsub = c.lane >> 3;
+    if (4 * c16 < kc) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int row = 4 * i + rsub;
+            cp_async16(dst + row * SROW + 4 * c16, reinterpret_cast<const float *>(rowptr[row]) + field_off + 32 * cc + 4 * c16);
+        }
+    }
+    cp_async_commit();
+    c.n_issued = n + 1;
+}
+// chunk n of this warp has landed (at most one younger chunk may still be in flight)
+__device__ __forceinline__ void wait_chunk(const RowCtx &c, uint32_t n) {
+    if (c.n_issued > n + 1) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncwarp();
-    bulk_g2s(c.sbuf + (n & 1) * (SBUF / 4) + c.lane * SROW, row_base + field_off + 32 * cc, kc * 4, full);
 }
 
 __device__ __forceinline__ void wait_group_mma(RowCtx &c) {
@@ -254,7 +273,7 @@ __device__ __forceinline__ void layer1(RowCtx &c, int obs, uint32_t w1_parity, N
     for (int cc = 0; cc < nch; cc++) {
         const uint32_t n = c.n_chunk++;
         const int kc = min(32, obs - 32 * cc);
-        umma::mbar_wait(c.bar + B_SFULL + c.warp * 2 + (n & 1), (n >> 1) & 1);
+        wait_chunk(c, n);
         const float *row = c.sbuf + (n & 1) * (SBUF / 4) + c.lane * SROW;
         float hi[32];
 #pragma unroll
@@ -377,7 +396,8 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
 
     if (warp == 0) umma::tmem_alloc(&mi.tmem_base, 512);
     if (tid == 0)
-        for (int i = 0; i < B_COUNT; i++) umma::mbar_init(bar + i, (i == B_W1FREE || i == B_ACTDONE) ? ntiles : 1);
+        for (int i = 0; i < B_COUNT; i++)
+            umma::mbar_init(bar + i, (i == B_W1FREE || i == B_ACTDONE) ? ntiles : (i == B_RFULL || i == B_RFULL + 1) ? 32 : 1);
     // prologue: the operand-layout tiles and the small vectors follow the flat parameters (which the host may have
     // changed between calls)
     if (warp < 8) {
@@ -422,11 +442,15 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 if (p < np) {
                     const uint32_t n = n_pass + p, b = n & 1;
                     umma::mbar_wait(bar + B_RFREE + b, ((n >> 1) & 1) ^ 1);
-                    if (lane == 0) mbar_expect_tx(bar + B_RFULL + b, 32u * obs * 4);
-                    __syncwarp();
-                    float *raw = reinterpret_cast<float *>(smem + (b ? R_W2T : R_W2)) + lane * RAWP;
-                    bulk_g2s(raw, reinterpret_cast<const float *>(L.records + (size_t)pslot[p] * W) + a.lay.off_state, obs * 4,
-                             bar + B_RFULL + b);
+                    float *raw = reinterpret_cast<float *>(smem + (b ? R_W2T : R_W2));
+                    const int q4 = obs >> 2;                       // 16-byte chunks per row
+                    for (int idx = lane; idx < 32 * q4; idx += 32) {
+                        const int row = idx / q4, ch = idx - row * q4;
+                        const int slot = __shfl_sync(0xffffffffu, pslot[p], row);
+                        cp_async16(raw + row * RAWP + 4 * ch, reinterpret_cast<const float *>(L.records + (size_t)slot * W) + a.lay.off_state + 4 * ch);
+                    }
+                    // the barrier's 32 arrivals fire as each lane's copies land
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar + B_RFULL + b)) : "memory");
                 }
             }
             n_pass += np;
@@ -441,7 +465,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     c.tm = mi.tmem_base;
     c.tlane = c.tm + ((uint32_t)(c.q * 32) << 16);
     c.a_col = TM_A0 + 128 * c.g; c.s_col = TM_S0 + 128 * c.g;
-    c.n_chunk = 0; c.n_mma = 0;
+    c.n_chunk = 0; c.n_issued = 0; c.n_mma = 0;
     c.elected = c.q == 0 && lane == 0;
     c.sbuf = reinterpret_cast<float *>(smem + STAGE + (warp & 7) * 2 * SBUF);
     c.bar = bar; c.smem = smem;
@@ -466,12 +490,13 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             if (d.A > 4) ids1 = rec[a.lay.off_avail + 1];
             if (d.A > 8) { ids2 = rec[a.lay.off_avail + 2]; ids3 = rec[a.lay.off_avail + 3]; }
         }
+        mi.rowptr[warp][lane] = (unsigned long long)rec;
+        __syncwarp();
     };
     auto first_chunks = [&](int round) {     // the two chunks every warp requests before a round starts
-        const float *rowf = reinterpret_cast<const float *>(rec);
         const uint32_t n0 = (uint32_t)round * 2 * nch;
-        issue_chunk(c, n0, rowf, a.lay.off_next_state, 0, obs);
-        issue_chunk(c, n0 + 1, rowf, nch > 1 ? a.lay.off_next_state : a.lay.off_state, nch > 1 ? 1 : 0, obs);
+        issue_chunk(c, n0, mi.rowptr[warp], a.lay.off_next_state, 0, obs);
+        issue_chunk(c, n0 + 1, mi.rowptr[warp], nch > 1 ? a.lay.off_next_state : a.lay.off_state, nch > 1 ? 1 : 0, obs);
     };
     if (active) {
         fetch_row(0);
@@ -499,11 +524,10 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         uint32_t mask2a = 0u, mask2b = 0u;
         const int act_now = act;
         if (active) {
-            const float *rowf = reinterpret_cast<const float *>(rec);
             auto ahead = [&](uint32_t n) {   // chunks of a round in order: next_state 0..nch-1, state 0..nch-1
                 const int s = (int)(n - (uint32_t)round * 2 * nch);
                 if (s < 2 * nch)
-                    issue_chunk(c, n, rowf, s < nch ? a.lay.off_next_state : a.lay.off_state, s < nch ? s : s - nch, obs);
+                    issue_chunk(c, n, mi.rowptr[warp], s < nch ? a.lay.off_next_state : a.lay.off_state, s < nch ? s : s - nch, obs);
             };
             // ================= phase T: y = max_a' Q_target(s', a') * gamma * (1 - term) + r =================
             layer1(c, obs, 0, ahead);
@@ -704,7 +728,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             float v[64];
             umma::tmem_ld32(c.tlane + c.s_col, v);            // h1
             umma::tmem_ld32(c.tlane + c.s_col + 32, v + 32);
-            if (p > 0) umma::mbar_wait(bar + B_H1FREE, (n - 1) & 1);      // the previous pass's G2 products are done
+            if (p > 0) umma::mbar_wait(bar + B_H1FREE + p - 1, round & 1);      // the previous pass's G2 products are done
             eh_hi[tt_off(0, colbase)] = 1.f;
 #pragma unroll
             for (int e = 0; e < 16; e++) eh_hi[tt_off(1 + e, colbase)] = (e == act_now) ? 1.f : 0.f;
@@ -741,12 +765,12 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     umma::mma_tf32(c.tm + TM_G2, EH.desc(ks), DL.desc(ks), i128, true);
                     umma::mma_tf32(c.tm + TM_G2, EH.desc(ks), DH.desc(ks), i128, true);
                 }
-                umma::mma_commit(bar + B_H1FREE);
+                umma::mma_commit(bar + B_H1FREE + p);
             }
             __syncwarp();
             // ---- G1 operands: S^T from the raw rows the loader fetched, dZ1^T stacked (hi ; lo)
+            if (p > 0) umma::mbar_wait(bar + B_H2FREE + p - 1, round & 1);   // first: orders this pass behind the fill it is about to wait for
             umma::mbar_wait(bar + B_RFULL + (n & 1), (n >> 1) & 1);
-            if (p > 0) umma::mbar_wait(bar + B_H2FREE, (n - 1) & 1);
             const float *raw = reinterpret_cast<const float *>(smem + ((n & 1) ? R_W2T : R_W2)) + lane * RAWP;
 #pragma unroll 4
             for (int k4 = 0; k4 < (obs >> 2); k4++) {
@@ -775,12 +799,12 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     umma::mma_tf32(c.tm + TM_G1, SH.desc(ks), D1.desc(ks), i128, p > 0 || ks > 0);   // S_hi x [dZ1_hi ; dZ1_lo]
                     umma::mma_tf32(c.tm + TM_G1, SL.desc(ks), D1.desc(ks), i64, true);              // S_lo x dZ1_hi
                 }
-                umma::mma_commit(bar + B_H2FREE);
+                umma::mma_commit(bar + B_H2FREE + p);
             }
             __syncwarp();
         }
-        umma::mbar_wait(bar + B_H1FREE, (n_pass + np - 1) & 1);
-        umma::mbar_wait(bar + B_H2FREE, (n_pass + np - 1) & 1);
+        umma::mbar_wait(bar + B_H1FREE + np - 1, round & 1);
+        umma::mbar_wait(bar + B_H2FREE + np - 1, round & 1);
         umma::fence_after_thread_sync();
         n_pass += np;
         TC_STAMP(7);

@@ -98,6 +98,7 @@ extern "C" int prl_buf_create(prl_buf **out, const prl_buf_desc *desc, void *sto
     b->stage[0] = b->stage[1] = nullptr;
     b->stage_records = 0;
     b->stage_next = 0;
+    b->shard_rank = 0; b->shard_world = 1; b->g_pushed = 0;
     cudaGetDevice(&b->device);
     // never leave the MT19937 stream all-zero (it twists to zeros for ever: the set-branch sampler would then
     // spin on duplicates): a distinct default stream per buffer until the caller seeds / hands over a state
@@ -397,6 +398,29 @@ extern "C" int prl_buf_push_device(prl_buf *b, int64_t n, const float *state, co
     return PRL_OK;
 }
 
+// Shard of a logical replay buffer of `world * capacity` transitions: the transition with global
+// write counter g lives on rank g mod world at local slot (g div world) mod capacity.  `global_pushed` = pushes to
+// the logical buffer so far; the local content must be exactly this rank's share, pushed in order.
+extern "C" int prl_buf_set_shard(prl_buf *b, int rank, int world, int64_t global_pushed) {
+    PRL_REQUIRE(b, "null buffer");
+    PRL_REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world && global_pushed >= 0, "bad shard description");
+    const int64_t mine = global_pushed / world + ((global_pushed % world) > rank ? 1 : 0);   // g < global_pushed, g mod world == rank
+    const int64_t expect = mine < b->desc.capacity ? mine : b->desc.capacity;
+    PRL_REQUIRE(world == 1 || b->len == expect,
+                "shard holds %lld transitions, %lld expected for rank %d of %d after %lld global pushes", (long long)b->len,
+                (long long)expect, rank, world, (long long)global_pushed);
+    PRL_REQUIRE(world == 1 || b->write_pos == mine % b->desc.capacity, "shard ring position does not match the global write counter");
+    b->shard_rank = rank; b->shard_world = world; b->g_pushed = global_pushed;
+    return PRL_OK;
+}
+// population of the logical buffer a shard belongs to (= prl_buf_len for an unsharded buffer)
+extern "C" int64_t prl_buf_global_len(const prl_buf *b) {
+    if (!b) return 0;
+    if (b->shard_world <= 1) return b->len;
+    const int64_t cap = b->desc.capacity * b->shard_world;
+    return b->g_pushed < cap ? b->g_pushed : cap;
+}
+
 // --------------------------------------------------------------------------
 // RNG state hand-off
 // --------------------------------------------------------------------------
@@ -461,7 +485,8 @@ static int64_t sample_setsize(int64_t k) {  // Lib/random.py:432-434
 // sampler geometry for `k` draws from the buffer's current population (shared with
 // the fused learner kernels); returns the dynamic shared memory the sampler needs
 int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *smem_bytes) {
-    const int64_t n = b->len;
+    const bool shard = b->shard_world > 1;
+    const int64_t n = prl_buf_global_len(b);   // a shard draws from the LOGICAL buffer: every rank the same indices
     if (k > n)
         return fail(PRL_EINVAL, "Can't get a batch of size %d from a replay buffer with only %lld elements", k,
                     (long long)n);
@@ -479,7 +504,8 @@ int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *
         *smem_bytes = (size_t)cap * 8;
     }
     if (*smem_bytes > 200 * 1024) return fail(PRL_EUNSUPPORTED, "sample size %d too large for the on-chip sampler", k);
-    sp->head = prl_buf_head(b); sp->capacity = b->desc.capacity;
+    sp->head = shard ? 0 : prl_buf_head(b);     // sharded: out_slot carries the logical index, owners map it themselves
+    sp->capacity = shard ? b->desc.capacity * b->shard_world : b->desc.capacity;
     sp->out_logical = nullptr; sp->out_slot = nullptr;
     return PRL_OK;
 }

@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace umma {
 
@@ -187,9 +188,12 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar) {  // arrives on `bar`
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// Bounded spin: a wait that cannot complete (protocol bug, lost TMA transaction) ends the kernel with a trap and a
+// message instead of hanging the device — over a second of polling, orders of magnitude beyond any legitimate wait.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
     uint32_t done;
+    long long t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -198,6 +202,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(a), "r"(parity)
             : "memory");
+        if (!done) {
+            if (t0 == 0) t0 = clock64();
+            if (clock64() - t0 < 3000000000ll) continue;   // ~1.5 s of SM clocks
+            printf("pearl_b200: mbarrier wait timed out: block %d thread %d barrier@%u parity %u\n", (int)blockIdx.x,
+                   (int)threadIdx.x, a, parity);
+            __trap();
+        }
     } while (!done);
 }
 

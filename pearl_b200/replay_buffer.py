@@ -73,6 +73,8 @@ class B200ReplayBuffer(ReplayBuffer):
         # rng="device": never leave the private MT19937 stream uninitialised (an all-zero state twists to zeros for
         # ever and the set-branch sampler would spin on duplicates); a distinct stream per buffer until seed() is called
         self._pending_seed = int.from_bytes(os.urandom(8), "little") if rng == "device" else None
+        self._shard = None            # (rank, world) when this buffer is one shard of a logical multi-GPU buffer
+        self._g_pushed = 0            # pushes to the logical buffer so far
 
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -123,7 +125,7 @@ class B200ReplayBuffer(ReplayBuffer):
 
     def _upgrade_to_dynamic(self) -> None:
         """Re-create the storage with per-transition action lists, keeping the content."""
-        n = len(self)
+        n = self.local_len()
         old = None
         if n:
             old = self._gather_logical(torch.arange(n, dtype=torch.int32, device=self._device))
@@ -259,13 +261,46 @@ class B200ReplayBuffer(ReplayBuffer):
         if on_dev:  # keep the sources alive until the pack kernel has run
             torch.cuda.current_stream(self._device).synchronize()
 
+    # ------------------------------------------------------------------ multi-GPU sharding
+    def set_shard(self, rank: int, world: int, global_pushed: int) -> None:
+        """Declare this buffer rank `rank`'s shard of ONE logical buffer of `world * capacity` transitions: the
+        transition with global write counter g lives on rank g mod world at local slot (g div world) mod capacity
+        (pearl_b200.dist.shard_owner).  The local content must be exactly this rank's share, pushed in order."""
+        _lib.check(self._lib.prl_buf_set_shard(self.handle, int(rank), int(world), int(global_pushed)))
+        self._shard = (int(rank), int(world)) if world > 1 else None
+        self._g_pushed = int(global_pushed)
+
+    def push_batch_sharded(self, rank: int, world: int, state, action, reward, next_state, terminated, truncated,
+                           **kwargs) -> None:
+        """Every rank calls this with the SAME global batch (a replicated producer); the rank keeps the rows it owns.
+        `len()` of a sharded buffer is the population of the logical buffer, and `learn()` of a learner with a
+        communicator draws the same `batch` global indices on every rank as one GPU would."""
+        state = torch.as_tensor(state)
+        n = state.shape[0]
+        first = (rank - self._g_pushed) % world
+        pick = lambda x: None if x is None else torch.as_tensor(x)[first::world]
+        if first < n:
+            self.push_batch(pick(state), pick(action), pick(reward), pick(next_state), pick(terminated), pick(truncated),
+                            **{k: pick(v) if torch.is_tensor(v) else v for k, v in kwargs.items()})
+        if self._handle.value:
+            self.set_shard(rank, world, self._g_pushed + n)
+        else:
+            self._g_pushed += n
+
+    def local_len(self) -> int:
+        return int(self._lib.prl_buf_len(self._handle)) if self._handle.value else 0
+
     # ------------------------------------------------------------------ read side
     def __len__(self) -> int:
-        return int(self._lib.prl_buf_len(self._handle)) if self._handle.value else 0
+        if not self._handle.value:
+            return 0
+        return int(self._lib.prl_buf_global_len(self._handle)) if self._shard else int(self._lib.prl_buf_len(self._handle))
 
     def clear(self) -> None:
         if self._handle.value:
             _lib.check(self._lib.prl_buf_clear(self._handle))
+            if self._shard:
+                self.set_shard(self._shard[0], self._shard[1], 0)
 
     def sample_indices(self, batch_size: int, rounds: int = 1):
         """(logical, slot) int32 [rounds, batch] tensors on the device; logical index 0 = oldest."""
@@ -284,6 +319,9 @@ class B200ReplayBuffer(ReplayBuffer):
         return logical, slot
 
     def _gather_slots(self, slot: torch.Tensor) -> dict:
+        if self._shard:
+            raise NotImplementedError("a sharded buffer holds 1 / world of the sampled rows: use learn() of a learner "
+                                      "with a communicator (the gradient, not the batch, crosses NVLink)")
         k = slot.numel()
         dev = self._device
         A = self.n_actions or 0

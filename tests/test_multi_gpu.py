@@ -56,6 +56,17 @@ def test_data_parallel_learner_matches_oracle_on_concatenated_batch(double):
     assert out.returncode == 0 and "DP_OK" in out.stdout, (out.stdout[-2000:], out.stderr[-4000:])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("double", [0, 1])
+def test_sharded_replay_learner_draws_the_single_gpu_indices(double):
+    """SURVEY.md 8e partitioning: replicated MT19937 stream, interleaved ownership, summed partial gradients."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2; bench.py --gpus N repeats this check in-run)")
+    out = _run_workers(os.path.join(ROOT, "tests", "dp_shard_worker.py"), min(n, 4), {"DP_DOUBLE": str(double)})
+    assert out.returncode == 0 and "DP_SHARD_OK" in out.stdout, (out.stdout[-2000:], out.stderr[-4000:])
+
+
 GAE_SHARD_WORKER = r'''
 import os, sys
 sys.path.insert(0, %r)
