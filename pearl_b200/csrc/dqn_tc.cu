@@ -55,8 +55,7 @@ int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *
 namespace {
 
 constexpr int NROW = 256;            // row threads: 2 groups x 4 warps
-constexpr int NTH = 384;             // launched threads: + one helper warpgroup (loader warp + 3 warps that only donate registers)
-constexpr int NLIVE = 288;           // threads that stay: row warps + loader
+constexpr int NTH = 384;             // 8 row warps + one helper warpgroup: loader, two MMA issuers, tile builder
 constexpr int HID = 64;
 // ---- shared memory map (bytes)
 constexpr int R_W1 = 0;              // 64 KB: stacked W1[:, :obs] tile [128][obs] (target, then online); grads: G1 operands
@@ -76,11 +75,11 @@ constexpr int TM_A0 = 0, TM_S0 = 256;          // group g: A operand at 128 g (h
 constexpr int TM_G1 = 0, TM_G2 = 128;          // weight-gradient accumulators (the A regions are free by then)
 
 // mbarrier indices
-enum {   // (B_SFULL: spare)
+enum {
     B_W1 = 0, B_W2, B_W2T, B_MMA /*2*/ = 3, B_W1FREE = 5, B_ACTDONE, B_RFULL /*2*/ = 7, B_RFREE /*2*/ = 9,
     // one barrier PER PASS for the two arena chains: a parity wait only tells adjacent phases apart, and pass p + 2 may
     // reach its wait before pass p has even committed
-    B_H1FREE /*8*/ = 11, B_H2FREE /*8*/ = 19, B_SFULL /*16*/ = 27, B_COUNT = 43
+    B_H1FREE /*8*/ = 11, B_H2FREE /*8*/ = 19, B_READY /*2*/ = 27, B_COUNT = 29
 };
 
 struct TcLearner {            // one per CTA, in global memory
@@ -140,7 +139,7 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory"); }
 __device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
-__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0, 288;" ::: "memory"); }   // row warps + loader
+__device__ __forceinline__ void cta_sync() { __syncthreads(); }
 
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
@@ -256,6 +255,13 @@ __device__ __forceinline__ void wait_chunk(const RowCtx &c, uint32_t n) {
     __syncwarp();
 }
 
+// hand the A operand (or any TMEM state) of this warp's rows to the group's issuer: 4 warp arrivals complete a phase
+__device__ __forceinline__ void publish_a(const RowCtx &c) {
+    umma::tmem_st_wait();
+    umma::fence_before_thread_sync();
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(c.bar + B_READY + c.g);
+}
 __device__ __forceinline__ void wait_group_mma(RowCtx &c) {
     umma::mbar_wait(c.bar + B_MMA + c.g, (c.n_mma - 1) & 1);
     umma::fence_after_thread_sync();
@@ -266,9 +272,8 @@ __device__ __forceinline__ void wait_group_mma(RowCtx &c) {
 // writes it to tensor memory (TS product: A never exists in shared memory in operand layout).  Two chunks (K = 64)
 // per MMA batch.  `request_ahead(n)`: issue the copies of the warp's chunk number n (two ahead of the one just read).
 template <typename NextFn>
-__device__ __forceinline__ void layer1(RowCtx &c, int obs, uint32_t w1_parity, NextFn request_ahead) {
+__device__ __forceinline__ void layer1(RowCtx &c, int obs, NextFn request_ahead) {
     const int nch = (obs + 31) >> 5;
-    const umma::Tile W1 = umma::make_tile(c.smem + R_W1, obs, 128);
     bool pending = false;
     for (int cc = 0; cc < nch; cc++) {
         const uint32_t n = c.n_chunk++;
@@ -296,22 +301,7 @@ __device__ __forceinline__ void layer1(RowCtx &c, int obs, uint32_t w1_parity, N
             umma::tmem_st32(c.tlane + c.a_col + 64 + 32 * (cc & 1), lo);
         }
         if ((cc & 1) || cc == nch - 1) {
-            umma::tmem_st_wait();
-            umma::fence_before_thread_sync();
-            group_sync(c.g);
-            if (c.elected) {
-                umma::fence_after_thread_sync();
-                if (cc <= 1) umma::mbar_wait(c.bar + B_W1, w1_parity);      // the weight tile has landed
-                const int ksteps = (((cc & 1) ? 32 : 0) + kc) >> 3, k0 = (cc & ~1) * 32;
-                const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
-                uint64_t bd = W1.shifted((uint32_t)(k0 >> 2) * 128).desc(0);
-                for (int ks = 0; ks < ksteps; ks++) {
-                    umma::mma_tf32_ts(c.tm + c.s_col, c.tm + c.a_col + ks * 8, bd, i128, cc > 1 || ks > 0);   // hi x [W_hi ; W_lo]
-                    umma::mma_tf32_ts(c.tm + c.s_col, c.tm + c.a_col + 64 + ks * 8, bd, i64, true);        // lo x W_hi
-                    bd += (uint64_t)((2 * 128) >> 4);
-                }
-                umma::mma_commit(c.bar + B_MMA + c.g);
-            }
+            publish_a(c);                           // the group's issuer multiplies this K batch (stacked W1 tile)
             c.n_mma++;
             pending = true;
         }
@@ -319,24 +309,75 @@ __device__ __forceinline__ void layer1(RowCtx &c, int obs, uint32_t w1_parity, N
     wait_group_mma(c);
 }
 
-// one 128 x 64 x 64 product of the group, A (hi | lo) in the group's TMEM A columns, B = the stacked tile at `region`
-//   stacked:  acc[128 cols] : [0,64) = A_hi W_hi + A_lo W_hi, [64,128) = A_hi W_lo        (N = 128 + N = 64 per K step)
-//   plain:    acc[64 cols] at acc_col                                                     (3 x N = 64 per K step)
-__device__ __forceinline__ void issue_hidden(const RowCtx &c, int region, bool stacked, uint32_t acc_col) {
-    const umma::Tile Wt = umma::make_tile(c.smem + region, HID, 128);
-    if (stacked) {
-        const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
-        uint64_t bd = Wt.desc(0);
+// ---- issuer side (one lane of a helper warp per row group) -------------------------------------------------------------
+struct IssueCtx { uint32_t tm, a_col; char *smem; uint64_t *done; };
+// K batch `b` (64 columns) of layer 1: acc[128 stacked columns] (+)= A [W_hi ; W_lo]^T : hi x stacked (N = 128), lo x W_hi (N = 64)
+__device__ __forceinline__ void issue_layer1(const IssueCtx &x, int obs, int b, uint32_t acc_col) {
+    const umma::Tile W1 = umma::make_tile(x.smem + R_W1, obs, 128);
+    const int ksteps = min(64, obs - 64 * b) >> 3;
+    const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
+    uint64_t bd = W1.shifted((uint32_t)(16 * b) * 128).desc(0);
+    for (int ks = 0; ks < ksteps; ks++) {
+        umma::mma_tf32_ts(x.tm + acc_col, x.tm + x.a_col + ks * 8, bd, i128, b > 0 || ks > 0);
+        umma::mma_tf32_ts(x.tm + acc_col, x.tm + x.a_col + 64 + ks * 8, bd, i64, true);
+        bd += (uint64_t)((2 * 128) >> 4);
+    }
+    umma::mma_commit(x.done);
+}
+// one 128 x 64 x 64 product, A (hi | lo) in the group's TMEM A columns, B = the stacked [hi ; lo] tile at `region`:
+// acc[64 columns at acc_col] = A_lo W_hi + A_hi W_lo + A_hi W_hi
+__device__ __forceinline__ void issue_hidden(const IssueCtx &x, int region, uint32_t acc_col) {
+    const umma::Tile Wt = umma::make_tile(x.smem + region, HID, 128);
+    umma::gemm3_ts(x.tm + acc_col, x.tm + x.a_col, x.tm + x.a_col + 64, Wt, Wt.rows_from(64), 128, HID, HID, false);
+    umma::mma_commit(x.done);
+}
+
+// stacked K-major operand tile [hi ; lo] of W[rows = 64 outputs][K] in shared memory from the flat fp32 weights
+// (row pitch `ld` floats); `transpose`: the tile of W^T (K = 64 outputs of W, rows = inputs).  One warp; lane = (row % 8,
+// chunk % 4): conflict-free 16-byte shared stores, 64-byte global segments.
+__device__ void build_tile_warp(float *tile, const float *__restrict__ W, int ld, int K, bool vec, int lane) {
+    if (vec) {
+        const int rl = lane & 7, cl = lane >> 3, cg = (K + 15) >> 4;     // groups of 4 chunks along K
+        for (int it = 0; it < 8 * cg; it += 4) {
+            float4 v[4];
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) {
-            umma::mma_tf32_ts(c.tm + acc_col, c.tm + c.a_col + ks * 8, bd, i128, ks > 0);
-            umma::mma_tf32_ts(c.tm + acc_col, c.tm + c.a_col + 64 + ks * 8, bd, i64, true);
-            bd += (uint64_t)((2 * 128) >> 4);
+            for (int u = 0; u < 4; u++) {
+                const int i2 = it + u, r = (i2 / cg) * 8 + rl, k = ((i2 % cg) * 4 + cl) * 4;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i2 < 8 * cg && k < K) v[u] = __ldcg(reinterpret_cast<const float4 *>(W + (size_t)r * ld + k));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i2 = it + u, r = (i2 / cg) * 8 + rl, k = ((i2 % cg) * 4 + cl) * 4;
+                if (i2 < 8 * cg && k < K) {
+                    *reinterpret_cast<float4 *>(tile + umma::tile_index(r, k, K)) = v[u];
+                    *reinterpret_cast<float4 *>(tile + umma::tile_index(64 + r, k, K)) =
+                        make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
+                }
+            }
         }
     } else {
-        umma::gemm3_ts(c.tm + acc_col, c.tm + c.a_col, c.tm + c.a_col + 64, Wt, Wt.rows_from(64), 128, HID, HID, false);
+        for (int e = lane; e < 64 * K; e += 32) {
+            const int r = e / K, k = e - r * K;
+            const float x = __ldcg(W + (size_t)r * ld + k);
+            tile[umma::tile_index(r, k, K)] = x;
+            tile[umma::tile_index(64 + r, k, K)] = tf32_lo(x);
+        }
     }
-    umma::mma_commit(c.bar + B_MMA + c.g);
+}
+// the tile of W2^T: element (r = input k, column = output j) = W2[j][k]; coalesced global reads along k, scattered stores
+__device__ void build_w2t_warp(float *tile, const float *__restrict__ W2, int lane) {
+    for (int e0 = lane; e0 < HID * HID; e0 += 32 * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = __ldcg(W2 + e0 + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + 32 * u, j = e >> 6, k = e & 63;
+            tile[umma::tile_index(k, j, HID)] = v[u];
+            tile[umma::tile_index(64 + k, j, HID)] = tf32_lo(v[u]);
+        }
+    }
 }
 
 // registers -> the group's A operand (hi | lo), 32 columns at `col`
@@ -346,12 +387,6 @@ __device__ __forceinline__ void put_a32(const RowCtx &c, int col, const float *h
     for (int i = 0; i < 32; i++) lo[i] = tf32_lo(hi[i]);
     umma::tmem_st32(c.tlane + c.a_col + col, hi);
     umma::tmem_st32(c.tlane + c.a_col + 64 + col, lo);
-}
-// hand the A operand to the issuing lane
-__device__ __forceinline__ void publish_a(const RowCtx &c) {
-    umma::tmem_st_wait();
-    umma::fence_before_thread_sync();
-    group_sync(c.g);
 }
 
 // N parameters: all loads first (one L2 round trip), then the arithmetic, then the stores
@@ -397,11 +432,11 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     if (warp == 0) umma::tmem_alloc(&mi.tmem_base, 512);
     if (tid == 0)
         for (int i = 0; i < B_COUNT; i++)
-            umma::mbar_init(bar + i, (i == B_W1FREE || i == B_ACTDONE) ? ntiles : (i == B_RFULL || i == B_RFULL + 1) ? 32 : 1);
+            umma::mbar_init(bar + i, (i == B_W1FREE || i == B_ACTDONE) ? ntiles : (i == B_RFULL || i == B_RFULL + 1) ? 32
+                                    : (i == B_READY || i == B_READY + 1) ? 4 : 1);
     // prologue: the operand-layout tiles and the small vectors follow the flat parameters (which the host may have
     // changed between calls)
     if (warp < 8) {
-        rebuild_tiles(L.w, d, L.tiles + to.oW1, L.tiles + to.oW2, L.tiles + to.oW2T, tid);
         rebuild_tiles(L.wt, d, L.tiles + to.tW1, L.tiles + to.tW2, nullptr, tid);
         load_smalls(L.wt, d, mi.t, tid);
         load_smalls(L.w, d, mi.o, tid);
@@ -418,47 +453,112 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
 
     if (warp >= 8) {
         // ================================================================== helper warpgroup
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp > 8) return;                    // three warps exist only to hand their registers to the row warps
-        // ---- LOADER: weight tiles and the raw rows of the weight-gradient passes, all TMA
-        for (int round = 0; round < a.rounds; round++) {
-            cta_sync();   // (A)
-            int pslot[8];
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        auto soft_due = [&](int round) { return (L.steps0 + round + 2) % a.freq == 0; };
+        if (warp == 8) {
+            // ---- LOADER: target weight tiles by TMA, raw state rows of the weight-gradient passes by cp.async
+            bool w1_prefetched = false;
+            for (int round = 0; round < a.rounds; round++) {
+                cta_sync();   // (A)
+                int pslot[8];
 #pragma unroll
-            for (int p = 0; p < 8; p++) pslot[p] = p < np ? L.slots[(size_t)round * a.B + p * 32 + lane] : 0;
-            if (lane == 0) {
-                mbar_expect_tx(bar + B_W1, w1_bytes);  bulk_g2s(smem + R_W1, L.tiles + to.tW1, w1_bytes, bar + B_W1);
-                mbar_expect_tx(bar + B_W2T, w2_bytes); bulk_g2s(smem + R_W2T, L.tiles + to.tW2, w2_bytes, bar + B_W2T);
-                mbar_expect_tx(bar + B_W2, w2_bytes);  bulk_g2s(smem + R_W2, L.tiles + to.oW2, w2_bytes, bar + B_W2);
-                umma::mbar_wait(bar + B_W1FREE, round & 1);      // every group is through target layer 1
-                mbar_expect_tx(bar + B_W1, w1_bytes);  bulk_g2s(smem + R_W1, L.tiles + to.oW1, w1_bytes, bar + B_W1);
-                umma::mbar_wait(bar + B_ACTDONE, round & 1);     // ... and through the all-actions products
-                mbar_expect_tx(bar + B_W2T, w2_bytes); bulk_g2s(smem + R_W2T, L.tiles + to.oW2T, w2_bytes, bar + B_W2T);
-            }
-            __syncwarp();
-            cta_sync();   // (B) phase O done: the weight regions become the arena of the weight-gradient passes
+                for (int p = 0; p < 8; p++) pslot[p] = p < np ? L.slots[(size_t)round * a.B + p * 32 + lane] : 0;
+                if (lane == 0) {
+                    if (!w1_prefetched) { mbar_expect_tx(bar + B_W1, w1_bytes); bulk_g2s(smem + R_W1, L.tiles + to.tW1, w1_bytes, bar + B_W1); }
+                    mbar_expect_tx(bar + B_W2T, w2_bytes); bulk_g2s(smem + R_W2T, L.tiles + to.tW2, w2_bytes, bar + B_W2T);
+                }
+                __syncwarp();
+                cta_sync();   // (B) phase O done: the weight regions become the arena of the weight-gradient passes
 #pragma unroll
-            for (int p = 0; p < 8; p++) {
-                if (p < np) {
-                    const uint32_t n = n_pass + p, b = n & 1;
-                    umma::mbar_wait(bar + B_RFREE + b, ((n >> 1) & 1) ^ 1);
-                    float *raw = reinterpret_cast<float *>(smem + (b ? R_W2T : R_W2));
-                    const int q4 = obs >> 2;                       // 16-byte chunks per row
-                    for (int idx = lane; idx < 32 * q4; idx += 32) {
-                        const int row = idx / q4, ch = idx - row * q4;
-                        const int slot = __shfl_sync(0xffffffffu, pslot[p], row);
-                        cp_async16(raw + row * RAWP + 4 * ch, reinterpret_cast<const float *>(L.records + (size_t)slot * W) + a.lay.off_state + 4 * ch);
+                for (int p = 0; p < 8; p++) {
+                    if (p < np) {
+                        const uint32_t n = n_pass + p, b = n & 1;
+                        umma::mbar_wait(bar + B_RFREE + b, ((n >> 1) & 1) ^ 1);
+                        float *raw = reinterpret_cast<float *>(smem + (b ? R_W2T : R_W2));
+                        const int q4 = obs >> 2;                       // 16-byte chunks per row
+                        for (int idx = lane; idx < 32 * q4; idx += 32) {
+                            const int row = idx / q4, ch = idx - row * q4;
+                            const int slot = __shfl_sync(0xffffffffu, pslot[p], row);
+                            cp_async16(raw + row * RAWP + 4 * ch, reinterpret_cast<const float *>(L.records + (size_t)slot * W) + a.lay.off_state + 4 * ch);
+                        }
+                        // the barrier's 32 arrivals fire as each lane's copies land
+                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar + B_RFULL + b)) : "memory");
                     }
-                    // the barrier's 32 arrivals fire as each lane's copies land
-                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar + B_RFULL + b)) : "memory");
+                }
+                n_pass += np;
+                // the next round's target W1 tile can travel while AdamW runs (the G1 arena is free once the last pass has
+                // multiplied), unless a soft target update is about to rewrite it
+                w1_prefetched = false;
+                if (round + 1 < a.rounds && !soft_due(round + 1)) {
+                    umma::mbar_wait(bar + B_H2FREE + np - 1, round & 1);
+                    if (lane == 0) { mbar_expect_tx(bar + B_W1, w1_bytes); bulk_g2s(smem + R_W1, L.tiles + to.tW1, w1_bytes, bar + B_W1); }
+                    w1_prefetched = true;
                 }
             }
-            n_pass += np;
+        } else if (warp == 11) {
+            // ---- TILE BUILDER: the online network's operand tiles straight from the flat weights AdamW just wrote
+            const bool vec1 = (d.D & 3) == 0 && (reinterpret_cast<uintptr_t>(L.w) & 15) == 0, vec2 = (d.oW2 & 3) == 0 && vec1;
+            for (int round = 0; round < a.rounds; round++) {
+                cta_sync();   // (A): AdamW's writes are visible
+                build_tile_warp(reinterpret_cast<float *>(smem + R_W2), L.w + d.oW2, HID, HID, vec2, lane);
+                umma::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + B_W2);
+                umma::mbar_wait(bar + B_W1FREE, round & 1);       // every group is through target layer 1
+                build_tile_warp(reinterpret_cast<float *>(smem + R_W1), L.w + d.oW1, d.D, obs, vec1, lane);
+                umma::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + B_W1);
+                umma::mbar_wait(bar + B_ACTDONE, round & 1);      // ... and through the all-actions products (target W2 is free)
+                build_w2t_warp(reinterpret_cast<float *>(smem + R_W2T), L.w + d.oW2, lane);
+                umma::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + B_W2T);
+                cta_sync();   // (B)
+            }
+        } else {
+            // ---- ISSUER of row group g: the group's products in program order, one lane; the row warps only publish
+            //      operands (B_READY) and wait for results (B_MMA), so the ~50-60 clk per issued MMA never blocks a row warp
+            const int g = warp - 9;
+            IssueCtx x;
+            x.tm = mi.tmem_base; x.a_col = TM_A0 + 128 * g; x.smem = smem; x.done = bar + B_MMA + g;
+            const uint32_t s_col = TM_S0 + 128 * g;
+            uint32_t n_ready = 0;
+            const int nb = (nch + 1) >> 1;
+            for (int round = 0; round < a.rounds; round++) {
+                cta_sync();   // (A)
+                if (g < ntiles && lane == 0) {
+                    auto ready = [&]() { umma::mbar_wait(bar + B_READY + g, n_ready & 1); n_ready++; umma::fence_after_thread_sync(); };
+                    for (int b = 0; b < nb; b++) {                       // target layer 1
+                        ready();
+                        if (b == 0) umma::mbar_wait(bar + B_W1, 0);
+                        issue_layer1(x, obs, b, s_col);
+                    }
+                    for (int ac = 0; ac < d.A; ac++) {                   // all-actions products, accumulators alternate
+                        ready();
+                        if (ac == 0) umma::mbar_wait(bar + B_W2T, 0);
+                        issue_hidden(x, R_W2T, s_col + 64 * (ac & 1));
+                    }
+                    for (int b = 0; b < nb; b++) {                       // online layer 1
+                        ready();
+                        if (b == 0) umma::mbar_wait(bar + B_W1, 1);
+                        issue_layer1(x, obs, b, s_col);
+                    }
+                    ready();                                             // layer 2
+                    umma::mbar_wait(bar + B_W2, round & 1);
+                    issue_hidden(x, R_W2, s_col + 64);
+                    ready();                                             // dH1 = dZ2 W2
+                    umma::mbar_wait(bar + B_W2T, 1);
+                    issue_hidden(x, R_W2T, s_col + 64);
+                }
+                __syncwarp();
+                cta_sync();   // (B)
+            }
         }
         cta_sync();       // end: everything is done before warp 0 frees the tensor memory
         return;
     }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
 
     RowCtx c;
     c.warp = warp; c.lane = lane; c.g = (warp >> 2) & 1; c.q = warp & 3; c.m = tid & 127;
@@ -530,7 +630,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     issue_chunk(c, n, mi.rowptr[warp], s < nch ? a.lay.off_next_state : a.lay.off_state, s < nch ? s : s - nch, obs);
             };
             // ================= phase T: y = max_a' Q_target(s', a') * gamma * (1 - term) + r =================
-            layer1(c, obs, 0, ahead);
+            layer1(c, obs, ahead);
             float yv;
             {
                 float t1[64];
@@ -548,37 +648,35 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 if (c.elected) mbar_arrive(bar + B_W1FREE);
                 TC_STAMP(2);
                 float best = -INFINITY;
-                auto epilogue = [&](int ap) {
+                auto epilogue = [&](int ap) {     // accumulator (ap & 1): 64 columns at s_col + 64 (ap & 1)
                     float qv = 0.f;
 #pragma unroll
                     for (int half = 0; half < 2; half++) {
-                        float d1[32], d2[32];
-                        umma::tmem_ld32(c.tlane + c.s_col + 32 * half, d1);
-                        umma::tmem_ld32(c.tlane + c.s_col + 64 + 32 * half, d2);
+                        float d1[32];
+                        umma::tmem_ld32(c.tlane + c.s_col + 64 * (ap & 1) + 32 * half, d1);
 #pragma unroll
                         for (int c4 = 0; c4 < 8; c4++) {
                             const float4 w3v = *reinterpret_cast<const float4 *>(&mi.t.w3[32 * half + 4 * c4]);
                             const float4 b2v = *reinterpret_cast<const float4 *>(&mi.t.b2[32 * half + 4 * c4]);
-                            qv = fmaf(w3v.x, fmaxf((d1[4 * c4 + 0] + d2[4 * c4 + 0]) + b2v.x, 0.f), qv);
-                            qv = fmaf(w3v.y, fmaxf((d1[4 * c4 + 1] + d2[4 * c4 + 1]) + b2v.y, 0.f), qv);
-                            qv = fmaf(w3v.z, fmaxf((d1[4 * c4 + 2] + d2[4 * c4 + 2]) + b2v.z, 0.f), qv);
-                            qv = fmaf(w3v.w, fmaxf((d1[4 * c4 + 3] + d2[4 * c4 + 3]) + b2v.w, 0.f), qv);
+                            qv = fmaf(w3v.x, fmaxf(d1[4 * c4 + 0] + b2v.x, 0.f), qv);
+                            qv = fmaf(w3v.y, fmaxf(d1[4 * c4 + 1] + b2v.y, 0.f), qv);
+                            qv = fmaf(w3v.z, fmaxf(d1[4 * c4 + 2] + b2v.z, 0.f), qv);
+                            qv = fmaf(w3v.w, fmaxf(d1[4 * c4 + 3] + b2v.w, 0.f), qv);
                         }
                     }
                     qv += mi.t.b3;
                     if (ap >= cnt) qv = -INFINITY;   // next_state_action_values[mask] = -inf
                     best = fmaxf(best, qv);
                 };
+                // Two accumulators per group: while the issuer multiplies action slot a, the row warps run the epilogue of
+                // slot a - 1; the A operand is rebuilt as soon as product a - 1 has read it.
                 for (int ac = 0; ac < d.A; ac++) {
                     int id = ac;
                     if (dyn && ac < cnt) {
                         const uint32_t wsel = ac < 4 ? ids0 : ac < 8 ? ids1 : ac < 12 ? ids2 : ids3;
                         id = (int)((wsel >> (8 * (ac & 3))) & 0xffu);
                     }
-                    if (ac > 0) {
-                        wait_group_mma(c);      // the previous product is done: its A operand is free, its result is ready
-                        epilogue(ac - 1);
-                    }
+                    if (ac > 0) wait_group_mma(c);      // product ac - 1 is done: the A operand is free, its result is ready
 #pragma unroll
                     for (int half = 0; half < 2; half++) {
                         float h[32];
@@ -593,12 +691,8 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         put_a32(c, 32 * half, h);
                     }
                     publish_a(c);
-                    if (c.elected) {
-                        umma::fence_after_thread_sync();
-                        if (ac == 0) umma::mbar_wait(bar + B_W2T, 0);      // target W2 has landed
-                        issue_hidden(c, R_W2T, true, c.s_col);
-                    }
                     c.n_mma++;
+                    if (ac > 0) epilogue(ac - 1);       // overlaps product ac
                 }
                 wait_group_mma(c);
                 epilogue(d.A - 1);
@@ -608,7 +702,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             TC_STAMP(3);
 
             // ================= phase O: online forward, loss, backward through the hidden layers =================
-            layer1(c, obs, 1, ahead);
+            layer1(c, obs, ahead);
             uint32_t mask1a = 0u, mask1b = 0u;
             {
                 float h1[64];
@@ -635,11 +729,6 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             }
             TC_STAMP(4);
             publish_a(c);
-            if (c.elected) {
-                umma::fence_after_thread_sync();
-                umma::mbar_wait(bar + B_W2, round & 1);
-                issue_hidden(c, R_W2, false, c.s_col + 64);
-            }
             c.n_mma++;
             wait_group_mma(c);
             {
@@ -674,12 +763,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 }
                 put_a32(c, 0, z);
                 put_a32(c, 32, z + 32);
-                publish_a(c);
-                if (c.elected) {
-                    umma::fence_after_thread_sync();
-                    umma::mbar_wait(bar + B_W2T, 1);        // online W2^T has landed
-                    issue_hidden(c, R_W2T, false, c.s_col + 64);   // dH1 = dZ2 W2
-                }
+                publish_a(c);                               // dH1 = dZ2 W2
                 c.n_mma++;
                 wait_group_mma(c);
                 umma::tmem_ld32(c.tlane + c.s_col + 64, z);
@@ -717,91 +801,104 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         TC_STAMP(6);
 
         // ================= weight gradients: pass p = the 32 batch rows of warp p =================
-        if (active) {
-            const int p = warp;
-            const uint32_t n = n_pass + p;
+        // Two warps per pass: the OWNER (warp p: the rows are its TMEM lanes and its registers hold dq, the ReLU mask and
+        // the action) builds the G2 operands [E ; H1 ; 0]^T and [dZ2 | dZ1]^T and issues G2; its PARTNER (warp p + 4 mod 8:
+        // same TMEM lane quarter) builds the G1 operands S^T (from the raw rows the loader fetched) and dZ1^T and issues G1.
+        // Each arena half is handed from pass to pass through one mbarrier per pass (tcgen05.commit arrives on it).
+        {
             const int colbase = (lane >> 2) * (TL / 4) + (lane & 3);
-            float *eh_hi = reinterpret_cast<float *>(smem + H1_EHT_HI), *eh_lo = reinterpret_cast<float *>(smem + H1_EHT_LO);
-            float *dz_hi = reinterpret_cast<float *>(smem + H1_DZ_HI), *dz_lo = reinterpret_cast<float *>(smem + H1_DZ_LO);
-            float *st_hi = reinterpret_cast<float *>(smem + H2_ST_HI), *st_lo = reinterpret_cast<float *>(smem + H2_ST_LO);
-            float *dz1s = reinterpret_cast<float *>(smem + H2_DZ1);
-            float v[64];
-            umma::tmem_ld32(c.tlane + c.s_col, v);            // h1
-            umma::tmem_ld32(c.tlane + c.s_col + 32, v + 32);
-            if (p > 0) umma::mbar_wait(bar + B_H1FREE + p - 1, round & 1);      // the previous pass's G2 products are done
-            eh_hi[tt_off(0, colbase)] = 1.f;
+            auto owner_half = [&](int p) {
+                float *eh_hi = reinterpret_cast<float *>(smem + H1_EHT_HI), *eh_lo = reinterpret_cast<float *>(smem + H1_EHT_LO);
+                float *dz_hi = reinterpret_cast<float *>(smem + H1_DZ_HI), *dz_lo = reinterpret_cast<float *>(smem + H1_DZ_LO);
+                float v[64];
+                umma::tmem_ld32(c.tlane + c.s_col, v);            // h1
+                umma::tmem_ld32(c.tlane + c.s_col + 32, v + 32);
+                if (p > 0) umma::mbar_wait(bar + B_H1FREE + p - 1, round & 1);      // the previous pass's G2 products are done
+                eh_hi[tt_off(0, colbase)] = 1.f;
 #pragma unroll
-            for (int e = 0; e < 16; e++) eh_hi[tt_off(1 + e, colbase)] = (e == act_now) ? 1.f : 0.f;
+                for (int e = 0; e < 16; e++) eh_hi[tt_off(1 + e, colbase)] = (e == act_now) ? 1.f : 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; j++) {
-                eh_hi[tt_off(32 + j, colbase)] = v[j];
-                eh_lo[tt_off(32 + j, colbase)] = tf32_lo(v[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < 64; j++) {
-                const bool on = j < 32 ? ((mask2a >> j) & 1u) : ((mask2b >> (j - 32)) & 1u);
-                const float x = on ? dq * mi.o.w3[j] : 0.f;   // dZ2 again (cheaper than parking it)
-                dz_hi[tt_off(j, colbase)] = x;
-                dz_lo[tt_off(j, colbase)] = tf32_lo(x);
-            }
-            umma::tmem_ld32(c.tlane + c.s_col + 64, v);       // dZ1
-            umma::tmem_ld32(c.tlane + c.s_col + 96, v + 32);
-#pragma unroll
-            for (int j = 0; j < 64; j++) {
-                dz_hi[tt_off(64 + j, colbase)] = v[j];
-                dz_lo[tt_off(64 + j, colbase)] = tf32_lo(v[j]);
-            }
-            umma::fence_async_smem();
-            umma::fence_before_thread_sync();
-            __syncwarp();
-            if (lane == 0) {
-                umma::fence_after_thread_sync();
-                const umma::Tile EH{umma::smem_u32(eh_hi), TL, TSBO}, EL{umma::smem_u32(eh_lo), TL, TSBO};
-                const umma::Tile DH{umma::smem_u32(dz_hi), TL, TSBO}, DL{umma::smem_u32(dz_lo), TL, TSBO};
-                const uint32_t i128 = umma::make_idesc_tf32(128, 128);
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    umma::mma_tf32(c.tm + TM_G2, EL.desc(ks), DH.desc(ks), i128, p > 0 || ks > 0);
-                    umma::mma_tf32(c.tm + TM_G2, EH.desc(ks), DL.desc(ks), i128, true);
-                    umma::mma_tf32(c.tm + TM_G2, EH.desc(ks), DH.desc(ks), i128, true);
+                for (int j = 0; j < 64; j++) {
+                    eh_hi[tt_off(32 + j, colbase)] = v[j];
+                    eh_lo[tt_off(32 + j, colbase)] = tf32_lo(v[j]);
                 }
-                umma::mma_commit(bar + B_H1FREE + p);
-            }
-            __syncwarp();
-            // ---- G1 operands: S^T from the raw rows the loader fetched, dZ1^T stacked (hi ; lo)
-            if (p > 0) umma::mbar_wait(bar + B_H2FREE + p - 1, round & 1);   // first: orders this pass behind the fill it is about to wait for
-            umma::mbar_wait(bar + B_RFULL + (n & 1), (n >> 1) & 1);
-            const float *raw = reinterpret_cast<const float *>(smem + ((n & 1) ? R_W2T : R_W2)) + lane * RAWP;
+#pragma unroll
+                for (int j = 0; j < 64; j++) {
+                    const bool on = j < 32 ? ((mask2a >> j) & 1u) : ((mask2b >> (j - 32)) & 1u);
+                    const float x = on ? dq * mi.o.w3[j] : 0.f;   // dZ2 again (cheaper than parking it)
+                    dz_hi[tt_off(j, colbase)] = x;
+                    dz_lo[tt_off(j, colbase)] = tf32_lo(x);
+                }
+                umma::tmem_ld32(c.tlane + c.s_col + 64, v);       // dZ1
+                umma::tmem_ld32(c.tlane + c.s_col + 96, v + 32);
+#pragma unroll
+                for (int j = 0; j < 64; j++) {
+                    dz_hi[tt_off(64 + j, colbase)] = v[j];
+                    dz_lo[tt_off(64 + j, colbase)] = tf32_lo(v[j]);
+                }
+                umma::fence_async_smem();
+                umma::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    umma::fence_after_thread_sync();
+                    const umma::Tile EH{umma::smem_u32(eh_hi), TL, TSBO}, EL{umma::smem_u32(eh_lo), TL, TSBO};
+                    const umma::Tile DH{umma::smem_u32(dz_hi), TL, TSBO}, DL{umma::smem_u32(dz_lo), TL, TSBO};
+                    const uint32_t i128 = umma::make_idesc_tf32(128, 128);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        umma::mma_tf32(c.tm + TM_G2, EL.desc(ks), DH.desc(ks), i128, p > 0 || ks > 0);
+                        umma::mma_tf32(c.tm + TM_G2, EH.desc(ks), DL.desc(ks), i128, true);
+                        umma::mma_tf32(c.tm + TM_G2, EH.desc(ks), DH.desc(ks), i128, true);
+                    }
+                    umma::mma_commit(bar + B_H1FREE + p);
+                }
+                __syncwarp();
+            };
+            auto partner_half = [&](int p) {
+                float *st_hi = reinterpret_cast<float *>(smem + H2_ST_HI), *st_lo = reinterpret_cast<float *>(smem + H2_ST_LO);
+                float *dz1s = reinterpret_cast<float *>(smem + H2_DZ1);
+                const uint32_t n = n_pass + p;
+                const uint32_t s_owner = TM_S0 + 128 * (p >> 2);  // the owner group's parking columns, this warp's lane quarter
+                float v[64];
+                umma::tmem_ld32(c.tlane + s_owner + 64, v);       // dZ1 of the pass's rows
+                umma::tmem_ld32(c.tlane + s_owner + 96, v + 32);
+                if (p > 0) umma::mbar_wait(bar + B_H2FREE + p - 1, round & 1);   // first: orders this pass behind the fill it waits for next
+                umma::mbar_wait(bar + B_RFULL + (n & 1), (n >> 1) & 1);
+                const float *raw = reinterpret_cast<const float *>(smem + ((n & 1) ? R_W2T : R_W2)) + lane * RAWP;
 #pragma unroll 4
-            for (int k4 = 0; k4 < (obs >> 2); k4++) {
-                const float4 x = *reinterpret_cast<const float4 *>(raw + 4 * k4);
-                const int o = tt_off(4 * k4, colbase);      // rows 4 k4 .. 4 k4 + 3 share one 8-row group
-                st_hi[o] = x.x; st_hi[o + 4] = x.y; st_hi[o + 8] = x.z; st_hi[o + 12] = x.w;
-                st_lo[o] = tf32_lo(x.x); st_lo[o + 4] = tf32_lo(x.y); st_lo[o + 8] = tf32_lo(x.z); st_lo[o + 12] = tf32_lo(x.w);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar + B_RFREE + (n & 1));
-#pragma unroll
-            for (int j = 0; j < 64; j++) {
-                dz1s[tt_off(j, colbase)] = v[j];
-                dz1s[tt_off(64 + j, colbase)] = tf32_lo(v[j]);
-            }
-            umma::fence_async_smem();
-            umma::fence_before_thread_sync();
-            __syncwarp();
-            if (lane == 0) {
-                umma::fence_after_thread_sync();
-                const umma::Tile SH{umma::smem_u32(st_hi), TL, TSBO}, SL{umma::smem_u32(st_lo), TL, TSBO};
-                const umma::Tile D1{umma::smem_u32(dz1s), TL, TSBO};
-                const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    umma::mma_tf32(c.tm + TM_G1, SH.desc(ks), D1.desc(ks), i128, p > 0 || ks > 0);   // S_hi x [dZ1_hi ; dZ1_lo]
-                    umma::mma_tf32(c.tm + TM_G1, SL.desc(ks), D1.desc(ks), i64, true);              // S_lo x dZ1_hi
+                for (int k4 = 0; k4 < (obs >> 2); k4++) {
+                    const float4 x = *reinterpret_cast<const float4 *>(raw + 4 * k4);
+                    const int o = tt_off(4 * k4, colbase);      // rows 4 k4 .. 4 k4 + 3 share one 8-row group
+                    st_hi[o] = x.x; st_hi[o + 4] = x.y; st_hi[o + 8] = x.z; st_hi[o + 12] = x.w;
+                    st_lo[o] = tf32_lo(x.x); st_lo[o + 4] = tf32_lo(x.y); st_lo[o + 8] = tf32_lo(x.z); st_lo[o + 12] = tf32_lo(x.w);
                 }
-                umma::mma_commit(bar + B_H2FREE + p);
-            }
-            __syncwarp();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + B_RFREE + (n & 1));
+#pragma unroll
+                for (int j = 0; j < 64; j++) {
+                    dz1s[tt_off(j, colbase)] = v[j];
+                    dz1s[tt_off(64 + j, colbase)] = tf32_lo(v[j]);
+                }
+                umma::fence_async_smem();
+                umma::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    umma::fence_after_thread_sync();
+                    const umma::Tile SH{umma::smem_u32(st_hi), TL, TSBO}, SL{umma::smem_u32(st_lo), TL, TSBO};
+                    const umma::Tile D1{umma::smem_u32(dz1s), TL, TSBO};
+                    const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        umma::mma_tf32(c.tm + TM_G1, SH.desc(ks), D1.desc(ks), i128, p > 0 || ks > 0);   // S_hi x [dZ1_hi ; dZ1_lo]
+                        umma::mma_tf32(c.tm + TM_G1, SL.desc(ks), D1.desc(ks), i64, true);              // S_lo x dZ1_hi
+                    }
+                    umma::mma_commit(bar + B_H2FREE + p);
+                }
+                __syncwarp();
+            };
+            const int p_own = warp, p_par = (warp + 4) & 7;
+            if (p_par < p_own) { if (p_par < np) partner_half(p_par); if (p_own < np) owner_half(p_own); }
+            else               { if (p_own < np) owner_half(p_own); if (p_par < np) partner_half(p_par); }
         }
         umma::mbar_wait(bar + B_H1FREE + np - 1, round & 1);
         umma::mbar_wait(bar + B_H2FREE + np - 1, round & 1);
@@ -821,7 +918,6 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             AdamScalarsTc hs;
             hs.decay = a.decay; hs.omb1 = a.omb1; hs.beta2 = a.beta2; hs.omb2 = a.omb2; hs.eps = a.eps;
             hs.step_size = sc.x; hs.bc2_sqrt = sc.y; hs.inv_bc2_sqrt = 1.0f / sc.y;
-            float *tW1 = L.tiles + to.oW1, *tW2 = L.tiles + to.oW2, *tW2T = L.tiles + to.oW2T;
             const int gs = c.g, j0 = 32 * gs;
             {   // G1[lane k][col j] = dW1[j][k]: this thread owns input k, columns j0 .. j0 + 31 (coalesced over k)
                 float g1[32], g2[32];
@@ -838,9 +934,6 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         gg[u] = g1[jj + u] + g2[jj + u];
                     }
                     adam_n<4>(L, idx, gg, wn, hs);
-                    if (k < obs)
-#pragma unroll
-                        for (int u = 0; u < 4; u++) put_stacked(tW1, j0 + jj + u, k, obs, wn[u]);
                 }
             }
             if (c.q == 1 || c.q == 2) {   // G2 lanes 32 + k2: dW2[j][k2] in the dZ2 columns
@@ -854,11 +947,6 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) { idx[u] = d.oW2 + (j0 + jj + u) * HID + k2; gg[u] = g2[jj + u]; }
                     adam_n<4>(L, idx, gg, wn, hs);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        put_stacked(tW2, j0 + jj + u, k2, HID, wn[u]);
-                        put_stacked(tW2T, k2, j0 + jj + u, HID, wn[u]);
-                    }
                 }
             } else if (c.q == 0) {        // G2 lane 0: db2 (dZ2 columns), db1 (dZ1 columns); lanes 1..A: dW1[:, obs + a]
                 float gz2[32], gz1[32];
@@ -894,7 +982,6 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 }
                 adam_n<2>(L, idx, gg, wn, hs);
             }
-            fence_proxy_async_all();      // the tile writes are read by TMA next round
             umma::fence_before_thread_sync();
             rows_sync();
             load_smalls(L.w, d, mi.o, tid);

@@ -290,6 +290,94 @@ class B200ReplayBuffer(ReplayBuffer):
     def local_len(self) -> int:
         return int(self._lib.prl_buf_len(self._handle)) if self._handle.value else 0
 
+    # ------------------------------------------------------------------ snapshot / offline data
+    def state_dict(self) -> dict:
+        """Snapshot of the buffer: the stored records in FIFO order (oldest first, raw record words as the kernels keep
+        them), the layout needed to re-create the storage, and the sampler's MT19937 stream.  The reference never
+        serialises replay-buffer contents (the buffer is not a Module; `PearlAgent.compare` only checks its type,
+        pearl_agent.py:313-318) — this is what makes a B200 training job resumable."""
+        if self._shard:
+            raise NotImplementedError("snapshot a sharded buffer shard by shard with set_shard cleared")
+        n = self.local_len()
+        out = dict(capacity=self.capacity, len=n, is_action_continuous=bool(self._is_action_continuous),
+                   obs_dim=self.obs_dim, n_actions=self.n_actions, act_dim=self.act_dim, rng_mode=self._rng_mode)
+        if n:
+            W = self._layout.record_words
+            head = int(self._lib.prl_buf_head(self._handle))
+            rec = self._storage[: self.capacity * W].view(self.capacity, W)
+            order = (torch.arange(n, device=self._device) + head) % self.capacity
+            out.update(records=rec[order].cpu(), record_words=W, dynamic=bool(self._desc.flags & _lib.PRL_BUF_DYNAMIC_ACTIONS),
+                       mt_state=torch.from_numpy(self.get_rng_state().astype(np.int64)))
+        return out
+
+    def load_state_dict(self, sd: dict) -> None:
+        """Restore a snapshot taken by `state_dict()` (the contents land at logical positions 0 .. len-1)."""
+        if int(sd["capacity"]) != self.capacity:
+            raise ValueError(f"snapshot of a buffer of capacity {sd['capacity']}, this one holds {self.capacity}")
+        self._is_action_continuous = bool(sd["is_action_continuous"])
+        n = int(sd["len"])
+        if self._handle.value:
+            self.clear()
+        if n == 0:
+            return
+        if not self._handle.value or bool(self._desc.flags & _lib.PRL_BUF_DYNAMIC_ACTIONS) != bool(sd["dynamic"]):
+            if self._handle.value:
+                self._lib.prl_buf_destroy(self._handle)
+                self._handle = C.c_void_p(0)
+            self._allocate(int(sd["obs_dim"]), int(sd["n_actions"] or 0), int(sd["act_dim"]), bool(sd["dynamic"]))
+        W = self._layout.record_words
+        if int(sd["record_words"]) != W:
+            raise ValueError("snapshot record layout does not match this build")
+        self._storage[: n * W].copy_(sd["records"].reshape(-1).to(self._device))
+        _lib.check(self._lib.prl_buf_set_occupancy(self._handle, n, 0))
+        self.set_rng_state(sd["mt_state"].numpy().astype(np.uint32))
+
+    def load_offline_data(self, transitions, max_number_actions_if_discrete: Optional[int] = None, chunk: int = 65536) -> int:
+        """The reference's `get_offline_data_in_buffer` (utils/functional_utils/train_and_eval/
+        offline_learning_and_evaluation.py:39-137) for a B200 buffer: `transitions` is the iterable of dicts a `.pt` offline
+        data file holds (`observation, action, reward, next_observation, curr_available_actions, next_available_actions,
+        done`); they are packed into the device ring `chunk` at a time instead of one Python push each.  Discrete action
+        sets must be the full `range(max_number_actions)` (a `Discrete(n)` space or a DiscreteActionSpace of all ids), as in
+        the reference's offline benchmarks.  Returns the number of transitions loaded."""
+        if self._is_action_continuous:
+            if max_number_actions_if_discrete is not None:
+                raise ValueError("is_action_continuous = True requires max_number_actions to be None")
+        elif max_number_actions_if_discrete is None:
+            raise ValueError("is_action_continuous = False requires max_number_actions to be an integer value")
+        cols = dict(s=[], a=[], r=[], ns=[], d=[])
+        total = 0
+
+        def flush():
+            nonlocal total
+            if not cols["s"]:
+                return
+            n = len(cols["s"])
+            st = torch.stack([torch.as_tensor(x, dtype=torch.float32).reshape(-1) for x in cols["s"]])
+            ns = torch.stack([torch.as_tensor(x, dtype=torch.float32).reshape(-1) for x in cols["ns"]])
+            if self._is_action_continuous:
+                ac = torch.stack([torch.as_tensor(x, dtype=torch.float32).reshape(-1) for x in cols["a"]])
+            else:
+                ac = torch.tensor([int(torch.as_tensor(x).reshape(-1)[0]) for x in cols["a"]], dtype=torch.int32)
+            self.push_batch(st, ac, torch.tensor([float(x) for x in cols["r"]]), ns,
+                            torch.tensor([bool(x) for x in cols["d"]]), torch.zeros(n, dtype=torch.bool),
+                            max_number_actions=max_number_actions_if_discrete)
+            total += n
+            for v in cols.values():
+                v.clear()
+
+        for t in transitions:
+            if not self._is_action_continuous:
+                for key in ("curr_available_actions", "next_available_actions"):
+                    sp = t.get(key)
+                    if sp is not None and int(getattr(sp, "n", max_number_actions_if_discrete)) != max_number_actions_if_discrete:
+                        raise NotImplementedError("offline transitions with partial action sets: push them one by one")
+            cols["s"].append(t["observation"]); cols["a"].append(t["action"]); cols["r"].append(t["reward"])
+            cols["ns"].append(t["next_observation"]); cols["d"].append(t["done"])
+            if len(cols["s"]) >= chunk:
+                flush()
+        flush()
+        return total
+
     # ------------------------------------------------------------------ read side
     def __len__(self) -> int:
         if not self._handle.value:

@@ -131,3 +131,84 @@ def test_prioritized_push_after_dynamic_upgrade_gets_priorities():
     leaves = buf.sum_tree[C2:C2 + cap].cpu().numpy()
     assert (leaves > 0).all()                     # every stored row, old and new, can be drawn
     np.testing.assert_allclose(float(buf.sum_tree[1]), leaves.astype(np.float64).sum(), rtol=1e-5)
+
+
+def test_buffer_snapshot_round_trip_and_offline_loader():
+    """f4: `state_dict()` / `load_state_dict()` of the device ring (contents in FIFO order + sampler stream), and the
+    reference's offline-data format (list of transition dicts, offline_learning_and_evaluation.py:39-137) loaded in
+    chunks — same ring as one `push()` per transition."""
+    import io
+    import pearl_b200
+    from oracle.synth import make_transitions
+    cap, obs, A = 300, 6, 4
+    d = make_transitions(450, obs, A, seed=9)                 # wraps
+    t = torch.from_numpy
+    keys = ("state", "action", "reward", "next_state", "terminated", "truncated")
+    a = pearl_b200.B200ReplayBuffer(cap, rng="device")
+    a.push_batch(*(t(d[k]) for k in keys), max_number_actions=A)
+    a.seed(21)
+    a.sample(16)                                              # advance the stream before the snapshot
+    blob = io.BytesIO()
+    torch.save(a.state_dict(), blob)
+    blob.seek(0)
+    b = pearl_b200.B200ReplayBuffer(cap, rng="device")
+    b.load_state_dict(torch.load(blob, weights_only=False))
+    assert len(b) == len(a) == cap
+    la, _ = a.sample_indices(32, rounds=3)
+    lb, _ = b.sample_indices(32, rounds=3)
+    assert torch.equal(la, lb)
+    ba, bb = a._gather_logical(la[0]), b._gather_logical(lb[0])
+    for k in ("state", "next_state", "reward", "action", "terminated"):
+        assert torch.equal(ba[k], bb[k]), k
+
+    class Discrete:                                           # what a gym offline data set stores
+        def __init__(self, n):
+            self.n = n
+    rows = [dict(observation=t(d["state"][i]), action=int(d["action"][i]), reward=float(d["reward"][i]),
+                 next_observation=t(d["next_state"][i]), curr_available_actions=Discrete(A), next_available_actions=Discrete(A),
+                 done=bool(d["terminated"][i])) for i in range(450)]
+    c = pearl_b200.B200ReplayBuffer(cap, rng="device")
+    assert c.load_offline_data(rows, max_number_actions_if_discrete=A, chunk=128) == 450
+    e = pearl_b200.B200ReplayBuffer(cap, rng="device")
+    for r in rows[:40]:                                       # the per-transition path of the reference loader
+        e.push(state=r["observation"], action=r["action"], reward=r["reward"], next_state=r["next_observation"],
+               curr_available_actions=_Space(A), next_available_actions=_Space(A), terminated=r["done"], truncated=False,
+               max_number_actions=A)
+    assert len(c) == cap
+    gc = c._gather_logical(torch.arange(cap, dtype=torch.int32, device=c.device))
+    want = {k: t(d[k][150:]) for k in keys}
+    assert torch.equal(gc["state"].cpu(), want["state"]) and torch.equal(gc["reward"].cpu(), want["reward"])
+    assert torch.equal(gc["action"].cpu(), want["action"].long()) and torch.equal(gc["terminated"].cpu(), want["terminated"])
+    ge = e._gather_logical(torch.arange(40, dtype=torch.int32, device=e.device))
+    assert torch.equal(ge["state"].cpu(), t(d["state"][:40])) and torch.equal(ge["mask"].cpu(), torch.zeros((40, A), dtype=torch.bool))
+
+
+def test_act_is_greedy_over_available_actions_and_explores_like_the_reference():
+    """f2: `act()` (deep_td_learning.py:200-254): exploit = argmax over the AVAILABLE actions of the fused Q forward;
+    with an epsilon-greedy module the draw consumes the global `random` stream exactly like the reference's module."""
+    import pearl_b200
+    obs, A = 10, 6
+    torch.manual_seed(0)
+    learner = _learner(obs, A)
+    s = torch.randn(obs)
+    q = learner.q_values(s.reshape(1, -1))[0].cpu()
+    full = _Space(A)
+    assert int(learner.act(s, full, exploit=True)) == int(q.argmax())
+    sub = _Space(A)
+    sub.actions = [torch.tensor([i]) for i in (1, 3, 4)]
+    sub.n = 3
+    assert int(learner.act(s, sub, exploit=True)) == (1, 3, 4)[int(q[[1, 3, 4]].argmax())]
+
+    class EGreedy:                                            # epsilon_greedy_exploration.py:52-83
+        def act(self, subjective_state, action_space, exploit_action, values=None, **kw):
+            if random.random() < 0.5:
+                return action_space.actions[random.randrange(action_space.n)]
+            return exploit_action
+    learner.exploration_module = EGreedy()
+    random.seed(3)
+    got = [int(learner.act(s, full)) for _ in range(20)]
+    random.seed(3)
+    want = []
+    for _ in range(20):
+        want.append(random.randrange(A) if random.random() < 0.5 else int(q.argmax()))
+    assert got == want

@@ -14,22 +14,7 @@ from oracle.ppo_oracle import OraclePPO
 pytestmark = pytest.mark.gpu
 
 
-def _close(a, b, what, rtol=1e-4, atol=2e-6):
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    scale = max(float(np.abs(b).max()), 1e-30)
-    err = float(np.abs(a - b).max())
-    assert err <= atol + rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
-
-
-def _close_params(a, b, what, lr, rounds, rtol=1e-4, atol=2e-6):
-    """See tests/test_sac.py: an element whose gradient is zero to within fp32 summation noise may take its AdamW
-    step the other way (<= 2 lr per step); at most 2e-5 of the elements may be of that kind."""
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    scale = max(float(np.abs(b).max()), 1e-30)
-    err = np.abs(a - b)
-    bad = int((err > atol + rtol * scale).sum())
-    assert bad <= max(1, int(2e-5 * a.size)), f"{what}: {bad} of {a.size} elements off by more than {rtol:g} of scale {scale:.3e}"
-    assert float(err.max()) <= 2.02 * lr * rounds + atol, f"{what}: max abs err {float(err.max()):.3e} exceeds the AdamW bound"
+from _tol import close as _close, close_params as _close_params  # elementwise 1e-4 (+ counted AdamW outliers)
 
 
 def _rollout_buffer(states, action, reward, terminated, truncated, n_act, capacity=None, prefill=0):

@@ -16,24 +16,7 @@ from oracle.sac_oracle import OracleSAC
 pytestmark = pytest.mark.gpu
 
 
-def _close(a, b, what, rtol=1e-4, atol=2e-6):
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    scale = max(float(np.abs(b).max()), 1e-30)
-    err = float(np.abs(a - b).max())
-    assert err <= atol + rtol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
-
-
-def _close_params(a, b, what, lr, rounds, rtol=1e-4, atol=2e-6):
-    """Parameters after `rounds` AdamW steps.  AdamW moves every element by ~lr * m / sqrt(v) whatever the gradient's
-    magnitude, so an element whose gradient is zero to within fp32 summation noise (a ~1e-6 fraction of them) can step
-    the other way than in the reference: such elements may differ by up to 2 * lr per step.  Everything else is held
-    to 1e-4 of the parameter scale; at most 2e-5 of the elements (3 of the 171k actor weights) may be of that kind."""
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    scale = max(float(np.abs(b).max()), 1e-30)
-    err = np.abs(a - b)
-    bad = int((err > atol + rtol * scale).sum())
-    assert bad <= max(1, int(2e-5 * a.size)), f"{what}: {bad} of {a.size} elements off by more than {rtol:g} of scale {scale:.3e}"
-    assert float(err.max()) <= 2.02 * lr * rounds + atol, f"{what}: max abs err {float(err.max()):.3e} exceeds the AdamW bound"
+from _tol import close as _close, close_params as _close_params  # elementwise 1e-4 (+ counted AdamW outliers)
 
 
 def _fill(buf, st, ac, rw, ns, term):
