@@ -68,7 +68,7 @@ constexpr int SBUF = 32 * SROW * 4;  // 4608 B per (warp, buffer)
 // transposed tiles of the weight-gradient passes: 128 (M or N) x 32 batch rows, chunk pitch 144 B
 constexpr int TL = 144, TSBO = 8 * TL, TTILE = 16 * TSBO;   // 18432 B
 constexpr int H1_EHT_HI = STAGE, H1_EHT_LO = STAGE + TTILE, H1_DZ_HI = STAGE + 2 * TTILE, H1_DZ_LO = STAGE + 3 * TTILE;
-constexpr int H2_ST_HI = R_W1, H2_ST_LO = R_W1 + TTILE, H2_DZ1 = R_W1 + 2 * TTILE;
+constexpr int H2_ST_HI = R_W1, H2_ST_LO = R_W1 + TTILE;
 constexpr int RAWP = 132;            // floats per raw row (128 + 4)
 // ---- tensor memory columns
 constexpr int TM_A0 = 0, TM_S0 = 256;          // group g: A operand at 128 g (hi 64 | lo 64), accumulators / parking at 256 + 128 g
@@ -79,7 +79,7 @@ enum {
     B_W1 = 0, B_W2, B_W2T, B_MMA /*2*/ = 3, B_W1FREE = 5, B_ACTDONE, B_RFULL /*2*/ = 7, B_RFREE /*2*/ = 9,
     // one barrier PER PASS for the two arena chains: a parity wait only tells adjacent phases apart, and pass p + 2 may
     // reach its wait before pass p has even committed
-    B_H1FREE /*8*/ = 11, B_H2FREE /*8*/ = 19, B_READY /*2*/ = 27, B_COUNT = 29
+    B_H1FREE /*8*/ = 11, B_H2FREE /*8*/ = 19, B_READY /*2*/ = 27, B_DZREADY /*8*/ = 29, B_COUNT = 37
 };
 
 struct TcLearner {            // one per CTA, in global memory
@@ -332,6 +332,21 @@ __device__ __forceinline__ void issue_hidden(const IssueCtx &x, int region, uint
     umma::mma_commit(x.done);
 }
 
+// the same product against the stacked tile as ONE N = 128 issue (A_hi x [W_hi ; W_lo]) plus one N = 64 issue (A_lo x W_hi)
+// per K step: acc[128 columns] = [A_hi W_hi + A_lo W_hi | A_hi W_lo]
+__device__ __forceinline__ void issue_hidden_stacked(const IssueCtx &x, int region, uint32_t acc_col) {
+    const umma::Tile Wt = umma::make_tile(x.smem + region, HID, 128);
+    const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
+    uint64_t bd = Wt.desc(0);
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+        umma::mma_tf32_ts(x.tm + acc_col, x.tm + x.a_col + ks * 8, bd, i128, ks > 0);
+        umma::mma_tf32_ts(x.tm + acc_col, x.tm + x.a_col + 64 + ks * 8, bd, i64, true);
+        bd += (uint64_t)((2 * 128) >> 4);
+    }
+    umma::mma_commit(x.done);
+}
+
 // stacked K-major operand tile [hi ; lo] of W[rows = 64 outputs][K] in shared memory from the flat fp32 weights
 // (row pitch `ld` floats); `transpose`: the tile of W^T (K = 64 outputs of W, rows = inputs).  One warp; lane = (row % 8,
 // chunk % 4): conflict-free 16-byte shared stores, 64-byte global segments.
@@ -389,22 +404,6 @@ __device__ __forceinline__ void put_a32(const RowCtx &c, int col, const float *h
     umma::tmem_st32(c.tlane + c.a_col + 64 + col, lo);
 }
 
-// N parameters: all loads first (one L2 round trip), then the arithmetic, then the stores
-template <int N>
-__device__ __forceinline__ void adam_n(const TcLearner &L, const int (&idx)[N], const float (&g)[N], float (&wn)[N],
-                                       const AdamScalarsTc &hs) {
-    float w[N], m[N], v[N], x[N];
-#pragma unroll
-    for (int i = 0; i < N; i++)
-        if (idx[i] >= 0) { w[i] = __ldcg(L.w + idx[i]); m[i] = __ldcg(L.m + idx[i]); v[i] = __ldcg(L.v + idx[i]); x[i] = __ldcg(L.vmax + idx[i]); }
-#pragma unroll
-    for (int i = 0; i < N; i++)
-        if (idx[i] >= 0) {
-            wn[i] = adam_math(w[i], m[i], v[i], x[i], g[i], hs);
-            L.w[idx[i]] = wn[i]; L.m[idx[i]] = m[i]; L.v[idx[i]] = v[i]; L.vmax[idx[i]] = x[i];
-        }
-}
-
 // float offset of element (r, column = batch row `col` of the pass) inside a transposed 128 x 32 tile
 __device__ __forceinline__ int tt_off(int r, int colbase) { return (r >> 3) * (TSBO / 4) + (r & 7) * 4 + colbase; }
 
@@ -429,11 +428,17 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
     const uint32_t w1_bytes = 128u * obs * 4, w2_bytes = 128u * HID * 4;
 
+    // De-phase the learners: identical CTAs started together would run in lock-step and hit L2 / HBM with their AdamW
+    // sweeps (432 KB each) and row gathers all at once; a start offset of up to ~50 us spreads those bursts over the round.
+    if (tid == 0 && gridDim.x > 1) {
+        const long long t0 = clock64(), wait = (long long)(blockIdx.x % 48) * 2000;
+        while (clock64() - t0 < wait) __nanosleep(100);
+    }
     if (warp == 0) umma::tmem_alloc(&mi.tmem_base, 512);
     if (tid == 0)
         for (int i = 0; i < B_COUNT; i++)
             umma::mbar_init(bar + i, (i == B_W1FREE || i == B_ACTDONE) ? ntiles : (i == B_RFULL || i == B_RFULL + 1) ? 32
-                                    : (i == B_READY || i == B_READY + 1) ? 4 : 1);
+                                    : (i == B_READY || i == B_READY + 1) ? 4 : (i >= B_H1FREE && i < B_H1FREE + 8) ? 2 : 1);
     // prologue: the operand-layout tiles and the small vectors follow the flat parameters (which the host may have
     // changed between calls)
     if (warp < 8) {
@@ -457,14 +462,13 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         auto soft_due = [&](int round) { return (L.steps0 + round + 2) % a.freq == 0; };
         if (warp == 8) {
             // ---- LOADER: target weight tiles by TMA, raw state rows of the weight-gradient passes by cp.async
-            bool w1_prefetched = false;
             for (int round = 0; round < a.rounds; round++) {
                 cta_sync();   // (A)
                 int pslot[8];
 #pragma unroll
                 for (int p = 0; p < 8; p++) pslot[p] = p < np ? L.slots[(size_t)round * a.B + p * 32 + lane] : 0;
                 if (lane == 0) {
-                    if (!w1_prefetched) { mbar_expect_tx(bar + B_W1, w1_bytes); bulk_g2s(smem + R_W1, L.tiles + to.tW1, w1_bytes, bar + B_W1); }
+                    mbar_expect_tx(bar + B_W1, w1_bytes);  bulk_g2s(smem + R_W1, L.tiles + to.tW1, w1_bytes, bar + B_W1);
                     mbar_expect_tx(bar + B_W2T, w2_bytes); bulk_g2s(smem + R_W2T, L.tiles + to.tW2, w2_bytes, bar + B_W2T);
                 }
                 __syncwarp();
@@ -486,14 +490,6 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     }
                 }
                 n_pass += np;
-                // the next round's target W1 tile can travel while AdamW runs (the G1 arena is free once the last pass has
-                // multiplied), unless a soft target update is about to rewrite it
-                w1_prefetched = false;
-                if (round + 1 < a.rounds && !soft_due(round + 1)) {
-                    umma::mbar_wait(bar + B_H2FREE + np - 1, round & 1);
-                    if (lane == 0) { mbar_expect_tx(bar + B_W1, w1_bytes); bulk_g2s(smem + R_W1, L.tiles + to.tW1, w1_bytes, bar + B_W1); }
-                    w1_prefetched = true;
-                }
             }
         } else if (warp == 11) {
             // ---- TILE BUILDER: the online network's operand tiles straight from the flat weights AdamW just wrote
@@ -534,10 +530,10 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         if (b == 0) umma::mbar_wait(bar + B_W1, 0);
                         issue_layer1(x, obs, b, s_col);
                     }
-                    for (int ac = 0; ac < d.A; ac++) {                   // all-actions products, accumulators alternate
+                    for (int ac = 0; ac < d.A; ac++) {                   // all-actions products (stacked: 2 issues per K step)
                         ready();
                         if (ac == 0) umma::mbar_wait(bar + B_W2T, 0);
-                        issue_hidden(x, R_W2T, s_col + 64 * (ac & 1));
+                        issue_hidden_stacked(x, R_W2T, s_col);
                     }
                     for (int b = 0; b < nb; b++) {                       // online layer 1
                         ready();
@@ -577,8 +573,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     int act = 0, cnt = 0;
     float rew = 0.f, term = 0.f;
     uint32_t ids0 = 0, ids1 = 0, ids2 = 0, ids3 = 0;
-    auto fetch_row = [&](int round) {
-        const int slot = L.slots[(size_t)round * a.B + c.g * 128 + c.m];
+    auto fetch_row = [&](int slot) {
         rec = L.records + (size_t)slot * W;
         act = (int)rec[a.lay.off_action];
         rew = __uint_as_float(rec[a.lay.off_reward]);
@@ -599,7 +594,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         issue_chunk(c, n0 + 1, mi.rowptr[warp], nch > 1 ? a.lay.off_next_state : a.lay.off_state, nch > 1 ? 1 : 0, obs);
     };
     if (active) {
-        fetch_row(0);
+        fetch_row(L.slots[c.g * 128 + c.m]);
         first_chunks(0);
     }
 
@@ -648,54 +643,71 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 if (c.elected) mbar_arrive(bar + B_W1FREE);
                 TC_STAMP(2);
                 float best = -INFINITY;
-                auto epilogue = [&](int ap) {     // accumulator (ap & 1): 64 columns at s_col + 64 (ap & 1)
-                    float qv = 0.f;
-#pragma unroll
-                    for (int half = 0; half < 2; half++) {
-                        float d1[32];
-                        umma::tmem_ld32(c.tlane + c.s_col + 64 * (ap & 1) + 32 * half, d1);
-#pragma unroll
-                        for (int c4 = 0; c4 < 8; c4++) {
-                            const float4 w3v = *reinterpret_cast<const float4 *>(&mi.t.w3[32 * half + 4 * c4]);
-                            const float4 b2v = *reinterpret_cast<const float4 *>(&mi.t.b2[32 * half + 4 * c4]);
-                            qv = fmaf(w3v.x, fmaxf(d1[4 * c4 + 0] + b2v.x, 0.f), qv);
-                            qv = fmaf(w3v.y, fmaxf(d1[4 * c4 + 1] + b2v.y, 0.f), qv);
-                            qv = fmaf(w3v.z, fmaxf(d1[4 * c4 + 2] + b2v.z, 0.f), qv);
-                            qv = fmaf(w3v.w, fmaxf(d1[4 * c4 + 3] + b2v.w, 0.f), qv);
-                        }
-                    }
-                    qv += mi.t.b3;
-                    if (ap >= cnt) qv = -INFINITY;   // next_state_action_values[mask] = -inf
-                    best = fmaxf(best, qv);
-                };
-                // Two accumulators per group: while the issuer multiplies action slot a, the row warps run the epilogue of
-                // slot a - 1; the A operand is rebuilt as soon as product a - 1 has read it.
-                for (int ac = 0; ac < d.A; ac++) {
+                float h[64];                      // the NEXT action slot's layer-1 activations, built while a product runs
+                auto build_h = [&](int ac) {
                     int id = ac;
                     if (dyn && ac < cnt) {
                         const uint32_t wsel = ac < 4 ? ids0 : ac < 8 ? ids1 : ac < 12 ? ids2 : ids3;
                         id = (int)((wsel >> (8 * (ac & 3))) & 0xffu);
                     }
-                    if (ac > 0) wait_group_mma(c);      // product ac - 1 is done: the A operand is free, its result is ready
 #pragma unroll
-                    for (int half = 0; half < 2; half++) {
-                        float h[32];
-#pragma unroll
-                        for (int c4 = 0; c4 < 8; c4++) {
-                            const float4 wv = *reinterpret_cast<const float4 *>(&mi.t.watb[id][32 * half + 4 * c4]);
-                            h[4 * c4 + 0] = fmaxf(t1[32 * half + 4 * c4 + 0] + wv.x, 0.f);
-                            h[4 * c4 + 1] = fmaxf(t1[32 * half + 4 * c4 + 1] + wv.y, 0.f);
-                            h[4 * c4 + 2] = fmaxf(t1[32 * half + 4 * c4 + 2] + wv.z, 0.f);
-                            h[4 * c4 + 3] = fmaxf(t1[32 * half + 4 * c4 + 3] + wv.w, 0.f);
-                        }
-                        put_a32(c, 32 * half, h);
+                    for (int c4 = 0; c4 < 16; c4++) {
+                        const float4 wv = *reinterpret_cast<const float4 *>(&mi.t.watb[id][4 * c4]);
+                        h[4 * c4 + 0] = fmaxf(t1[4 * c4 + 0] + wv.x, 0.f);
+                        h[4 * c4 + 1] = fmaxf(t1[4 * c4 + 1] + wv.y, 0.f);
+                        h[4 * c4 + 2] = fmaxf(t1[4 * c4 + 2] + wv.z, 0.f);
+                        h[4 * c4 + 3] = fmaxf(t1[4 * c4 + 3] + wv.w, 0.f);
                     }
+                };
+                auto finish = [&](const float *z, int ap) {     // z = layer-2 pre-activations of slot ap (accumulator halves summed)
+                    float qv = 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; c4++) {
+                        const float4 w3v = *reinterpret_cast<const float4 *>(&mi.t.w3[4 * c4]);
+                        const float4 b2v = *reinterpret_cast<const float4 *>(&mi.t.b2[4 * c4]);
+                        qv = fmaf(w3v.x, fmaxf(z[4 * c4 + 0] + b2v.x, 0.f), qv);
+                        qv = fmaf(w3v.y, fmaxf(z[4 * c4 + 1] + b2v.y, 0.f), qv);
+                        qv = fmaf(w3v.z, fmaxf(z[4 * c4 + 2] + b2v.z, 0.f), qv);
+                        qv = fmaf(w3v.w, fmaxf(z[4 * c4 + 3] + b2v.w, 0.f), qv);
+                    }
+                    qv += mi.t.b3;
+                    if (ap >= cnt) qv = -INFINITY;   // next_state_action_values[mask] = -inf
+                    best = fmaxf(best, qv);
+                };
+                auto read_acc = [&](float *z) {
+                    float d2[32];
+                    umma::tmem_ld32(c.tlane + c.s_col, z);
+                    umma::tmem_ld32(c.tlane + c.s_col + 64, d2);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) z[i] += d2[i];
+                    umma::tmem_ld32(c.tlane + c.s_col + 32, z + 32);
+                    umma::tmem_ld32(c.tlane + c.s_col + 96, d2);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) z[32 + i] += d2[i];
+                };
+                // Per slot the only serial work between two products is: operand registers -> TMEM, accumulator -> registers,
+                // publish.  The epilogue arithmetic of slot a - 1 and the operand of slot a + 1 are computed while product a runs.
+                build_h(0);
+                for (int ac = 0; ac < d.A; ac++) {
+                    if (ac == 2) TC_STAMP(13);
+                    if (ac > 0) wait_group_mma(c);      // product ac - 1 is done: its A operand is free, its result is ready
+                    if (ac == 2) TC_STAMP(14);
+                    put_a32(c, 0, h);
+                    put_a32(c, 32, h + 32);
+                    float z[64];
+                    if (ac > 0) read_acc(z);            // before product ac overwrites the accumulator
                     publish_a(c);
+                    if (ac == 2) TC_STAMP(15);
                     c.n_mma++;
-                    if (ac > 0) epilogue(ac - 1);       // overlaps product ac
+                    if (ac > 0) finish(z, ac - 1);
+                    if (ac + 1 < d.A) build_h(ac + 1);
                 }
                 wait_group_mma(c);
-                epilogue(d.A - 1);
+                {
+                    float z[64];
+                    read_acc(z);
+                    finish(z, d.A - 1);
+                }
                 if (c.elected) mbar_arrive(bar + B_ACTDONE);
                 yv = __fadd_rn(__fmul_rn(__fmul_rn(best, a.gamma), 1.f - term), rew);
             }
@@ -800,20 +812,25 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         }
         TC_STAMP(6);
 
+        // the next round's slot travels during the passes (its record fields are requested before AdamW)
+        int next_slot = 0;
+        if (active && round + 1 < a.rounds) next_slot = L.slots[(size_t)(round + 1) * a.B + c.g * 128 + c.m];
         // ================= weight gradients: pass p = the 32 batch rows of warp p =================
-        // Two warps per pass: the OWNER (warp p: the rows are its TMEM lanes and its registers hold dq, the ReLU mask and
-        // the action) builds the G2 operands [E ; H1 ; 0]^T and [dZ2 | dZ1]^T and issues G2; its PARTNER (warp p + 4 mod 8:
-        // same TMEM lane quarter) builds the G1 operands S^T (from the raw rows the loader fetched) and dZ1^T and issues G1.
-        // Each arena half is handed from pass to pass through one mbarrier per pass (tcgen05.commit arrives on it).
+        // The OWNER of pass p (warp p: the rows are its TMEM lanes and its registers hold dq, the ReLU mask and the action)
+        // builds [E ; H1 ; 0]^T and [dZ2 | dZ1]^T and issues G2.  The S^T tiles need no TMEM (the loader re-fetched the raw
+        // rows), so they are built by warp p + 6 mod 8 — on ANOTHER sub-partition than the owner (a TMEM lane quarter is
+        // tied to the sub-partition of its warps, so splitting the owner's own work would not add issue slots) — which then
+        // issues G1 = S^T dZ1 against the dZ1 rows of the owner's tile.  Arena hand-over between passes: one mbarrier per pass
+        // (tcgen05.commit arrives): the G2 arena needs the commits of G2(p) and G1(p), the S^T arena that of G1(p).
         {
             const int colbase = (lane >> 2) * (TL / 4) + (lane & 3);
+            float *dz_hi = reinterpret_cast<float *>(smem + H1_DZ_HI), *dz_lo = reinterpret_cast<float *>(smem + H1_DZ_LO);
             auto owner_half = [&](int p) {
                 float *eh_hi = reinterpret_cast<float *>(smem + H1_EHT_HI), *eh_lo = reinterpret_cast<float *>(smem + H1_EHT_LO);
-                float *dz_hi = reinterpret_cast<float *>(smem + H1_DZ_HI), *dz_lo = reinterpret_cast<float *>(smem + H1_DZ_LO);
                 float v[64];
                 umma::tmem_ld32(c.tlane + c.s_col, v);            // h1
                 umma::tmem_ld32(c.tlane + c.s_col + 32, v + 32);
-                if (p > 0) umma::mbar_wait(bar + B_H1FREE + p - 1, round & 1);      // the previous pass's G2 products are done
+                if (p > 0) umma::mbar_wait(bar + B_H1FREE + p - 1, round & 1);      // the previous pass's G2 and G1 are done
                 eh_hi[tt_off(0, colbase)] = 1.f;
 #pragma unroll
                 for (int e = 0; e < 16; e++) eh_hi[tt_off(1 + e, colbase)] = (e == act_now) ? 1.f : 0.f;
@@ -822,19 +839,22 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     eh_hi[tt_off(32 + j, colbase)] = v[j];
                     eh_lo[tt_off(32 + j, colbase)] = tf32_lo(v[j]);
                 }
-#pragma unroll
-                for (int j = 0; j < 64; j++) {
-                    const bool on = j < 32 ? ((mask2a >> j) & 1u) : ((mask2b >> (j - 32)) & 1u);
-                    const float x = on ? dq * mi.o.w3[j] : 0.f;   // dZ2 again (cheaper than parking it)
-                    dz_hi[tt_off(j, colbase)] = x;
-                    dz_lo[tt_off(j, colbase)] = tf32_lo(x);
-                }
                 umma::tmem_ld32(c.tlane + c.s_col + 64, v);       // dZ1
                 umma::tmem_ld32(c.tlane + c.s_col + 96, v + 32);
 #pragma unroll
                 for (int j = 0; j < 64; j++) {
                     dz_hi[tt_off(64 + j, colbase)] = v[j];
                     dz_lo[tt_off(64 + j, colbase)] = tf32_lo(v[j]);
+                }
+                umma::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar + B_DZREADY + p);  // the S^T builder may multiply against dZ1^T
+#pragma unroll
+                for (int j = 0; j < 64; j++) {
+                    const bool on = j < 32 ? ((mask2a >> j) & 1u) : ((mask2b >> (j - 32)) & 1u);
+                    const float x = on ? dq * mi.o.w3[j] : 0.f;   // dZ2 again (cheaper than parking it)
+                    dz_hi[tt_off(j, colbase)] = x;
+                    dz_lo[tt_off(j, colbase)] = tf32_lo(x);
                 }
                 umma::fence_async_smem();
                 umma::fence_before_thread_sync();
@@ -854,14 +874,9 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 }
                 __syncwarp();
             };
-            auto partner_half = [&](int p) {
+            auto st_half = [&](int p) {
                 float *st_hi = reinterpret_cast<float *>(smem + H2_ST_HI), *st_lo = reinterpret_cast<float *>(smem + H2_ST_LO);
-                float *dz1s = reinterpret_cast<float *>(smem + H2_DZ1);
                 const uint32_t n = n_pass + p;
-                const uint32_t s_owner = TM_S0 + 128 * (p >> 2);  // the owner group's parking columns, this warp's lane quarter
-                float v[64];
-                umma::tmem_ld32(c.tlane + s_owner + 64, v);       // dZ1 of the pass's rows
-                umma::tmem_ld32(c.tlane + s_owner + 96, v + 32);
                 if (p > 0) umma::mbar_wait(bar + B_H2FREE + p - 1, round & 1);   // first: orders this pass behind the fill it waits for next
                 umma::mbar_wait(bar + B_RFULL + (n & 1), (n >> 1) & 1);
                 const float *raw = reinterpret_cast<const float *>(smem + ((n & 1) ? R_W2T : R_W2)) + lane * RAWP;
@@ -874,31 +889,30 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar + B_RFREE + (n & 1));
-#pragma unroll
-                for (int j = 0; j < 64; j++) {
-                    dz1s[tt_off(j, colbase)] = v[j];
-                    dz1s[tt_off(64 + j, colbase)] = tf32_lo(v[j]);
-                }
                 umma::fence_async_smem();
                 umma::fence_before_thread_sync();
                 __syncwarp();
                 if (lane == 0) {
+                    umma::mbar_wait(bar + B_DZREADY + p, round & 1);             // the owner's dZ1^T rows are in place
                     umma::fence_after_thread_sync();
                     const umma::Tile SH{umma::smem_u32(st_hi), TL, TSBO}, SL{umma::smem_u32(st_lo), TL, TSBO};
-                    const umma::Tile D1{umma::smem_u32(dz1s), TL, TSBO};
-                    const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
+                    const umma::Tile D1H = umma::Tile{umma::smem_u32(dz_hi), TL, TSBO}.rows_from(64);
+                    const umma::Tile D1L = umma::Tile{umma::smem_u32(dz_lo), TL, TSBO}.rows_from(64);
+                    const uint32_t i64 = umma::make_idesc_tf32(128, 64);
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++) {
-                        umma::mma_tf32(c.tm + TM_G1, SH.desc(ks), D1.desc(ks), i128, p > 0 || ks > 0);   // S_hi x [dZ1_hi ; dZ1_lo]
-                        umma::mma_tf32(c.tm + TM_G1, SL.desc(ks), D1.desc(ks), i64, true);              // S_lo x dZ1_hi
+                        umma::mma_tf32(c.tm + TM_G1, SL.desc(ks), D1H.desc(ks), i64, p > 0 || ks > 0);
+                        umma::mma_tf32(c.tm + TM_G1, SH.desc(ks), D1L.desc(ks), i64, true);
+                        umma::mma_tf32(c.tm + TM_G1, SH.desc(ks), D1H.desc(ks), i64, true);
                     }
                     umma::mma_commit(bar + B_H2FREE + p);
+                    umma::mma_commit(bar + B_H1FREE + p);
                 }
                 __syncwarp();
             };
-            const int p_own = warp, p_par = (warp + 4) & 7;
-            if (p_par < p_own) { if (p_par < np) partner_half(p_par); if (p_own < np) owner_half(p_own); }
-            else               { if (p_own < np) owner_half(p_own); if (p_par < np) partner_half(p_par); }
+            const int p_own = warp, p_st = (warp + 2) & 7;
+            if (p_st < p_own) { if (p_st < np) st_half(p_st); if (p_own < np && active) owner_half(p_own); }
+            else              { if (p_own < np && active) owner_half(p_own); if (p_st < np) st_half(p_st); }
         }
         umma::mbar_wait(bar + B_H1FREE + np - 1, round & 1);
         umma::mbar_wait(bar + B_H2FREE + np - 1, round & 1);
@@ -908,82 +922,108 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
 
         // the next round's row and its first two chunks travel while AdamW runs (the staging buffers are free again)
         if (active && round + 1 < a.rounds) {
-            fetch_row(round + 1);
+            fetch_row(next_slot);
             first_chunks(round + 1);
         }
+        TC_STAMP(9);
 
-        // ================= AdamW straight from the TMEM accumulators =================
+        // ================= AdamW =================
+        // (1) TMEM accumulators -> the gradient in the flat (torch) parameter order in shared memory (the G1 arena is free):
+        //     lane = input index, so a warp's 32 values of one output row are 128 contiguous bytes (conflict-free).
+        // (2) all 256 row threads sweep the flat vectors with 16-byte accesses, two float4 groups in flight per thread.
         {
             const float2 sc = L.scal[round];
             AdamScalarsTc hs;
             hs.decay = a.decay; hs.omb1 = a.omb1; hs.beta2 = a.beta2; hs.omb2 = a.omb2; hs.eps = a.eps;
             hs.step_size = sc.x; hs.bc2_sqrt = sc.y; hs.inv_bc2_sqrt = 1.0f / sc.y;
+            float *gsm = reinterpret_cast<float *>(smem + R_W1);
             const int gs = c.g, j0 = 32 * gs;
-            {   // G1[lane k][col j] = dW1[j][k]: this thread owns input k, columns j0 .. j0 + 31 (coalesced over k)
-                float g1[32], g2[32];
+            {   // G1[lane k][col j] = dW1[j][k]
+                float g1[32];
                 umma::tmem_ld32(c.tlane + TM_G1 + j0, g1);
-                umma::tmem_ld32(c.tlane + TM_G1 + 64 + j0, g2);
                 const int k = 32 * c.q + lane;
+                if (k < obs)
 #pragma unroll
-                for (int jj = 0; jj < 32; jj += 4) {
-                    int idx[4];
-                    float gg[4], wn[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        idx[u] = k < obs ? d.oW1 + (j0 + jj + u) * d.D + k : -1;
-                        gg[u] = g1[jj + u] + g2[jj + u];
-                    }
-                    adam_n<4>(L, idx, gg, wn, hs);
-                }
+                    for (int jj = 0; jj < 32; jj++) gsm[d.oW1 + (j0 + jj) * d.D + k] = g1[jj];
             }
             if (c.q == 1 || c.q == 2) {   // G2 lanes 32 + k2: dW2[j][k2] in the dZ2 columns
                 float g2[32];
                 umma::tmem_ld32(c.tlane + TM_G2 + j0, g2);
                 const int k2 = 32 * (c.q - 1) + lane;
 #pragma unroll
-                for (int jj = 0; jj < 32; jj += 4) {
-                    int idx[4];
-                    float gg[4], wn[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) { idx[u] = d.oW2 + (j0 + jj + u) * HID + k2; gg[u] = g2[jj + u]; }
-                    adam_n<4>(L, idx, gg, wn, hs);
-                }
+                for (int jj = 0; jj < 32; jj++) gsm[d.oW2 + (j0 + jj) * HID + k2] = g2[jj];
             } else if (c.q == 0) {        // G2 lane 0: db2 (dZ2 columns), db1 (dZ1 columns); lanes 1..A: dW1[:, obs + a]
                 float gz2[32], gz1[32];
                 umma::tmem_ld32(c.tlane + TM_G2 + j0, gz2);
                 umma::tmem_ld32(c.tlane + TM_G2 + 64 + j0, gz1);
+                if (lane == 0) {
 #pragma unroll
-                for (int jj = 0; jj < 32; jj += 4) {
-                    int idx[8];
-                    float gg[8], wn[8];
+                    for (int jj = 0; jj < 32; jj++) { gsm[d.ob1 + j0 + jj] = gz1[jj]; gsm[d.ob2 + j0 + jj] = gz2[jj]; }
+                } else if (lane <= d.A) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int j = j0 + jj + u;
-                        idx[u] = lane == 0 ? d.ob1 + j : (lane <= d.A ? d.oW1 + j * d.D + obs + lane - 1 : -1);
-                        gg[u] = gz1[jj + u];
-                        idx[4 + u] = lane == 0 ? d.ob2 + j : -1;
-                        gg[4 + u] = gz2[jj + u];
-                    }
-                    adam_n<8>(L, idx, gg, wn, hs);
+                    for (int jj = 0; jj < 32; jj++) gsm[d.oW1 + (j0 + jj) * d.D + obs + lane - 1] = gz1[jj];
                 }
             } else {                      // W3 and b3 from the shuffle reductions of phase O, fixed summation order
                 const int j = j0 + lane;
                 float gsum = 0.f;
 #pragma unroll
                 for (int w8 = 0; w8 < 8; w8++) gsum += mi.redw[w8][j];
-                int idx[2] = {d.oW3 + j, -1};
-                float gg[2] = {gsum, 0.f}, wn[2];
+                gsm[d.oW3 + j] = gsum;
                 if (gs == 1 && lane == 0) {
                     float ds = 0.f, ms = 0.f;
 #pragma unroll
                     for (int w8 = 0; w8 < 8; w8++) { ds += mi.reddb3[w8]; ms += mi.redmae[w8]; }
-                    idx[1] = d.ob3; gg[1] = ds;
+                    gsm[d.ob3] = ds;
                     L.out_mae[round] = ms / (float)a.B;   // reported "loss": mean |q - y|
                 }
-                adam_n<2>(L, idx, gg, wn, hs);
+            }
+            TC_STAMP(10);
+            umma::fence_before_thread_sync();
+            rows_sync();
+            TC_STAMP(11);
+            const int P = d.P;
+            if ((reinterpret_cast<uintptr_t>(L.w) | reinterpret_cast<uintptr_t>(L.m) | reinterpret_cast<uintptr_t>(L.v) |
+                 reinterpret_cast<uintptr_t>(L.vmax)) & 15) {
+                for (int i = tid; i < P; i += NROW) {      // unaligned vectors: scalar sweep
+                    float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
+                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gsm[i], hs);
+                    L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
+                }
+            } else {
+                const int P4 = P >> 2;
+                for (int q0 = tid; q0 < P4; q0 += 2 * NROW) {
+                    float4 w4[2], m4[2], v4[2], x4[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int qq = q0 + u * NROW;
+                        if (qq < P4) {
+                            w4[u] = __ldcg(reinterpret_cast<const float4 *>(L.w) + qq); m4[u] = __ldcg(reinterpret_cast<const float4 *>(L.m) + qq);
+                            v4[u] = __ldcg(reinterpret_cast<const float4 *>(L.v) + qq); x4[u] = __ldcg(reinterpret_cast<const float4 *>(L.vmax) + qq);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int qq = q0 + u * NROW;
+                        if (qq < P4) {
+                            const float4 g4 = *reinterpret_cast<const float4 *>(gsm + 4 * qq);
+                            w4[u].x = adam_math(w4[u].x, m4[u].x, v4[u].x, x4[u].x, g4.x, hs);
+                            w4[u].y = adam_math(w4[u].y, m4[u].y, v4[u].y, x4[u].y, g4.y, hs);
+                            w4[u].z = adam_math(w4[u].z, m4[u].z, v4[u].z, x4[u].z, g4.z, hs);
+                            w4[u].w = adam_math(w4[u].w, m4[u].w, v4[u].w, x4[u].w, g4.w, hs);
+                            reinterpret_cast<float4 *>(L.w)[qq] = w4[u]; reinterpret_cast<float4 *>(L.m)[qq] = m4[u];
+                            reinterpret_cast<float4 *>(L.v)[qq] = v4[u]; reinterpret_cast<float4 *>(L.vmax)[qq] = x4[u];
+                        }
+                    }
+                }
+                for (int i = 4 * P4 + tid; i < P; i += NROW) {
+                    float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
+                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gsm[i], hs);
+                    L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
+                }
             }
             umma::fence_before_thread_sync();
             rows_sync();
+            TC_STAMP(12);
             load_smalls(L.w, d, mi.o, tid);
         }
         TC_STAMP(8);

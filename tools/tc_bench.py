@@ -43,3 +43,6 @@ tot = (s[1:, 0] - s[:-1, 0]).mean()
 print(f"{tot:.0f} clk/round (CTA 0, group 0)")
 for i, n in enumerate(names):
     print(f"  {n:28s} {(s[:, i+1]-s[:, i]).mean():10.0f} clk")
+d = lambda a, b: (s[:, a] - s[:, b]).mean()
+print(f"  AdamW region: next row + chunks {d(9,7):.0f} | G1 part {d(10,9):.0f} | G2 / W3 part {d(11,10):.0f} | rows_sync {d(12,11):.0f} | smalls {d(8,12):.0f}")
+print(f"  action slot 2: epilogue(0)+loop {d(13,2):.0f} since phase start | wait MMA {d(14,13):.0f} | build + publish {d(15,14):.0f}")
