@@ -1,44 +1,33 @@
 // dqn_tc.cu — tensor-core DQN learner: ONE SM (one CTA) runs one complete learner, every dense
 // contraction of the step on tcgen05 (3xTF32 UMMA, fp32 accumulators in TMEM), so that a launch
 // with L CTAs trains L independent learners (seeds / agents) concurrently — the aggregate mode that
-// fills a B200.
+// fills a B200 — and a single learner needs one SM instead of 65.
 //
 // Same semantics as the cooperative SIMT kernel in dqn.cu (DeepQLearning.learn: sample -> Q(s,a) ->
 // max_a' Q_target(s',a') -> MSE -> backward -> AdamW(amsgrad) -> scheduled soft target update; reference
-// call sites in include/pearl_b200.h).  Shape class: two hidden layers of 64, obs % 8 == 0, obs <= 128,
-// n_actions <= 16, batch in {128, 256}; everything else stays on the SIMT kernel.
+// call sites in include/pearl_b200.h).  Supported shape class: two hidden layers of 64, obs % 8 == 0,
+// obs <= 128, n_actions in {1,2,4,8,16}, batch in {128, 256}; everything else stays on the SIMT kernel.
 //
-// Warp-specialised CTA of 9 warps:
-//   warps 0-3 / 4-7  two ROW GROUPS: group g owns batch rows [128 g, 128 g + 128) for the whole step; thread
-//                    (g, m) is batch row m of that tile = TMEM lane m.  The groups are independent pipelines
-//                    (own A operand + own accumulator in tensor memory, own mbarriers) that meet only at the
-//                    weight-gradient phase, so the tensor pipe always has the other group's products to run
-//                    while one group is in SIMT code.  The elected lane of a group issues that group's MMAs.
-//   warp 8           LOADER: TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the weight tiles and of
-//                    the raw state rows of the weight-gradient passes.
-// Data movement is TMA throughout: every sampled record row reaches shared memory as 128-byte bulk copies
-// issued by the lane that owns the row into a warp-private double buffer (issued one phase ahead, the next
-// round's first chunks during AdamW), and the weights are kept in global memory a second time IN THE UMMA
-// OPERAND LAYOUT (hi = the fp32 value, lo = x - trunc_tf32(x), stacked [hi ; lo] along N), written by AdamW /
-// the soft target update, so staging a network is three bulk copies instead of a SIMT pass.
+// Per gradient step (256 threads, thread (m = tid % 128, h = tid / 128) owns batch row m of the
+// current 128-row tile = TMEM lane m, and column half h):
+//   phase T  target net: T1 = S' W1s^T per row tile (K chunks of 64 staged through smem); then one
+//            128 x 64 x 64 product per (row tile, action slot): A tile row m = relu(T1[m] + W1a[:,a] + b1)
+//            built from registers, two thread groups ping-pong (own A buffer + own accumulator) so the
+//            tensor pipe always has the other group's tile; running max over action slots in registers.
+//   phase O  online net forward (same tiles), loss gradient, dZ2, dH1 = dZ2 W2 (B operand = W2^T tile),
+//            and the weight gradients as tensor-core products over the batch dimension:
+//            dW2 = dZ2^T H1, dW1s = dZ1^T S, and [db | dW1a] = dZ^T E with E = [1 | onehot(action)];
+//            their operands are explicitly transposed tiles written with a 144-byte chunk pitch
+//            (bank-conflict-free column scatter).  Accumulators for all of these live in TMEM.
+//   AdamW    gradients read straight from TMEM (M = 64 lane map), parameters / moments in L2.
 //
-// Per gradient step:
-//   phase T  T1 = S' W1s_t^T (rows -> TMEM, TS products); then for every action slot one 128 x 64 x 64 product
-//            whose A row m is relu(T1[m] + W1_t[:, obs + a] + b1) built in registers.  B is the STACKED tile
-//            [W_hi ; W_lo] (N = 128): A_hi x [W_hi ; W_lo] is one N = 128 instruction (the N = 64 form is
-//            issue-bound at 53 clk against a 32-clk pipe floor, N = 128 runs at the floor), A_lo x W_hi one
-//            N = 64 instruction: 2 instead of 3 issues per K step; the epilogue adds the two accumulator halves.
-//   phase O  online forward on the group's tile, MSE gradient, dZ2, dH1 = dZ2 W2 (B = stacked W2^T);
-//            h1 and dZ1 are parked in the group's TMEM columns.
-//   grads    contractions over the batch as M = 128 products on TRANSPOSED tiles (144-byte chunk pitch =
-//            bank-conflict-free column scatter), 32 batch rows (one warp) per pass:
-//              G1 = S^T dZ1                        -> dW1[:, :obs]^T
-//              G2 = [E ; H1 ; 0]^T [dZ2 | dZ1]     -> dW2^T, db2, db1, dW1[:, obs:]^T   (E = [1 | onehot(action)])
-//            The pass's warp builds the tiles from its own TMEM lanes and issues the products itself; two
-//            arena halves (G2 operands / G1 operands) are chained through mbarriers so that pass p + 1 is
-//            being built while pass p multiplies.
-//   AdamW    straight from the TMEM accumulators (lane = input index: coalesced L2 accesses), new weights
-//            written to the flat vector AND to the operand-layout tiles.
+// Round 2: the weights are kept in global memory a second time IN THE UMMA OPERAND LAYOUT (hi tile = the fp32 values —
+// the tensor core truncates them to TF32 — and lo tile = x - trunc_tf32(x)), written by AdamW / the soft target update
+// next to the flat torch-order vectors, so staging a network's B operands is three TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx) issued by one thread instead of a SIMT split-and-scatter pass of all 256
+// threads (18.5 k of 172 k clk per round in round 1); the online W1 tiles travel while the all-actions products run.
+// A warp-specialised rewrite of this kernel (row groups + issuer / loader / tile-builder warps) was built and measured
+// in round 2 as well — bit-correct but slower; see profiles/r2_k_dqn_tc_summary.md.
 #include <math.h>
 #include <stdarg.h>
 
@@ -54,39 +43,26 @@ int prl_sampler_params(const prl_buf *b, int k, prl::SamplerParams *sp, size_t *
 
 namespace {
 
-constexpr int NROW = 256;            // row threads: 2 groups x 4 warps
-constexpr int NTH = 384;             // 8 row warps + one helper warpgroup: loader, two MMA issuers, tile builder
+constexpr int NTH = 256;
 constexpr int HID = 64;
-// ---- shared memory map (bytes)
-constexpr int R_W1 = 0;              // 64 KB: stacked W1[:, :obs] tile [128][obs] (target, then online); grads: G1 operands
-constexpr int R_W2 = 65536;          // 32 KB: stacked online W2 [128][64];                          grads: raw rows, buffer 0
-constexpr int STAGE = 98304;         // 72 KB: 8 warps x 2 x [32 rows][36 floats] row chunks;       grads: G2 operands
-constexpr int R_W2T = 172032;        // 32 KB: stacked target W2 (phase T) / online W2^T (phase O); grads: raw rows, buffer 1
-constexpr int MISC_OFF = 204800;
-constexpr int SROW = 36;             // floats per staged row chunk (32 + 4: conflict-free 128-bit reads)
-constexpr int SBUF = 32 * SROW * 4;  // 4608 B per (warp, buffer)
-// transposed tiles of the weight-gradient passes: 128 (M or N) x 32 batch rows, chunk pitch 144 B
-constexpr int TL = 144, TSBO = 8 * TL, TTILE = 16 * TSBO;   // 18432 B
-constexpr int H1_EHT_HI = STAGE, H1_EHT_LO = STAGE + TTILE, H1_DZ_HI = STAGE + 2 * TTILE, H1_DZ_LO = STAGE + 3 * TTILE;
-constexpr int H2_ST_HI = R_W1, H2_ST_LO = R_W1 + TTILE;
-constexpr int RAWP = 132;            // floats per raw row (128 + 4)
-// ---- tensor memory columns
-constexpr int TM_A0 = 0, TM_S0 = 256;          // group g: A operand at 128 g (hi 64 | lo 64), accumulators / parking at 256 + 128 g
-constexpr int TM_G1 = 0, TM_G2 = 128;          // weight-gradient accumulators (the A regions are free by then)
-
-// mbarrier indices
-enum {
-    B_W1 = 0, B_W2, B_W2T, B_MMA /*2*/ = 3, B_W1FREE = 5, B_ACTDONE, B_RFULL /*2*/ = 7, B_RFREE /*2*/ = 9,
-    // one barrier PER PASS for the two arena chains: a parity wait only tells adjacent phases apart, and pass p + 2 may
-    // reach its wait before pass p has even committed
-    B_H1FREE /*8*/ = 11, B_H2FREE /*8*/ = 19, B_READY /*2*/ = 27, B_DZREADY /*8*/ = 29, B_COUNT = 37
-};
+constexpr int MAX_B = 256;
+// shared memory regions (bytes)
+constexpr int REG1 = 0, REG2 = 65536, REG3 = 131072, MISC_OFF = 196608;
+constexpr int HALF = 32768;          // hi tile at region base, lo tile at base + HALF
+// transposed-tile arena (regions 1+2) for the weight-gradient products, 64 batch rows per pass
+constexpr int TL = 144;              // chunk pitch of transposed tiles
+constexpr int AR_A_HI = 0, AR_A_LO = 18432, AR_B_HI = 36864, AR_B_LO = 73728, AR_E = 110592;
+// TMEM columns
+constexpr int TM_T1 = 0, TM_ACC0 = 128, TM_ACC1 = 192, TM_DW2 = 256, TM_DW1 = 320, TM_DE2 = 448, TM_DE1 = 480;
+// A operands held in tensor memory (TS products) while the weight-gradient accumulators are not live:
+// group g: hi at TM_A + 128 g, lo 64 columns further
+constexpr int TM_A = 256;
 
 struct TcLearner {            // one per CTA, in global memory
     const uint32_t *records;
+    float *tiles;             // operand-layout weight tiles: online net, then target net (net_tile_floats each)
     const int32_t *slots;     // [rounds][B]
     float *w, *wt, *m, *v, *vmax;
-    float *tiles;             // operand-layout copies: online [W1s | W2 | W2^T], target [W1s | W2]
     const float2 *scal;       // [rounds]
     float *out_mae, *out_q, *out_y;
     long long steps0;
@@ -109,24 +85,36 @@ struct TcArgs {
         if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[(size_t)round * 16 + (idx)] = clock64(); \
     } while (0)
 
-struct Smalls {              // the small fp32 vectors of one network
-    float watb[16][68];      // W1[:, obs + a] + b1, row pitch 68: rows of different action ids fall in different banks
-    float b2[HID], w3[HID];
-    float b3, pad[3];
-};
 struct Misc {
-    Smalls t, o;
-    float redw[8][HID];
+    float watb[16][HID];     // W1[:, obs + a] + b1 of the network being evaluated
+    float b2[HID], w3[HID];
+    float b3, pad0[3];
+    float y[MAX_B];
+    float vpart[128][2];
+    float vmax2[2][128];
+    int act[MAX_B], cnt[MAX_B], slot[MAX_B];
+    float rew[MAX_B], term[MAX_B];
+    float redw[8][32];
     float redmae[8], reddb3[8];
-    unsigned long long rowptr[8][32];   // this round's record row of every row thread (the warp's lanes copy each other's rows)
-    unsigned long long bar[B_COUNT + 1];
+    unsigned long long bar[10];   // 1,2: per-group MMA; 3,4,5: phase-O products; 6: target tiles; 7: online W1 tiles; 8: online W2 tiles
     uint32_t tmem_base;
 };
 
-// ------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+__device__ __forceinline__ void cp_async16_zfill_tc(void *smem_dst, const void *gmem_src, int src_bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory"); }
+
+__device__ __forceinline__ void st_split4(float *hi_base, float *lo_base, int idx, float4 v) {
+    float4 h, l;
+    umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+    umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<float4 *>(hi_base + idx) = h;
+    *reinterpret_cast<float4 *>(lo_base + idx) = l;
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -137,11 +125,49 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory"); }
-__device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
-__device__ __forceinline__ void cta_sync() { __syncthreads(); }
-
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Operand-layout copies of one network's matrices in global memory (floats):
+//   [W1 hi: 64 x obs][W1 lo][W2 hi: 64 x 64][W2 lo][W2^T hi][W2^T lo]      (the shared-memory images, tile by tile)
+struct NetTiles { float *w1hi, *w1lo, *w2; };   // w2: the 4 x 4096-float block W2 hi | W2 lo | W2^T hi | W2^T lo
+__host__ __device__ inline int net_tile_floats(int obs) { return 128 * obs + 4 * HID * HID; }
+__device__ __forceinline__ NetTiles net_tiles(float *base, int obs) { return NetTiles{base, base + 64 * obs, base + 128 * obs}; }
+// all tiles of one network from its flat parameter vector (kernel prologue, soft target update)
+__device__ void rebuild_tiles(const float *__restrict__ net, const Dims &d, const NetTiles &t, int tid) {
+    for (int e = tid; e < HID * d.obs; e += NTH) {
+        const int j = e / d.obs, k = e - j * d.obs;
+        const float x = __ldcg(net + d.oW1 + (size_t)j * d.D + k);
+        const int idx = umma::tile_index(j, k, d.obs);
+        t.w1hi[idx] = x; t.w1lo[idx] = tf32_lo(x);
+    }
+    for (int e = tid; e < HID * HID; e += NTH) {
+        const int j = e >> 6, k = e & 63;
+        const float x = __ldcg(net + d.oW2 + e), lo = tf32_lo(x);
+        const int i1 = umma::tile_index(j, k, HID), i2 = umma::tile_index(k, j, HID);
+        t.w2[i1] = x; t.w2[4096 + i1] = lo; t.w2[8192 + i2] = x; t.w2[12288 + i2] = lo;
+    }
+}
+// the small fp32 vectors of a network (action columns + b1, b2, w3, b3); all loads of a thread issued before the first use
+__device__ void load_smalls(const float *__restrict__ net, const Dims &d, Misc &mi) {
+    const int tid = threadIdx.x;
+    float wa[4], bb[4];                                           // A * 64 <= 1024 elements: <= 4 per thread
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int e = tid + u * NTH;
+        if (e < d.A * HID) {
+            const int j = e / d.A, a = e - j * d.A;
+            wa[u] = __ldcg(net + d.oW1 + (size_t)j * d.D + d.obs + a);
+            bb[u] = __ldcg(net + d.ob1 + j);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int e = tid + u * NTH;
+        if (e < d.A * HID) { const int j = e / d.A, a = e - j * d.A; mi.watb[a][j] = wa[u] + bb[u]; }
+    }
+    if (tid < HID) { mi.b2[tid] = __ldcg(net + d.ob2 + tid); mi.w3[tid] = __ldcg(net + d.oW3 + tid); }
+    if (tid == 0) mi.b3 = __ldcg(net + d.ob3);
+}
 
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
@@ -149,6 +175,10 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 struct AdamScalarsTc : AdamScalars { float inv_bc2_sqrt; };
+
+// AdamW on parameters [i0, i0 + valid) with gradients g[OFF .. OFF + COUNT): COUNT is a compile-time
+// multiple of 16 so that g stays in registers; `valid` <= COUNT masks the tail.  Per 16-parameter batch:
+// all loads first (one L2 round trip), then arithmetic, then stores.
 __device__ __forceinline__ float adam_math(float w, float &m, float &v, float &x, float g, const AdamScalarsTc &hs) {
     float p = __fmul_rn(w, hs.decay);
     m = fmaf(hs.omb1, g - m, m);
@@ -158,6 +188,71 @@ __device__ __forceinline__ float adam_math(float w, float &m, float &v, float &x
     // software sequences; well inside the 1e-4 parity budget
     const float denom = __fadd_rn(__fmul_rn(fast_sqrt(x), hs.inv_bc2_sqrt), hs.eps);
     return __fadd_rn(p, __fdividef(__fmul_rn(-hs.step_size, m), denom));
+}
+// T1[tile] = X[tile rows] W1s^T, X = state (online) or next_state (target).  The two 128-thread groups
+// take alternate row tiles; each thread streams its own row from global memory, splits it and writes it
+// straight into tensor memory (TS product: no shared-memory staging of A), 64 columns of K per pass.
+__device__ void layer1_all_tiles(const TcArgs &a, const TcLearner &L, Misc &mi, char *smem, int field_off, uint32_t tm,
+                                 uint32_t tlane, uint32_t &parg, int round = 0, bool stamp = false) {
+    const int m = threadIdx.x & 127, g = threadIdx.x >> 7;
+    const int ntiles = a.B >> 7;
+    const umma::Tile B_hi = umma::make_tile(smem + REG1, a.d.obs, 128), B_lo = umma::make_tile(smem + REG1 + HALF, a.d.obs, 128);
+    const uint32_t a_hi = TM_A + 128 * g, a_lo = a_hi + 64;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
+    // staging buffer of this group in region 2: [128 rows][64 floats], 16-byte chunk c of row r stored at
+    // chunk position c ^ (r & 7): rows arrive by coalesced 16-byte cp.async (16 lanes per row), and the
+    // row-owning thread reads its row back with conflict-free 128-bit loads.
+    float *sbuf = reinterpret_cast<float *>(smem + REG2 + g * 32768);
+    for (int t = g; t < ntiles; t += 2) {
+        for (int kc = 0; kc * 64 < a.d.obs; kc++) {
+            if (stamp && kc == 1) TC_STAMP(10);
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int item = i * 128 + m, rr = item >> 4, c = item & 15, k = kc * 64 + c * 4;
+                const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[t * 128 + rr] * a.lay.record_words) +
+                                   field_off + k;
+                const int nb = k < a.d.obs ? 16 : 0;
+                cp_async16_zfill_tc(sbuf + rr * 64 + ((c ^ (rr & 7)) << 2), nb ? src : reinterpret_cast<const float *>(L.records), nb);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            group_sync(g);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                float hi[32], lo[32];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int c = half * 8 + i;
+                    const float4 v = *reinterpret_cast<const float4 *>(sbuf + m * 64 + ((c ^ (m & 7)) << 2));
+                    umma::split_tf32(v.x, hi[4 * i + 0], lo[4 * i + 0]); umma::split_tf32(v.y, hi[4 * i + 1], lo[4 * i + 1]);
+                    umma::split_tf32(v.z, hi[4 * i + 2], lo[4 * i + 2]); umma::split_tf32(v.w, hi[4 * i + 3], lo[4 * i + 3]);
+                }
+                umma::tmem_st32(tlane + a_hi + half * 32, hi);
+                umma::tmem_st32(tlane + a_lo + half * 32, lo);
+            }
+            umma::tmem_st_wait();
+            if (stamp && kc == 1) TC_STAMP(11);
+            umma::fence_before_thread_sync();
+            group_sync(g);
+            if (stamp && kc == 1) TC_STAMP(12);
+            if (m == 0) {
+                umma::fence_after_thread_sync();
+                const int keff = min(64, a.d.obs - kc * 64);
+                umma::gemm3_ts(tm + TM_T1 + t * 64, tm + a_hi, tm + a_lo, B_hi.shifted(kc * 2048), B_lo.shifted(kc * 2048), 128, HID,
+                               keff, kc > 0);
+                umma::mma_commit(&bar[1 + g]);
+            }
+            if (stamp && kc == 1) TC_STAMP(13);
+            umma::mbar_wait(&bar[1 + g], parg);
+            parg ^= 1;
+            umma::fence_after_thread_sync();
+            if (stamp && kc == 1) TC_STAMP(14);
+        }
+    }
+    if (stamp) TC_STAMP(15);
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
 }
 
 // v[c] = this lane's (row's) value of column c; returns, in lane c, the sum of column c over the warp's
@@ -175,237 +270,12 @@ __device__ __forceinline__ float warp_colsum32(float *v, int lane) {
     }
     return v[0];
 }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-
-// ------------------------------------------------------------------------------------------ operand-layout weight tiles
-// float offsets inside TcLearner::tiles
-struct TileOff { int oW1, oW2, oW2T, tW1, tW2, total; };
-__host__ __device__ inline TileOff tile_offsets(int obs) {
-    TileOff t;
-    t.oW1 = 0; t.oW2 = 128 * obs; t.oW2T = t.oW2 + 128 * HID; t.tW1 = t.oW2T + 128 * HID; t.tW2 = t.tW1 + 128 * obs;
-    t.total = t.tW2 + 128 * HID;
-    return t;
-}
-// stacked tile: rows [0, 64) hold the value (the tensor core truncates it to TF32), rows [64, 128) the residual
-__device__ __forceinline__ void put_stacked(float *tile, int r, int k, int K, float x) {
-    tile[umma::tile_index(r, k, K)] = x;
-    tile[umma::tile_index(64 + r, k, K)] = tf32_lo(x);
-}
-// all tiles of one network from its flat parameter vector (kernel prologue, soft target update)
-__device__ void rebuild_tiles(const float *__restrict__ net, const Dims &d, float *tW1, float *tW2, float *tW2T, int tid) {
-    for (int e = tid; e < HID * d.obs; e += NROW) {
-        const int j = e / d.obs, k = e - j * d.obs;
-        put_stacked(tW1, j, k, d.obs, __ldcg(net + d.oW1 + (size_t)j * d.D + k));
-    }
-    for (int e = tid; e < HID * HID; e += NROW) {
-        const int j = e >> 6, k = e & 63;
-        const float x = __ldcg(net + d.oW2 + e);
-        put_stacked(tW2, j, k, HID, x);
-        if (tW2T) put_stacked(tW2T, k, j, HID, x);
-    }
-}
-__device__ void load_smalls(const float *__restrict__ net, const Dims &d, Smalls &s, int tid) {
-    for (int e = tid; e < d.A * HID; e += NROW) {
-        const int j = e / d.A, ac = e - j * d.A;
-        s.watb[ac][j] = __ldcg(net + d.oW1 + (size_t)j * d.D + d.obs + ac) + __ldcg(net + d.ob1 + j);
-    }
-    if (tid < HID) { s.b2[tid] = __ldcg(net + d.ob2 + tid); s.w3[tid] = __ldcg(net + d.oW3 + tid); }
-    if (tid == 0) s.b3 = __ldcg(net + d.ob3);
-}
-
-// ------------------------------------------------------------------------------------------ per-thread pipeline state
-struct RowCtx {
-    int g, q, lane, warp, m;       // group, warp within the group (TMEM lane quarter), lane, warp id, row within the tile
-    uint32_t tm, tlane;            // TMEM base, this warp's lane window
-    uint32_t a_col, s_col;         // the group's A-operand and accumulator columns
-    uint32_t n_chunk;              // staged row chunks consumed so far by this warp (running, all phases and rounds)
-    uint32_t n_issued;             // staged row chunks requested so far
-    uint32_t n_mma;                // MMA batches committed so far on the group's barrier
-    bool elected;                  // issues the group's MMAs
-    float *sbuf;                   // this warp's two staging buffers
-    uint64_t *bar;
-    char *smem;
-};
-
-// Chunk `cc` (32 columns) of the field at `field_off` of this warp's 32 rows -> buffer (n & 1): 16-byte cp.async, 8 lanes
-// per row (one full 128-byte line), 4 rows per instruction; one cp.async group per chunk.  (Per-row TMA bulk copies were
-// measured first: ~2300 128-byte operations per round serialise in the SM's TMA unit and tripled the round time; TMA is
-// kept for what it is good at here, the 16 - 64 KB weight tiles.)
-__device__ __forceinline__ void issue_chunk(RowCtx &c, uint32_t n, const unsigned long long *rowptr, int field_off, int cc, int obs) {
-    const int kc = min(32, obs - 32 * cc);
-    float *dst = c.sbuf + (n & 1) * (SBUF / 4);
-    const int c16 = c.lane & 7, rsub = c.lane >> 3;
-    if (4 * c16 < kc) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int row = 4 * i + rsub;
-            cp_async16(dst + row * SROW + 4 * c16, reinterpret_cast<const float *>(rowptr[row]) + field_off + 32 * cc + 4 * c16);
-        }
-    }
-    cp_async_commit();
-    c.n_issued = n + 1;
-}
-// chunk n of this warp has landed (at most one younger chunk may still be in flight)
-__device__ __forceinline__ void wait_chunk(const RowCtx &c, uint32_t n) {
-    if (c.n_issued > n + 1) cp_async_wait<1>(); else cp_async_wait<0>();
-    __syncwarp();
-}
-
-// hand the A operand (or any TMEM state) of this warp's rows to the group's issuer: 4 warp arrivals complete a phase
-__device__ __forceinline__ void publish_a(const RowCtx &c) {
-    umma::tmem_st_wait();
-    umma::fence_before_thread_sync();
-    __syncwarp();
-    if (c.lane == 0) mbar_arrive(c.bar + B_READY + c.g);
-}
-__device__ __forceinline__ void wait_group_mma(RowCtx &c) {
-    umma::mbar_wait(c.bar + B_MMA + c.g, (c.n_mma - 1) & 1);
-    umma::fence_after_thread_sync();
-}
-
-// Layer 1 of the group's tile: acc[128 rows x 128 stacked columns] = X W1s^T, X = the staged field of the sampled rows.
-// Chunks of 32 columns arrive by TMA in the warp's private double buffer; the row thread splits its chunk and
-// writes it to tensor memory (TS product: A never exists in shared memory in operand layout).  Two chunks (K = 64)
-// per MMA batch.  `request_ahead(n)`: issue the copies of the warp's chunk number n (two ahead of the one just read).
-template <typename NextFn>
-__device__ __forceinline__ void layer1(RowCtx &c, int obs, NextFn request_ahead) {
-    const int nch = (obs + 31) >> 5;
-    bool pending = false;
-    for (int cc = 0; cc < nch; cc++) {
-        const uint32_t n = c.n_chunk++;
-        const int kc = min(32, obs - 32 * cc);
-        wait_chunk(c, n);
-        const float *row = c.sbuf + (n & 1) * (SBUF / 4) + c.lane * SROW;
-        float hi[32];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * i < kc) v = *reinterpret_cast<const float4 *>(row + 4 * i);
-            hi[4 * i + 0] = v.x; hi[4 * i + 1] = v.y; hi[4 * i + 2] = v.z; hi[4 * i + 3] = v.w;
-        }
-        __syncwarp();
-        request_ahead(n + 2);                       // this buffer is free again
-        if (pending && (cc & 1) == 0) {             // the previous batch still reads the A operand
-            wait_group_mma(c);
-            pending = false;
-        }
-        {
-            float lo[32];
-#pragma unroll
-            for (int i = 0; i < 32; i++) lo[i] = tf32_lo(hi[i]);
-            umma::tmem_st32(c.tlane + c.a_col + 32 * (cc & 1), hi);
-            umma::tmem_st32(c.tlane + c.a_col + 64 + 32 * (cc & 1), lo);
-        }
-        if ((cc & 1) || cc == nch - 1) {
-            publish_a(c);                           // the group's issuer multiplies this K batch (stacked W1 tile)
-            c.n_mma++;
-            pending = true;
-        }
-    }
-    wait_group_mma(c);
-}
-
-// ---- issuer side (one lane of a helper warp per row group) -------------------------------------------------------------
-struct IssueCtx { uint32_t tm, a_col; char *smem; uint64_t *done; };
-// K batch `b` (64 columns) of layer 1: acc[128 stacked columns] (+)= A [W_hi ; W_lo]^T : hi x stacked (N = 128), lo x W_hi (N = 64)
-__device__ __forceinline__ void issue_layer1(const IssueCtx &x, int obs, int b, uint32_t acc_col) {
-    const umma::Tile W1 = umma::make_tile(x.smem + R_W1, obs, 128);
-    const int ksteps = min(64, obs - 64 * b) >> 3;
-    const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
-    uint64_t bd = W1.shifted((uint32_t)(16 * b) * 128).desc(0);
-    for (int ks = 0; ks < ksteps; ks++) {
-        umma::mma_tf32_ts(x.tm + acc_col, x.tm + x.a_col + ks * 8, bd, i128, b > 0 || ks > 0);
-        umma::mma_tf32_ts(x.tm + acc_col, x.tm + x.a_col + 64 + ks * 8, bd, i64, true);
-        bd += (uint64_t)((2 * 128) >> 4);
-    }
-    umma::mma_commit(x.done);
-}
-// one 128 x 64 x 64 product, A (hi | lo) in the group's TMEM A columns, B = the stacked [hi ; lo] tile at `region`:
-// acc[64 columns at acc_col] = A_lo W_hi + A_hi W_lo + A_hi W_hi
-__device__ __forceinline__ void issue_hidden(const IssueCtx &x, int region, uint32_t acc_col) {
-    const umma::Tile Wt = umma::make_tile(x.smem + region, HID, 128);
-    umma::gemm3_ts(x.tm + acc_col, x.tm + x.a_col, x.tm + x.a_col + 64, Wt, Wt.rows_from(64), 128, HID, HID, false);
-    umma::mma_commit(x.done);
-}
-
-// the same product against the stacked tile as ONE N = 128 issue (A_hi x [W_hi ; W_lo]) plus one N = 64 issue (A_lo x W_hi)
-// per K step: acc[128 columns] = [A_hi W_hi + A_lo W_hi | A_hi W_lo]
-__device__ __forceinline__ void issue_hidden_stacked(const IssueCtx &x, int region, uint32_t acc_col) {
-    const umma::Tile Wt = umma::make_tile(x.smem + region, HID, 128);
-    const uint32_t i128 = umma::make_idesc_tf32(128, 128), i64 = umma::make_idesc_tf32(128, 64);
-    uint64_t bd = Wt.desc(0);
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) {
-        umma::mma_tf32_ts(x.tm + acc_col, x.tm + x.a_col + ks * 8, bd, i128, ks > 0);
-        umma::mma_tf32_ts(x.tm + acc_col, x.tm + x.a_col + 64 + ks * 8, bd, i64, true);
-        bd += (uint64_t)((2 * 128) >> 4);
-    }
-    umma::mma_commit(x.done);
-}
-
-// stacked K-major operand tile [hi ; lo] of W[rows = 64 outputs][K] in shared memory from the flat fp32 weights
-// (row pitch `ld` floats); `transpose`: the tile of W^T (K = 64 outputs of W, rows = inputs).  One warp; lane = (row % 8,
-// chunk % 4): conflict-free 16-byte shared stores, 64-byte global segments.
-__device__ void build_tile_warp(float *tile, const float *__restrict__ W, int ld, int K, bool vec, int lane) {
-    if (vec) {
-        const int rl = lane & 7, cl = lane >> 3, cg = (K + 15) >> 4;     // groups of 4 chunks along K
-        for (int it = 0; it < 8 * cg; it += 4) {
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i2 = it + u, r = (i2 / cg) * 8 + rl, k = ((i2 % cg) * 4 + cl) * 4;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i2 < 8 * cg && k < K) v[u] = __ldcg(reinterpret_cast<const float4 *>(W + (size_t)r * ld + k));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i2 = it + u, r = (i2 / cg) * 8 + rl, k = ((i2 % cg) * 4 + cl) * 4;
-                if (i2 < 8 * cg && k < K) {
-                    *reinterpret_cast<float4 *>(tile + umma::tile_index(r, k, K)) = v[u];
-                    *reinterpret_cast<float4 *>(tile + umma::tile_index(64 + r, k, K)) =
-                        make_float4(tf32_lo(v[u].x), tf32_lo(v[u].y), tf32_lo(v[u].z), tf32_lo(v[u].w));
-                }
-            }
-        }
-    } else {
-        for (int e = lane; e < 64 * K; e += 32) {
-            const int r = e / K, k = e - r * K;
-            const float x = __ldcg(W + (size_t)r * ld + k);
-            tile[umma::tile_index(r, k, K)] = x;
-            tile[umma::tile_index(64 + r, k, K)] = tf32_lo(x);
-        }
-    }
-}
-// the tile of W2^T: element (r = input k, column = output j) = W2[j][k]; coalesced global reads along k, scattered stores
-__device__ void build_w2t_warp(float *tile, const float *__restrict__ W2, int lane) {
-    for (int e0 = lane; e0 < HID * HID; e0 += 32 * 8) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = __ldcg(W2 + e0 + 32 * u);
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int e = e0 + 32 * u, j = e >> 6, k = e & 63;
-            tile[umma::tile_index(k, j, HID)] = v[u];
-            tile[umma::tile_index(64 + k, j, HID)] = tf32_lo(v[u]);
-        }
-    }
-}
-
-// registers -> the group's A operand (hi | lo), 32 columns at `col`
-__device__ __forceinline__ void put_a32(const RowCtx &c, int col, const float *hi) {
-    float lo[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) lo[i] = tf32_lo(hi[i]);
-    umma::tmem_st32(c.tlane + c.a_col + col, hi);
-    umma::tmem_st32(c.tlane + c.a_col + 64 + col, lo);
-}
-
-// float offset of element (r, column = batch row `col` of the pass) inside a transposed 128 x 32 tile
-__device__ __forceinline__ int tt_off(int r, int colbase) { return (r >> 3) * (TSBO / 4) + (r & 7) * 4 + colbase; }
 
 __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     extern __shared__ __align__(1024) char smem[];
@@ -421,616 +291,476 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
     }
     const Dims &d = a.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = tid & 127, h = tid >> 7;
     const int ntiles = a.B >> 7;
     const int W = a.lay.record_words;
-    const int obs = d.obs, nch = (obs + 31) >> 5;
-    const TileOff to = tile_offsets(obs);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
-    const uint32_t w1_bytes = 128u * obs * 4, w2_bytes = 128u * HID * 4;
 
-    // De-phase the learners: identical CTAs started together would run in lock-step and hit L2 / HBM with their AdamW
-    // sweeps (432 KB each) and row gathers all at once; a start offset of up to ~50 us spreads those bursts over the round.
+    // De-phase the learners: identical CTAs started together run in lock-step and hit L2 / HBM with their AdamW sweeps
+    // (432 KB each) and row gathers all at once; a start offset of up to ~50 us spreads those bursts over the round.
     if (tid == 0 && gridDim.x > 1) {
         const long long t0 = clock64(), wait = (long long)(blockIdx.x % 48) * 2000;
         while (clock64() - t0 < wait) __nanosleep(100);
     }
     if (warp == 0) umma::tmem_alloc(&mi.tmem_base, 512);
     if (tid == 0)
-        for (int i = 0; i < B_COUNT; i++)
-            umma::mbar_init(bar + i, (i == B_W1FREE || i == B_ACTDONE) ? ntiles : (i == B_RFULL || i == B_RFULL + 1) ? 32
-                                    : (i == B_READY || i == B_READY + 1) ? 4 : (i >= B_H1FREE && i < B_H1FREE + 8) ? 2 : 1);
-    // prologue: the operand-layout tiles and the small vectors follow the flat parameters (which the host may have
-    // changed between calls)
-    if (warp < 8) {
-        rebuild_tiles(L.wt, d, L.tiles + to.tW1, L.tiles + to.tW2, nullptr, tid);
-        load_smalls(L.wt, d, mi.t, tid);
-        load_smalls(L.w, d, mi.o, tid);
-        mi.redw[warp][lane] = 0.f; mi.redw[warp][32 + lane] = 0.f;
-        if (lane == 0) { mi.redmae[warp] = 0.f; mi.reddb3[warp] = 0.f; }
-        fence_proxy_async_all();
-    }
+        for (int i = 0; i < 10; i++) umma::mbar_init(reinterpret_cast<uint64_t *>(&mi.bar[i]), 1);
+    // the operand-layout tiles follow the flat parameters (which the host may have changed between calls)
+    const NetTiles To = net_tiles(L.tiles, d.obs), Tt = net_tiles(L.tiles + net_tile_floats(d.obs), d.obs);
+    rebuild_tiles(L.w, d, To, tid);
+    rebuild_tiles(L.wt, d, Tt, tid);
+    fence_proxy_async_all();
     umma::fence_before_thread_sync();
     __syncthreads();
     umma::fence_after_thread_sync();
-
-    const int np = 4 * ntiles;                                   // weight-gradient passes per round (32 rows each)
-    uint32_t n_pass = 0;                                         // running pass counter (identical in every thread)
-
-    if (warp >= 8) {
-        // ================================================================== helper warpgroup
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        auto soft_due = [&](int round) { return (L.steps0 + round + 2) % a.freq == 0; };
-        if (warp == 8) {
-            // ---- LOADER: target weight tiles by TMA, raw state rows of the weight-gradient passes by cp.async
-            for (int round = 0; round < a.rounds; round++) {
-                cta_sync();   // (A)
-                int pslot[8];
-#pragma unroll
-                for (int p = 0; p < 8; p++) pslot[p] = p < np ? L.slots[(size_t)round * a.B + p * 32 + lane] : 0;
-                if (lane == 0) {
-                    mbar_expect_tx(bar + B_W1, w1_bytes);  bulk_g2s(smem + R_W1, L.tiles + to.tW1, w1_bytes, bar + B_W1);
-                    mbar_expect_tx(bar + B_W2T, w2_bytes); bulk_g2s(smem + R_W2T, L.tiles + to.tW2, w2_bytes, bar + B_W2T);
-                }
-                __syncwarp();
-                cta_sync();   // (B) phase O done: the weight regions become the arena of the weight-gradient passes
-#pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    if (p < np) {
-                        const uint32_t n = n_pass + p, b = n & 1;
-                        umma::mbar_wait(bar + B_RFREE + b, ((n >> 1) & 1) ^ 1);
-                        float *raw = reinterpret_cast<float *>(smem + (b ? R_W2T : R_W2));
-                        const int q4 = obs >> 2;                       // 16-byte chunks per row
-                        for (int idx = lane; idx < 32 * q4; idx += 32) {
-                            const int row = idx / q4, ch = idx - row * q4;
-                            const int slot = __shfl_sync(0xffffffffu, pslot[p], row);
-                            cp_async16(raw + row * RAWP + 4 * ch, reinterpret_cast<const float *>(L.records + (size_t)slot * W) + a.lay.off_state + 4 * ch);
-                        }
-                        // the barrier's 32 arrivals fire as each lane's copies land
-                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(umma::smem_u32(bar + B_RFULL + b)) : "memory");
-                    }
-                }
-                n_pass += np;
-            }
-        } else if (warp == 11) {
-            // ---- TILE BUILDER: the online network's operand tiles straight from the flat weights AdamW just wrote
-            const bool vec1 = (d.D & 3) == 0 && (reinterpret_cast<uintptr_t>(L.w) & 15) == 0, vec2 = (d.oW2 & 3) == 0 && vec1;
-            for (int round = 0; round < a.rounds; round++) {
-                cta_sync();   // (A): AdamW's writes are visible
-                build_tile_warp(reinterpret_cast<float *>(smem + R_W2), L.w + d.oW2, HID, HID, vec2, lane);
-                umma::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar + B_W2);
-                umma::mbar_wait(bar + B_W1FREE, round & 1);       // every group is through target layer 1
-                build_tile_warp(reinterpret_cast<float *>(smem + R_W1), L.w + d.oW1, d.D, obs, vec1, lane);
-                umma::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar + B_W1);
-                umma::mbar_wait(bar + B_ACTDONE, round & 1);      // ... and through the all-actions products (target W2 is free)
-                build_w2t_warp(reinterpret_cast<float *>(smem + R_W2T), L.w + d.oW2, lane);
-                umma::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar + B_W2T);
-                cta_sync();   // (B)
-            }
-        } else {
-            // ---- ISSUER of row group g: the group's products in program order, one lane; the row warps only publish
-            //      operands (B_READY) and wait for results (B_MMA), so the ~50-60 clk per issued MMA never blocks a row warp
-            const int g = warp - 9;
-            IssueCtx x;
-            x.tm = mi.tmem_base; x.a_col = TM_A0 + 128 * g; x.smem = smem; x.done = bar + B_MMA + g;
-            const uint32_t s_col = TM_S0 + 128 * g;
-            uint32_t n_ready = 0;
-            const int nb = (nch + 1) >> 1;
-            for (int round = 0; round < a.rounds; round++) {
-                cta_sync();   // (A)
-                if (g < ntiles && lane == 0) {
-                    auto ready = [&]() { umma::mbar_wait(bar + B_READY + g, n_ready & 1); n_ready++; umma::fence_after_thread_sync(); };
-                    for (int b = 0; b < nb; b++) {                       // target layer 1
-                        ready();
-                        if (b == 0) umma::mbar_wait(bar + B_W1, 0);
-                        issue_layer1(x, obs, b, s_col);
-                    }
-                    for (int ac = 0; ac < d.A; ac++) {                   // all-actions products (stacked: 2 issues per K step)
-                        ready();
-                        if (ac == 0) umma::mbar_wait(bar + B_W2T, 0);
-                        issue_hidden_stacked(x, R_W2T, s_col);
-                    }
-                    for (int b = 0; b < nb; b++) {                       // online layer 1
-                        ready();
-                        if (b == 0) umma::mbar_wait(bar + B_W1, 1);
-                        issue_layer1(x, obs, b, s_col);
-                    }
-                    ready();                                             // layer 2
-                    umma::mbar_wait(bar + B_W2, round & 1);
-                    issue_hidden(x, R_W2, s_col + 64);
-                    ready();                                             // dH1 = dZ2 W2
-                    umma::mbar_wait(bar + B_W2T, 1);
-                    issue_hidden(x, R_W2T, s_col + 64);
-                }
-                __syncwarp();
-                cta_sync();   // (B)
-            }
-        }
-        cta_sync();       // end: everything is done before warp 0 frees the tensor memory
-        return;
-    }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-
-    RowCtx c;
-    c.warp = warp; c.lane = lane; c.g = (warp >> 2) & 1; c.q = warp & 3; c.m = tid & 127;
-    c.tm = mi.tmem_base;
-    c.tlane = c.tm + ((uint32_t)(c.q * 32) << 16);
-    c.a_col = TM_A0 + 128 * c.g; c.s_col = TM_S0 + 128 * c.g;
-    c.n_chunk = 0; c.n_issued = 0; c.n_mma = 0;
-    c.elected = c.q == 0 && lane == 0;
-    c.sbuf = reinterpret_cast<float *>(smem + STAGE + (warp & 7) * 2 * SBUF);
-    c.bar = bar; c.smem = smem;
-    const bool active = c.g < ntiles;
-    const bool dyn = (L.buf_flags & PRL_BUF_DYNAMIC_ACTIONS) != 0;
-
-    // this round's row: slot and scalars are fetched one round ahead
-    const uint32_t *rec = L.records;
-    int act = 0, cnt = 0;
-    float rew = 0.f, term = 0.f;
-    uint32_t ids0 = 0, ids1 = 0, ids2 = 0, ids3 = 0;
-    auto fetch_row = [&](int slot) {
-        rec = L.records + (size_t)slot * W;
-        act = (int)rec[a.lay.off_action];
-        rew = __uint_as_float(rec[a.lay.off_reward]);
-        const uint32_t fl = rec[a.lay.off_flags];
-        term = (fl & 1u) ? 1.f : 0.f;
-        cnt = (int)((fl >> 8) & 0xffffu);
-        if (dyn) {
-            ids0 = rec[a.lay.off_avail];
-            if (d.A > 4) ids1 = rec[a.lay.off_avail + 1];
-            if (d.A > 8) { ids2 = rec[a.lay.off_avail + 2]; ids3 = rec[a.lay.off_avail + 3]; }
-        }
-        mi.rowptr[warp][lane] = (unsigned long long)rec;
-        __syncwarp();
+    const uint32_t w1_bytes = 64u * d.obs * 4, w2_bytes = 2u * HID * HID * 4;
+    // B-operand tiles of one network by TMA: W1 hi / lo into region 1, the W2 block into region 3
+    auto tma_w1 = [&](const NetTiles &t, uint64_t *b) {
+        mbar_expect_tx(b, 2 * w1_bytes);
+        bulk_g2s(smem + REG1, t.w1hi, w1_bytes, b);
+        bulk_g2s(smem + REG1 + HALF, t.w1lo, w1_bytes, b);
     };
-    auto first_chunks = [&](int round) {     // the two chunks every warp requests before a round starts
-        const uint32_t n0 = (uint32_t)round * 2 * nch;
-        issue_chunk(c, n0, mi.rowptr[warp], a.lay.off_next_state, 0, obs);
-        issue_chunk(c, n0 + 1, mi.rowptr[warp], nch > 1 ? a.lay.off_next_state : a.lay.off_state, nch > 1 ? 1 : 0, obs);
+    auto tma_w2 = [&](const NetTiles &t, uint64_t *b, bool with_w2t) {
+        mbar_expect_tx(b, (with_w2t ? 2 : 1) * w2_bytes);
+        bulk_g2s(smem + REG3, t.w2, (with_w2t ? 2 : 1) * w2_bytes, b);
     };
-    if (active) {
-        fetch_row(L.slots[c.g * 128 + c.m]);
-        first_chunks(0);
-    }
+    const uint32_t tm = mi.tmem_base;
+    const uint32_t tlane = tm + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
+    uint32_t parg = 0, par3 = 0, par4 = 0, par5 = 0;                  // mbarrier phase parities
+    uint64_t *bar = reinterpret_cast<uint64_t *>(mi.bar);
 
     for (int round = 0; round < a.rounds; round++) {
         TC_STAMP(0);
+        // ---- per-round row scalars + L2 prefetch of the NEXT round's transitions
+        if (tid < a.B) {
+            const int slot = L.slots[(size_t)round * a.B + tid];
+            const uint32_t *r = L.records + (size_t)slot * W;
+            mi.slot[tid] = slot;
+            mi.act[tid] = (int)r[a.lay.off_action];
+            mi.rew[tid] = __uint_as_float(r[a.lay.off_reward]);
+            const uint32_t fl = r[a.lay.off_flags];
+            mi.term[tid] = (fl & 1u) ? 1.f : 0.f;
+            mi.cnt[tid] = (int)((fl >> 8) & 0xffffu);
+            if (round + 1 < a.rounds) {
+                const char *nx = reinterpret_cast<const char *>(L.records + (size_t)L.slots[(size_t)(round + 1) * a.B + tid] * W);
+                for (int o = 0; o < W * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+            }
+        }
         // ---- scheduled soft target update happens BEFORE this round's gradient step
         //      (deep_td_learning.py:283-284: (training_steps + 1) % freq == 0)
         if ((L.steps0 + round + 2) % a.freq == 0) {
-            for (int i = tid; i < d.P; i += NROW) L.wt[i] = soft_update(__ldcg(L.w + i), __ldcg(L.wt + i), a.tau, a.omtau);
-            rows_sync();
-            rebuild_tiles(L.wt, d, L.tiles + to.tW1, L.tiles + to.tW2, nullptr, tid);
-            load_smalls(L.wt, d, mi.t, tid);
+            for (int i = tid; i < d.P; i += NTH) L.wt[i] = soft_update(__ldcg(L.w + i), __ldcg(L.wt + i), a.tau, a.omtau);
+            __syncthreads();
+            rebuild_tiles(L.wt, d, Tt, tid);
             fence_proxy_async_all();
         }
-        umma::fence_before_thread_sync();
-        cta_sync();        // (A) parameters, tiles and TMEM of the previous round are settled; the weight regions are free
-        umma::fence_after_thread_sync();
+        __syncthreads();
+
+        // ================= phase T: y = max_a' Q_target(s', a') * gamma * (1 - term) + r =================
         TC_STAMP(1);
-
-        // ---------------------------------------------------------------------- ROW GROUPS
-        float dq = 0.f;
-        uint32_t mask2a = 0u, mask2b = 0u;
-        const int act_now = act;
-        if (active) {
-            auto ahead = [&](uint32_t n) {   // chunks of a round in order: next_state 0..nch-1, state 0..nch-1
-                const int s = (int)(n - (uint32_t)round * 2 * nch);
-                if (s < 2 * nch)
-                    issue_chunk(c, n, mi.rowptr[warp], s < nch ? a.lay.off_next_state : a.lay.off_state, s < nch ? s : s - nch, obs);
-            };
-            // ================= phase T: y = max_a' Q_target(s', a') * gamma * (1 - term) + r =================
-            layer1(c, obs, ahead);
-            float yv;
-            {
+        if (tid == 0) {     // target tiles: three TMA bulk copies (regions 1 and 3 are free: every product of the last round was waited for)
+            mbar_expect_tx(bar + 6, 2 * w1_bytes + w2_bytes);
+            bulk_g2s(smem + REG1, Tt.w1hi, w1_bytes, bar + 6);
+            bulk_g2s(smem + REG1 + HALF, Tt.w1lo, w1_bytes, bar + 6);
+            bulk_g2s(smem + REG3, Tt.w2, w2_bytes, bar + 6);
+        }
+        load_smalls(L.wt, d, mi);
+        umma::mbar_wait(bar + 6, round & 1);
+        __syncthreads();
+        TC_STAMP(2);
+        layer1_all_tiles(a, L, mi, smem, a.lay.off_next_state, tm, tlane, parg);
+        if (tid == 0) tma_w1(To, bar + 7);      // region 1 is free again: the online W1 tiles travel while the all-actions products run
+        TC_STAMP(3);
+        {
+            // group g = h: own A operand in tensor memory and own accumulator; the two groups ping-pong
+            const umma::Tile B_hi = umma::make_tile(smem + REG3, 64, 128), B_lo = umma::make_tile(smem + REG3 + 16384, 64, 128);
+            const uint32_t acc_col = h ? TM_ACC1 : TM_ACC0;
+            const uint32_t a_hi = TM_A + 128 * h, a_lo = a_hi + 64;
+            for (int t = 0; t < ntiles; t++) {
+                const int row = t * 128 + m;
                 float t1[64];
-                {
-                    float d2[32];
-                    umma::tmem_ld32(c.tlane + c.s_col, t1);
-                    umma::tmem_ld32(c.tlane + c.s_col + 64, d2);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) t1[i] += d2[i];
-                    umma::tmem_ld32(c.tlane + c.s_col + 32, t1 + 32);
-                    umma::tmem_ld32(c.tlane + c.s_col + 96, d2);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) t1[32 + i] += d2[i];
-                }
-                if (c.elected) mbar_arrive(bar + B_W1FREE);
-                TC_STAMP(2);
+                umma::tmem_ld32(tlane + TM_T1 + t * 64, t1);
+                umma::tmem_ld32(tlane + TM_T1 + t * 64 + 32, t1 + 32);
+                const int cnt = mi.cnt[row];
+                const uint8_t *ids = reinterpret_cast<const uint8_t *>(L.records + (size_t)mi.slot[row] * W + a.lay.off_avail);
                 float best = -INFINITY;
-                float h[64];                      // the NEXT action slot's layer-1 activations, built while a product runs
-                auto build_h = [&](int ac) {
-                    int id = ac;
-                    if (dyn && ac < cnt) {
-                        const uint32_t wsel = ac < 4 ? ids0 : ac < 8 ? ids1 : ac < 12 ? ids2 : ids3;
-                        id = (int)((wsel >> (8 * (ac & 3))) & 0xffu);
+                for (int act = h; act < d.A; act += 2) {
+                    int id = act;
+                    if ((L.buf_flags & PRL_BUF_DYNAMIC_ACTIONS) && act < cnt) id = ids[act];
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        float hi[32], lo[32];
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; c4++) {
+                            const float4 wv = *reinterpret_cast<const float4 *>(&mi.watb[id][half * 32 + 4 * c4]);
+                            const int c = half * 32 + 4 * c4;
+                            umma::split_tf32(fmaxf(t1[c + 0] + wv.x, 0.f), hi[4 * c4 + 0], lo[4 * c4 + 0]);
+                            umma::split_tf32(fmaxf(t1[c + 1] + wv.y, 0.f), hi[4 * c4 + 1], lo[4 * c4 + 1]);
+                            umma::split_tf32(fmaxf(t1[c + 2] + wv.z, 0.f), hi[4 * c4 + 2], lo[4 * c4 + 2]);
+                            umma::split_tf32(fmaxf(t1[c + 3] + wv.w, 0.f), hi[4 * c4 + 3], lo[4 * c4 + 3]);
+                        }
+                        umma::tmem_st32(tlane + a_hi + half * 32, hi);
+                        umma::tmem_st32(tlane + a_lo + half * 32, lo);
                     }
+                    umma::tmem_st_wait();
+                    
+                    umma::fence_before_thread_sync();
+                    group_sync(h);
+                    
+                    if (m == 0) {
+                        umma::fence_after_thread_sync();
+                        umma::gemm3_ts(tm + acc_col, tm + a_hi, tm + a_lo, B_hi, B_lo, 128, HID, HID, false);
+                        umma::mma_commit(&bar[1 + h]);
+                    }
+                    
+                    umma::mbar_wait(&bar[1 + h], parg);
+                    parg ^= 1;
+                    umma::fence_after_thread_sync();
+                    
+                    float acc[64];
+                    umma::tmem_ld32(tlane + acc_col, acc);
+                    umma::tmem_ld32(tlane + acc_col + 32, acc + 32);
+                    float q = 0.f;
 #pragma unroll
                     for (int c4 = 0; c4 < 16; c4++) {
-                        const float4 wv = *reinterpret_cast<const float4 *>(&mi.t.watb[id][4 * c4]);
-                        h[4 * c4 + 0] = fmaxf(t1[4 * c4 + 0] + wv.x, 0.f);
-                        h[4 * c4 + 1] = fmaxf(t1[4 * c4 + 1] + wv.y, 0.f);
-                        h[4 * c4 + 2] = fmaxf(t1[4 * c4 + 2] + wv.z, 0.f);
-                        h[4 * c4 + 3] = fmaxf(t1[4 * c4 + 3] + wv.w, 0.f);
+                        const float4 w3v = *reinterpret_cast<const float4 *>(&mi.w3[4 * c4]);
+                        const float4 b2v = *reinterpret_cast<const float4 *>(&mi.b2[4 * c4]);
+                        q = fmaf(w3v.x, fmaxf(acc[4 * c4 + 0] + b2v.x, 0.f), q);
+                        q = fmaf(w3v.y, fmaxf(acc[4 * c4 + 1] + b2v.y, 0.f), q);
+                        q = fmaf(w3v.z, fmaxf(acc[4 * c4 + 2] + b2v.z, 0.f), q);
+                        q = fmaf(w3v.w, fmaxf(acc[4 * c4 + 3] + b2v.w, 0.f), q);
                     }
-                };
-                auto finish = [&](const float *z, int ap) {     // z = layer-2 pre-activations of slot ap (accumulator halves summed)
-                    float qv = 0.f;
-#pragma unroll
-                    for (int c4 = 0; c4 < 16; c4++) {
-                        const float4 w3v = *reinterpret_cast<const float4 *>(&mi.t.w3[4 * c4]);
-                        const float4 b2v = *reinterpret_cast<const float4 *>(&mi.t.b2[4 * c4]);
-                        qv = fmaf(w3v.x, fmaxf(z[4 * c4 + 0] + b2v.x, 0.f), qv);
-                        qv = fmaf(w3v.y, fmaxf(z[4 * c4 + 1] + b2v.y, 0.f), qv);
-                        qv = fmaf(w3v.z, fmaxf(z[4 * c4 + 2] + b2v.z, 0.f), qv);
-                        qv = fmaf(w3v.w, fmaxf(z[4 * c4 + 3] + b2v.w, 0.f), qv);
-                    }
-                    qv += mi.t.b3;
-                    if (ap >= cnt) qv = -INFINITY;   // next_state_action_values[mask] = -inf
-                    best = fmaxf(best, qv);
-                };
-                auto read_acc = [&](float *z) {
-                    float d2[32];
-                    umma::tmem_ld32(c.tlane + c.s_col, z);
-                    umma::tmem_ld32(c.tlane + c.s_col + 64, d2);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) z[i] += d2[i];
-                    umma::tmem_ld32(c.tlane + c.s_col + 32, z + 32);
-                    umma::tmem_ld32(c.tlane + c.s_col + 96, d2);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) z[32 + i] += d2[i];
-                };
-                // Per slot the only serial work between two products is: operand registers -> TMEM, accumulator -> registers,
-                // publish.  The epilogue arithmetic of slot a - 1 and the operand of slot a + 1 are computed while product a runs.
-                build_h(0);
-                for (int ac = 0; ac < d.A; ac++) {
-                    if (ac == 2) TC_STAMP(13);
-                    if (ac > 0) wait_group_mma(c);      // product ac - 1 is done: its A operand is free, its result is ready
-                    if (ac == 2) TC_STAMP(14);
-                    put_a32(c, 0, h);
-                    put_a32(c, 32, h + 32);
-                    float z[64];
-                    if (ac > 0) read_acc(z);            // before product ac overwrites the accumulator
-                    publish_a(c);
-                    if (ac == 2) TC_STAMP(15);
-                    c.n_mma++;
-                    if (ac > 0) finish(z, ac - 1);
-                    if (ac + 1 < d.A) build_h(ac + 1);
+                    q += mi.b3;
+                    if (act >= cnt) q = -INFINITY;   // next_state_action_values[mask] = -inf
+                    best = fmaxf(best, q);
+                    
+                    
                 }
-                wait_group_mma(c);
-                {
-                    float z[64];
-                    read_acc(z);
-                    finish(z, d.A - 1);
+                mi.vmax2[h][m] = best;
+                umma::fence_before_thread_sync();
+                __syncthreads();
+                if (h == 0) {
+                    const float v = fmaxf(mi.vmax2[0][m], mi.vmax2[1][m]);
+                    mi.y[row] = __fadd_rn(__fmul_rn(__fmul_rn(v, a.gamma), 1.f - mi.term[row]), mi.rew[row]);
                 }
-                if (c.elected) mbar_arrive(bar + B_ACTDONE);
-                yv = __fadd_rn(__fmul_rn(__fmul_rn(best, a.gamma), 1.f - term), rew);
-            }
-            TC_STAMP(3);
-
-            // ================= phase O: online forward, loss, backward through the hidden layers =================
-            layer1(c, obs, ahead);
-            uint32_t mask1a = 0u, mask1b = 0u;
-            {
-                float h1[64];
-                {
-                    float d2[32];
-                    umma::tmem_ld32(c.tlane + c.s_col, h1);
-                    umma::tmem_ld32(c.tlane + c.s_col + 64, d2);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) h1[i] += d2[i];
-                    umma::tmem_ld32(c.tlane + c.s_col + 32, h1 + 32);
-                    umma::tmem_ld32(c.tlane + c.s_col + 96, d2);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) h1[32 + i] += d2[i];
-                }
-#pragma unroll
-                for (int j = 0; j < 64; j++) {
-                    h1[j] = fmaxf(h1[j] + mi.o.watb[act_now][j], 0.f);
-                    if (h1[j] > 0.f) { if (j < 32) mask1a |= 1u << j; else mask1b |= 1u << (j - 32); }
-                }
-                umma::tmem_st32(c.tlane + c.s_col, h1);          // parked for the weight-gradient pass
-                umma::tmem_st32(c.tlane + c.s_col + 32, h1 + 32);
-                put_a32(c, 0, h1);
-                put_a32(c, 32, h1 + 32);
-            }
-            TC_STAMP(4);
-            publish_a(c);
-            c.n_mma++;
-            wait_group_mma(c);
-            {
-                float z[64];   // h2, then dZ2, then dZ1
-                umma::tmem_ld32(c.tlane + c.s_col + 64, z);
-                umma::tmem_ld32(c.tlane + c.s_col + 96, z + 32);
-                float part = 0.f;
-#pragma unroll
-                for (int j = 0; j < 64; j++) { z[j] = fmaxf(z[j] + mi.o.b2[j], 0.f); part = fmaf(mi.o.w3[j], z[j], part); }
-                const float qv = part + mi.o.b3;
-                dq = (qv - yv) * a.inv_b2;
-                const int row = c.g * 128 + c.m;
-                if (L.out_q) L.out_q[(size_t)round * a.B + row] = qv;
-                if (L.out_y) L.out_y[(size_t)round * a.B + row] = yv;
-                {   // dW3[j] = sum_rows dq h2[j]: reduce over this warp's 32 rows, lane j keeps columns j and 32 + j
-                    float cs[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) cs[j] = dq * z[j];
-                    const float s0 = warp_colsum32(cs, lane);
-#pragma unroll
-                    for (int j = 0; j < 32; j++) cs[j] = dq * z[32 + j];
-                    const float s1 = warp_colsum32(cs, lane);
-                    mi.redw[warp][lane] = s0; mi.redw[warp][32 + lane] = s1;
-                    const float ms = warp_sum(fabsf(qv - yv)), ds = warp_sum(dq);
-                    if (lane == 0) { mi.redmae[warp] = ms; mi.reddb3[warp] = ds; }
-                }
-#pragma unroll
-                for (int j = 0; j < 64; j++) {
-                    const bool on = z[j] > 0.f;
-                    if (on) { if (j < 32) mask2a |= 1u << j; else mask2b |= 1u << (j - 32); }
-                    z[j] = on ? dq * mi.o.w3[j] : 0.f;      // dZ2
-                }
-                put_a32(c, 0, z);
-                put_a32(c, 32, z + 32);
-                publish_a(c);                               // dH1 = dZ2 W2
-                c.n_mma++;
-                wait_group_mma(c);
-                umma::tmem_ld32(c.tlane + c.s_col + 64, z);
-                umma::tmem_ld32(c.tlane + c.s_col + 96, z + 32);
-#pragma unroll
-                for (int j = 0; j < 64; j++) {
-                    const bool on = j < 32 ? ((mask1a >> j) & 1u) : ((mask1b >> (j - 32)) & 1u);
-                    z[j] = on ? z[j] : 0.f;                 // dZ1
-                }
-                umma::tmem_st32(c.tlane + c.s_col + 64, z);   // parked for the weight-gradient pass
-                umma::tmem_st32(c.tlane + c.s_col + 96, z + 32);
+                __syncthreads();
             }
         }
+
+        // ================= phase O: online forward, loss, backward =================
+        TC_STAMP(4);
+        if (tid == 0) tma_w2(To, bar + 8, true);   // region 3 held the target W2 until the last all-actions product
+        load_smalls(L.w, d, mi);
+        umma::mbar_wait(bar + 7, round & 1);
+        umma::mbar_wait(bar + 8, round & 1);
+        __syncthreads();
         TC_STAMP(5);
-        umma::tmem_st_wait();
-        umma::fence_before_thread_sync();
-        cta_sync();        // (B) every product of phase O is complete: A columns -> gradient accumulators, weight regions -> arena
-        umma::fence_after_thread_sync();
-        {   // constant-zero parts of the transposed operand tiles (the arena was weights / row chunks until now)
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            auto zero = [&](int byte_off, int bytes) {
-                for (int i = tid * 16; i < bytes; i += NROW * 16) *reinterpret_cast<float4 *>(smem + byte_off + i) = z4;
-            };
-            zero(H1_EHT_HI + 2 * TSBO, 2 * TSBO);      // E rows 16..31 (row 16 is rewritten by the passes)
-            zero(H1_EHT_HI + 12 * TSBO, 4 * TSBO);     // rows 96..127
-            zero(H1_EHT_LO, 4 * TSBO);                 // E is exact: no residual
-            zero(H1_EHT_LO + 12 * TSBO, 4 * TSBO);
-            if (obs < 128) {
-                zero(H2_ST_HI + (obs >> 3) * TSBO, (16 - (obs >> 3)) * TSBO);
-                zero(H2_ST_LO + (obs >> 3) * TSBO, (16 - (obs >> 3)) * TSBO);
+        layer1_all_tiles(a, L, mi, smem, a.lay.off_state, tm, tlane, parg, round, true);
+        TC_STAMP(6);
+        float dw3_acc = 0.f, mae_acc = 0.f, db3_acc = 0.f;
+        const umma::Tile W2_hi = umma::make_tile(smem + REG3, 64, 128), W2_lo = umma::make_tile(smem + REG3 + 16384, 64, 128);
+        const umma::Tile W2T_hi = umma::make_tile(smem + REG3 + 32768, 64, 128), W2T_lo = umma::make_tile(smem + REG3 + 49152, 64, 128);
+        float *r2hi = reinterpret_cast<float *>(smem + REG2), *r2lo = r2hi + HALF / 4;
+        const umma::Tile R2_hi = umma::make_tile(r2hi, 64, 128), R2_lo = umma::make_tile(r2lo, 64, 128);
+        for (int t = 0; t < ntiles; t++) {
+            const int row = t * 128 + m, c0 = h * 32;
+            float h1[32];
+            umma::tmem_ld32(tlane + TM_T1 + t * 64 + c0, h1);
+            {
+                const int ai = mi.act[row];
+#pragma unroll
+                for (int c = 0; c < 32; c++) h1[c] = fmaxf(h1[c] + mi.watb[ai][c0 + c], 0.f);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; c4++)
+                    st_split4(r2hi, r2lo, umma::tile_index(m, c0 + 4 * c4, 64),
+                              make_float4(h1[4 * c4], h1[4 * c4 + 1], h1[4 * c4 + 2], h1[4 * c4 + 3]));
             }
             umma::fence_async_smem();
-            rows_sync();
-        }
-        TC_STAMP(6);
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_thread_sync();
+                umma::gemm3(tm + TM_ACC0, R2_hi, R2_lo, W2_hi, W2_lo, 128, HID, HID, false);
+                umma::mma_commit(&bar[4]);
+            }
+            umma::mbar_wait(&bar[4], par4);
+            par4 ^= 1;
+            umma::fence_after_thread_sync();
+            float z[32];   // h2, then dz2
+            umma::tmem_ld32(tlane + TM_ACC0 + c0, z);
+            float part = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c++) { z[c] = fmaxf(z[c] + mi.b2[c0 + c], 0.f); part = fmaf(mi.w3[c0 + c], z[c], part); }
+            mi.vpart[m][h] = part;
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            const float q = mi.vpart[m][0] + mi.vpart[m][1] + mi.b3;
+            const float y = mi.y[row];
+            const float dq = (q - y) * a.inv_b2;
+            if (h == 0) {
+                if (L.out_q) L.out_q[(size_t)round * a.B + row] = q;
+                if (L.out_y) L.out_y[(size_t)round * a.B + row] = y;
+                mae_acc += fabsf(q - y);
+                db3_acc += dq;
+            }
+            // dW3[c0 + c] += sum_rows dq * h2 : reduce over this warp's 32 rows, lane c keeps column c
+            {
+                float cs[32];
+#pragma unroll
+                for (int c = 0; c < 32; c++) cs[c] = dq * z[c];
+                dw3_acc += warp_colsum32(cs, lane);   // lane c receives the sum of column c over the 32 rows
+            }
+#pragma unroll
+            for (int c = 0; c < 32; c++) z[c] = (z[c] > 0.f) ? dq * mi.w3[c0 + c] : 0.f;   // dZ2
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++)
+                st_split4(r2hi, r2lo, umma::tile_index(m, c0 + 4 * c4, 64),
+                          make_float4(z[4 * c4], z[4 * c4 + 1], z[4 * c4 + 2], z[4 * c4 + 3]));
+            umma::fence_async_smem();
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_thread_sync();
+                umma::gemm3(tm + TM_ACC1, R2_hi, R2_lo, W2T_hi, W2T_lo, 128, HID, HID, false);   // dH1 = dZ2 W2
+                umma::mma_commit(&bar[5]);
+            }
+            umma::mbar_wait(&bar[5], par5);
+            par5 ^= 1;
+            umma::fence_after_thread_sync();
+            float dz1[32];
+            umma::tmem_ld32(tlane + TM_ACC1 + c0, dz1);
+            if (t == 0) TC_STAMP(7);
+#pragma unroll
+            for (int c = 0; c < 32; c++) dz1[c] = (h1[c] > 0.f) ? dz1[c] : 0.f;
 
-        // the next round's slot travels during the passes (its record fields are requested before AdamW)
-        int next_slot = 0;
-        if (active && round + 1 < a.rounds) next_slot = L.slots[(size_t)(round + 1) * a.B + c.g * 128 + c.m];
-        // ================= weight gradients: pass p = the 32 batch rows of warp p =================
-        // The OWNER of pass p (warp p: the rows are its TMEM lanes and its registers hold dq, the ReLU mask and the action)
-        // builds [E ; H1 ; 0]^T and [dZ2 | dZ1]^T and issues G2.  The S^T tiles need no TMEM (the loader re-fetched the raw
-        // rows), so they are built by warp p + 6 mod 8 — on ANOTHER sub-partition than the owner (a TMEM lane quarter is
-        // tied to the sub-partition of its warps, so splitting the owner's own work would not add issue slots) — which then
-        // issues G1 = S^T dZ1 against the dZ1 rows of the owner's tile.  Arena hand-over between passes: one mbarrier per pass
-        // (tcgen05.commit arrives): the G2 arena needs the commits of G2(p) and G1(p), the S^T arena that of G1(p).
-        {
-            const int colbase = (lane >> 2) * (TL / 4) + (lane & 3);
-            float *dz_hi = reinterpret_cast<float *>(smem + H1_DZ_HI), *dz_lo = reinterpret_cast<float *>(smem + H1_DZ_LO);
-            auto owner_half = [&](int p) {
-                float *eh_hi = reinterpret_cast<float *>(smem + H1_EHT_HI), *eh_lo = reinterpret_cast<float *>(smem + H1_EHT_LO);
-                float v[64];
-                umma::tmem_ld32(c.tlane + c.s_col, v);            // h1
-                umma::tmem_ld32(c.tlane + c.s_col + 32, v + 32);
-                if (p > 0) umma::mbar_wait(bar + B_H1FREE + p - 1, round & 1);      // the previous pass's G2 and G1 are done
-                eh_hi[tt_off(0, colbase)] = 1.f;
+            // ---- weight gradients: contractions over the batch rows, 64 rows per pass
+            float *arena = reinterpret_cast<float *>(smem);
+            const umma::Tile TA_hi = umma::make_tile(smem + AR_A_HI, 64, TL), TA_lo = umma::make_tile(smem + AR_A_LO, 64, TL);
+            const umma::Tile TB_hi = umma::make_tile(smem + AR_B_HI, 64, TL), TB_lo = umma::make_tile(smem + AR_B_LO, 64, TL);
+            const umma::Tile TE = umma::make_tile(smem + AR_E, 64, TL);
+            for (int hf = 0; hf < 2; hf++) {
+                const bool mine = (m >> 6) == hf;
+                const int rr = m & 63;
+                const bool first = (t == 0 && hf == 0);
+                umma::fence_before_thread_sync();
+                __syncthreads();   // previous products have been waited for: the arena is free
+                if (mine) {
 #pragma unroll
-                for (int e = 0; e < 16; e++) eh_hi[tt_off(1 + e, colbase)] = (e == act_now) ? 1.f : 0.f;
+                    for (int c = 0; c < 32; c++) {
+                        const int idx = umma::tile_index2(c0 + c, rr, 64, TL);
+                        float hi, lo;
+                        umma::split_tf32(z[c], hi, lo);            // dZ2^T
+                        arena[AR_A_HI / 4 + idx] = hi; arena[AR_A_LO / 4 + idx] = lo;
+                        umma::split_tf32(h1[c], hi, lo);           // H1^T
+                        arena[AR_B_HI / 4 + idx] = hi; arena[AR_B_LO / 4 + idx] = lo;
+                    }
+                    const int ai = mi.act[row];
 #pragma unroll
-                for (int j = 0; j < 64; j++) {
-                    eh_hi[tt_off(32 + j, colbase)] = v[j];
-                    eh_lo[tt_off(32 + j, colbase)] = tf32_lo(v[j]);
-                }
-                umma::tmem_ld32(c.tlane + c.s_col + 64, v);       // dZ1
-                umma::tmem_ld32(c.tlane + c.s_col + 96, v + 32);
-#pragma unroll
-                for (int j = 0; j < 64; j++) {
-                    dz_hi[tt_off(64 + j, colbase)] = v[j];
-                    dz_lo[tt_off(64 + j, colbase)] = tf32_lo(v[j]);
-                }
-                umma::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar + B_DZREADY + p);  // the S^T builder may multiply against dZ1^T
-#pragma unroll
-                for (int j = 0; j < 64; j++) {
-                    const bool on = j < 32 ? ((mask2a >> j) & 1u) : ((mask2b >> (j - 32)) & 1u);
-                    const float x = on ? dq * mi.o.w3[j] : 0.f;   // dZ2 again (cheaper than parking it)
-                    dz_hi[tt_off(j, colbase)] = x;
-                    dz_lo[tt_off(j, colbase)] = tf32_lo(x);
+                    for (int e = 0; e < 16; e++) {                 // E^T: [1 | onehot(action)]
+                        const int er = h * 16 + e;
+                        arena[AR_E / 4 + umma::tile_index2(er, rr, 64, TL)] = (er == 0 || er == ai + 1) ? 1.f : 0.f;
+                    }
                 }
                 umma::fence_async_smem();
                 umma::fence_before_thread_sync();
-                __syncwarp();
-                if (lane == 0) {
+                __syncthreads();
+                if (tid == 0) {
                     umma::fence_after_thread_sync();
-                    const umma::Tile EH{umma::smem_u32(eh_hi), TL, TSBO}, EL{umma::smem_u32(eh_lo), TL, TSBO};
-                    const umma::Tile DH{umma::smem_u32(dz_hi), TL, TSBO}, DL{umma::smem_u32(dz_lo), TL, TSBO};
-                    const uint32_t i128 = umma::make_idesc_tf32(128, 128);
+                    umma::gemm3(tm + TM_DW2, TA_hi, TA_lo, TB_hi, TB_lo, 64, HID, 64, !first);
+                    umma::gemm3(tm + TM_DE2, TA_hi, TA_lo, TE, TE, 64, 32, 64, !first, false, true);
+                    umma::mma_commit(&bar[3]);
+                }
+                umma::mbar_wait(&bar[3], par3);
+                par3 ^= 1;
+                umma::fence_after_thread_sync();
+                umma::fence_before_thread_sync();
+                __syncthreads();
+                if (mine) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        umma::mma_tf32(c.tm + TM_G2, EL.desc(ks), DH.desc(ks), i128, p > 0 || ks > 0);
-                        umma::mma_tf32(c.tm + TM_G2, EH.desc(ks), DL.desc(ks), i128, true);
-                        umma::mma_tf32(c.tm + TM_G2, EH.desc(ks), DH.desc(ks), i128, true);
+                    for (int c = 0; c < 32; c++) {
+                        const int idx = umma::tile_index2(c0 + c, rr, 64, TL);
+                        float hi, lo;
+                        umma::split_tf32(dz1[c], hi, lo);          // dZ1^T
+                        arena[AR_A_HI / 4 + idx] = hi; arena[AR_A_LO / 4 + idx] = lo;
                     }
-                    umma::mma_commit(bar + B_H1FREE + p);
                 }
-                __syncwarp();
-            };
-            auto st_half = [&](int p) {
-                float *st_hi = reinterpret_cast<float *>(smem + H2_ST_HI), *st_lo = reinterpret_cast<float *>(smem + H2_ST_LO);
-                const uint32_t n = n_pass + p;
-                if (p > 0) umma::mbar_wait(bar + B_H2FREE + p - 1, round & 1);   // first: orders this pass behind the fill it waits for next
-                umma::mbar_wait(bar + B_RFULL + (n & 1), (n >> 1) & 1);
-                const float *raw = reinterpret_cast<const float *>(smem + ((n & 1) ? R_W2T : R_W2)) + lane * RAWP;
-#pragma unroll 4
-                for (int k4 = 0; k4 < (obs >> 2); k4++) {
-                    const float4 x = *reinterpret_cast<const float4 *>(raw + 4 * k4);
-                    const int o = tt_off(4 * k4, colbase);      // rows 4 k4 .. 4 k4 + 3 share one 8-row group
-                    st_hi[o] = x.x; st_hi[o + 4] = x.y; st_hi[o + 8] = x.z; st_hi[o + 12] = x.w;
-                    st_lo[o] = tf32_lo(x.x); st_lo[o + 4] = tf32_lo(x.y); st_lo[o + 8] = tf32_lo(x.z); st_lo[o + 12] = tf32_lo(x.w);
+                // S^T: every warp reads whole state rows of this half coalesced (lane = k) and scatters them
+                // into column rr of the transposed tile
+                for (int r0 = 0; r0 < 8; r0 += 4) {
+                    float v[4][4];
+#pragma unroll
+                    for (int ri = 0; ri < 4; ri++) {
+                        const int rq = warp + 8 * (r0 + ri);
+                        const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[t * 128 + hf * 64 + rq] * W) + a.lay.off_state;
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++) v[ri][jj] = (lane + 32 * jj < d.obs) ? __ldg(src + lane + 32 * jj) : 0.f;
+                    }
+#pragma unroll
+                    for (int ri = 0; ri < 4; ri++) {
+                        const int rq = warp + 8 * (r0 + ri);
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++)
+                            if (lane + 32 * jj < d.obs) {
+                                float hi, lo;
+                                umma::split_tf32(v[ri][jj], hi, lo);
+                                const int idx = umma::tile_index2(lane + 32 * jj, rq, 64, TL);
+                                arena[AR_B_HI / 4 + idx] = hi; arena[AR_B_LO / 4 + idx] = lo;
+                            }
+                    }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar + B_RFREE + (n & 1));
                 umma::fence_async_smem();
                 umma::fence_before_thread_sync();
-                __syncwarp();
-                if (lane == 0) {
-                    umma::mbar_wait(bar + B_DZREADY + p, round & 1);             // the owner's dZ1^T rows are in place
+                __syncthreads();
+                if (tid == 0) {
                     umma::fence_after_thread_sync();
-                    const umma::Tile SH{umma::smem_u32(st_hi), TL, TSBO}, SL{umma::smem_u32(st_lo), TL, TSBO};
-                    const umma::Tile D1H = umma::Tile{umma::smem_u32(dz_hi), TL, TSBO}.rows_from(64);
-                    const umma::Tile D1L = umma::Tile{umma::smem_u32(dz_lo), TL, TSBO}.rows_from(64);
-                    const uint32_t i64 = umma::make_idesc_tf32(128, 64);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        umma::mma_tf32(c.tm + TM_G1, SL.desc(ks), D1H.desc(ks), i64, p > 0 || ks > 0);
-                        umma::mma_tf32(c.tm + TM_G1, SH.desc(ks), D1L.desc(ks), i64, true);
-                        umma::mma_tf32(c.tm + TM_G1, SH.desc(ks), D1H.desc(ks), i64, true);
-                    }
-                    umma::mma_commit(bar + B_H2FREE + p);
-                    umma::mma_commit(bar + B_H1FREE + p);
+                    umma::gemm3(tm + TM_DW1, TA_hi, TA_lo, TB_hi, TB_lo, 64, d.obs, 64, !first);
+                    umma::gemm3(tm + TM_DE1, TA_hi, TA_lo, TE, TE, 64, 32, 64, !first, false, true);
+                    umma::mma_commit(&bar[3]);
                 }
-                __syncwarp();
-            };
-            const int p_own = warp, p_st = (warp + 2) & 7;
-            if (p_st < p_own) { if (p_st < np) st_half(p_st); if (p_own < np && active) owner_half(p_own); }
-            else              { if (p_own < np && active) owner_half(p_own); if (p_st < np) st_half(p_st); }
+                umma::mbar_wait(&bar[3], par3);
+                par3 ^= 1;
+                umma::fence_after_thread_sync();
+            }
         }
-        umma::mbar_wait(bar + B_H1FREE + np - 1, round & 1);
-        umma::mbar_wait(bar + B_H2FREE + np - 1, round & 1);
+
+        TC_STAMP(8);
+        // ================= AdamW (gradients straight from TMEM; M = 64 rows live in lanes 32q + (0..15)) ==========
+        mi.redw[warp][lane] = dw3_acc;
+        if (lane == 0) { mi.redmae[warp] = 0.f; mi.reddb3[warp] = 0.f; }
+        {
+            const float ms = warp_sum(mae_acc), ds = warp_sum(db3_acc);
+            if (lane == 0) { mi.redmae[warp] = ms; mi.reddb3[warp] = ds; }
+        }
+        umma::fence_before_thread_sync();
+        __syncthreads();
         umma::fence_after_thread_sync();
-        n_pass += np;
-        TC_STAMP(7);
-
-        // the next round's row and its first two chunks travel while AdamW runs (the staging buffers are free again)
-        if (active && round + 1 < a.rounds) {
-            fetch_row(next_slot);
-            first_chunks(round + 1);
-        }
-        TC_STAMP(9);
-
-        // ================= AdamW =================
-        // (1) TMEM accumulators -> the gradient in the flat (torch) parameter order in shared memory (the G1 arena is free):
-        //     lane = input index, so a warp's 32 values of one output row are 128 contiguous bytes (conflict-free).
-        // (2) all 256 row threads sweep the flat vectors with 16-byte accesses, two float4 groups in flight per thread.
         {
+            // 1) gradients TMEM -> shared staging (arena is free: every product has been waited for).  Row
+            //    pitches are odd, so the 16 live lanes of a warp (rows 16q .. 16q+15) hit distinct banks.
+            float *gs_w2 = reinterpret_cast<float *>(smem);            // [64][65]
+            const int pitch1 = d.D | 1;
+            float *gs_w1 = gs_w2 + 64 * 65;                            // [64][pitch1]   (state cols, then action cols)
+            float *gs_b1 = gs_w1 + 64 * pitch1, *gs_b2 = gs_b1 + 64;
+            const int j = (warp & 3) * 16 + (lane & 15);               // M = 64 lane map: lanes >= 16 hold nothing
+            const bool live = lane < 16;
+            float g[32];
+            umma::tmem_ld32(tlane + TM_DW2 + h * 32, g);
+            if (live)
+#pragma unroll
+                for (int c = 0; c < 32; c++) gs_w2[j * 65 + h * 32 + c] = g[c];
+            for (int cc = 0; cc < 2; cc++) {
+                const int kbase = h * 64 + cc * 32;
+                if (kbase < d.obs) {   // warp-uniform
+                    umma::tmem_ld32(tlane + TM_DW1 + kbase, g);
+                    if (live)
+#pragma unroll
+                        for (int c = 0; c < 32; c++)
+                            if (kbase + c < d.obs) gs_w1[j * pitch1 + kbase + c] = g[c];
+                }
+            }
+            umma::tmem_ld32(tlane + (h ? TM_DE1 : TM_DE2), g);
+            if (live) {
+                if (h == 0) gs_b2[j] = g[0];
+                else {
+                    gs_b1[j] = g[0];
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        if (k < d.A) gs_w1[j * pitch1 + d.obs + k] = g[1 + k];
+                }
+            }
+            umma::fence_before_thread_sync();
+            __syncthreads();
+            // 2) AdamW over the flat parameter vector, all 256 threads, fully coalesced 16-byte accesses
             const float2 sc = L.scal[round];
             AdamScalarsTc hs;
             hs.decay = a.decay; hs.omb1 = a.omb1; hs.beta2 = a.beta2; hs.omb2 = a.omb2; hs.eps = a.eps;
             hs.step_size = sc.x; hs.bc2_sqrt = sc.y; hs.inv_bc2_sqrt = 1.0f / sc.y;
-            float *gsm = reinterpret_cast<float *>(smem + R_W1);
-            const int gs = c.g, j0 = 32 * gs;
-            {   // G1[lane k][col j] = dW1[j][k]
-                float g1[32];
-                umma::tmem_ld32(c.tlane + TM_G1 + j0, g1);
-                const int k = 32 * c.q + lane;
-                if (k < obs)
+            const bool vecD = ((d.D & 3) == 0) && ((d.oW2 & 3) == 0);
+            if (vecD) {
+                const int D4 = d.D >> 2;
+                for (int row = warp; row < HID; row += 8)
+                    for (int c4 = lane; c4 < D4; c4 += 32) {
+                        const int i = d.oW1 + row * d.D + c4 * 4;
+                        const float *gp = gs_w1 + row * pitch1 + c4 * 4;
+                        float4 w4 = __ldcg(reinterpret_cast<const float4 *>(L.w + i)), m4 = __ldcg(reinterpret_cast<const float4 *>(L.m + i));
+                        float4 v4 = __ldcg(reinterpret_cast<const float4 *>(L.v + i)), x4 = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i));
+                        w4.x = adam_math(w4.x, m4.x, v4.x, x4.x, gp[0], hs); w4.y = adam_math(w4.y, m4.y, v4.y, x4.y, gp[1], hs);
+                        w4.z = adam_math(w4.z, m4.z, v4.z, x4.z, gp[2], hs); w4.w = adam_math(w4.w, m4.w, v4.w, x4.w, gp[3], hs);
+                        *reinterpret_cast<float4 *>(L.w + i) = w4; *reinterpret_cast<float4 *>(L.m + i) = m4;
+                        *reinterpret_cast<float4 *>(L.v + i) = v4; *reinterpret_cast<float4 *>(L.vmax + i) = x4;
+                        if (c4 * 4 < d.obs) {   // the same 16-byte chunk of the operand-layout tiles (hi = the value, lo = residual)
+                            const int ti = umma::tile_index(row, c4 * 4, d.obs);
+                            *reinterpret_cast<float4 *>(To.w1hi + ti) = w4;
+                            *reinterpret_cast<float4 *>(To.w1lo + ti) = make_float4(tf32_lo(w4.x), tf32_lo(w4.y), tf32_lo(w4.z), tf32_lo(w4.w));
+                        }
+                    }
+                for (int q4 = tid; q4 < HID * HID / 4; q4 += NTH) {   // W2: 16 float4 per row
+                    const int row = q4 >> 4, c = (q4 & 15) * 4, i = d.oW2 + q4 * 4;
+                    const float *gp = gs_w2 + row * 65 + c;
+                    float4 w4 = __ldcg(reinterpret_cast<const float4 *>(L.w + i)), m4 = __ldcg(reinterpret_cast<const float4 *>(L.m + i));
+                    float4 v4 = __ldcg(reinterpret_cast<const float4 *>(L.v + i)), x4 = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i));
+                    w4.x = adam_math(w4.x, m4.x, v4.x, x4.x, gp[0], hs); w4.y = adam_math(w4.y, m4.y, v4.y, x4.y, gp[1], hs);
+                    w4.z = adam_math(w4.z, m4.z, v4.z, x4.z, gp[2], hs); w4.w = adam_math(w4.w, m4.w, v4.w, x4.w, gp[3], hs);
+                    *reinterpret_cast<float4 *>(L.w + i) = w4; *reinterpret_cast<float4 *>(L.m + i) = m4;
+                    *reinterpret_cast<float4 *>(L.v + i) = v4; *reinterpret_cast<float4 *>(L.vmax + i) = x4;
+                    {
+                        const float4 l4 = make_float4(tf32_lo(w4.x), tf32_lo(w4.y), tf32_lo(w4.z), tf32_lo(w4.w));
+                        const int ti = umma::tile_index(row, c, HID);
+                        *reinterpret_cast<float4 *>(To.w2 + ti) = w4;
+                        *reinterpret_cast<float4 *>(To.w2 + 4096 + ti) = l4;
+                        const float hh[4] = {w4.x, w4.y, w4.z, w4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-                    for (int jj = 0; jj < 32; jj++) gsm[d.oW1 + (j0 + jj) * d.D + k] = g1[jj];
-            }
-            if (c.q == 1 || c.q == 2) {   // G2 lanes 32 + k2: dW2[j][k2] in the dZ2 columns
-                float g2[32];
-                umma::tmem_ld32(c.tlane + TM_G2 + j0, g2);
-                const int k2 = 32 * (c.q - 1) + lane;
-#pragma unroll
-                for (int jj = 0; jj < 32; jj++) gsm[d.oW2 + (j0 + jj) * HID + k2] = g2[jj];
-            } else if (c.q == 0) {        // G2 lane 0: db2 (dZ2 columns), db1 (dZ1 columns); lanes 1..A: dW1[:, obs + a]
-                float gz2[32], gz1[32];
-                umma::tmem_ld32(c.tlane + TM_G2 + j0, gz2);
-                umma::tmem_ld32(c.tlane + TM_G2 + 64 + j0, gz1);
-                if (lane == 0) {
-#pragma unroll
-                    for (int jj = 0; jj < 32; jj++) { gsm[d.ob1 + j0 + jj] = gz1[jj]; gsm[d.ob2 + j0 + jj] = gz2[jj]; }
-                } else if (lane <= d.A) {
-#pragma unroll
-                    for (int jj = 0; jj < 32; jj++) gsm[d.oW1 + (j0 + jj) * d.D + obs + lane - 1] = gz1[jj];
-                }
-            } else {                      // W3 and b3 from the shuffle reductions of phase O, fixed summation order
-                const int j = j0 + lane;
-                float gsum = 0.f;
-#pragma unroll
-                for (int w8 = 0; w8 < 8; w8++) gsum += mi.redw[w8][j];
-                gsm[d.oW3 + j] = gsum;
-                if (gs == 1 && lane == 0) {
-                    float ds = 0.f, ms = 0.f;
-#pragma unroll
-                    for (int w8 = 0; w8 < 8; w8++) { ds += mi.reddb3[w8]; ms += mi.redmae[w8]; }
-                    gsm[d.ob3] = ds;
-                    L.out_mae[round] = ms / (float)a.B;   // reported "loss": mean |q - y|
-                }
-            }
-            TC_STAMP(10);
-            umma::fence_before_thread_sync();
-            rows_sync();
-            TC_STAMP(11);
-            const int P = d.P;
-            if ((reinterpret_cast<uintptr_t>(L.w) | reinterpret_cast<uintptr_t>(L.m) | reinterpret_cast<uintptr_t>(L.v) |
-                 reinterpret_cast<uintptr_t>(L.vmax)) & 15) {
-                for (int i = tid; i < P; i += NROW) {      // unaligned vectors: scalar sweep
-                    float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
-                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gsm[i], hs);
-                    L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
+                        for (int u = 0; u < 4; u++) {       // W2^T tile: element (k = c + u, j = row)
+                            const int tt = umma::tile_index(c + u, row, HID);
+                            To.w2[8192 + tt] = hh[u]; To.w2[12288 + tt] = ll[u];
+                        }
+                    }
                 }
             } else {
-                const int P4 = P >> 2;
-                for (int q0 = tid; q0 < P4; q0 += 2 * NROW) {
-                    float4 w4[2], m4[2], v4[2], x4[2];
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const int qq = q0 + u * NROW;
-                        if (qq < P4) {
-                            w4[u] = __ldcg(reinterpret_cast<const float4 *>(L.w) + qq); m4[u] = __ldcg(reinterpret_cast<const float4 *>(L.m) + qq);
-                            v4[u] = __ldcg(reinterpret_cast<const float4 *>(L.v) + qq); x4[u] = __ldcg(reinterpret_cast<const float4 *>(L.vmax) + qq);
-                        }
+                for (int row = warp; row < HID; row += 8)
+                    for (int c = lane; c < d.D; c += 32) {
+                        const int i = d.oW1 + row * d.D + c;
+                        float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
+                        L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gs_w1[row * pitch1 + c], hs);
+                        L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
                     }
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const int qq = q0 + u * NROW;
-                        if (qq < P4) {
-                            const float4 g4 = *reinterpret_cast<const float4 *>(gsm + 4 * qq);
-                            w4[u].x = adam_math(w4[u].x, m4[u].x, v4[u].x, x4[u].x, g4.x, hs);
-                            w4[u].y = adam_math(w4[u].y, m4[u].y, v4[u].y, x4[u].y, g4.y, hs);
-                            w4[u].z = adam_math(w4[u].z, m4[u].z, v4[u].z, x4[u].z, g4.z, hs);
-                            w4[u].w = adam_math(w4[u].w, m4[u].w, v4[u].w, x4[u].w, g4.w, hs);
-                            reinterpret_cast<float4 *>(L.w)[qq] = w4[u]; reinterpret_cast<float4 *>(L.m)[qq] = m4[u];
-                            reinterpret_cast<float4 *>(L.v)[qq] = v4[u]; reinterpret_cast<float4 *>(L.vmax)[qq] = x4[u];
-                        }
-                    }
-                }
-                for (int i = 4 * P4 + tid; i < P; i += NROW) {
+                for (int e = tid; e < HID * HID; e += NTH) {
+                    const int i = d.oW2 + e;
                     float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
-                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gsm[i], hs);
+                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gs_w2[(e >> 6) * 65 + (e & 63)], hs);
+                    L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
+                }
+                __syncthreads();
+                rebuild_tiles(L.w, d, To, tid);         // unaligned shapes (D % 4 != 0): tiles from the flat vector
+            }
+            fence_proxy_async_all();                    // the tile writes are read by TMA in the next round
+            {   // b1 | b2 | W3 | b3: 64 + 64 + 64 + 1 parameters, one per thread
+                int i = -1;
+                float gg = 0.f;
+                if (tid < 64) { i = d.ob1 + tid; gg = gs_b1[tid]; }
+                else if (tid < 128) { i = d.ob2 + tid - 64; gg = gs_b2[tid - 64]; }
+                else if (tid < 192) {   // W3: sum the four row-quarter partials of this column in fixed order
+                    const int col = tid - 128, hh = col >> 5, c = col & 31;
+                    gg = ((mi.redw[hh * 4 + 0][c] + mi.redw[hh * 4 + 1][c]) + mi.redw[hh * 4 + 2][c]) + mi.redw[hh * 4 + 3][c];
+                    i = d.oW3 + col;
+                } else if (tid == 192) {
+                    gg = ((mi.reddb3[0] + mi.reddb3[1]) + mi.reddb3[2]) + mi.reddb3[3];
+                    i = d.ob3;
+                    const float e = ((mi.redmae[0] + mi.redmae[1]) + mi.redmae[2]) + mi.redmae[3];
+                    L.out_mae[round] = e / (float)a.B;   // reported "loss": mean |q - y|
+                }
+                if (i >= 0) {
+                    float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
+                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gg, hs);
                     L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
                 }
             }
-            umma::fence_before_thread_sync();
-            rows_sync();
-            TC_STAMP(12);
-            load_smalls(L.w, d, mi.o, tid);
         }
-        TC_STAMP(8);
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        umma::fence_after_thread_sync();
+        TC_STAMP(9);
     }
-    umma::fence_before_thread_sync();
-    cta_sync();
-    if (warp == 0) umma::tmem_dealloc(mi.tmem_base, 512);
+    if (warp == 0) umma::tmem_dealloc(tm, 512);
 }
 
 // a few microseconds of nothing: lets the learner CTAs of the main stream take their SMs before the next chunk's
@@ -1089,8 +819,6 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
         PRL_CUDA(cudaHostAlloc((void **)&h_samp, 32 * 1024, cudaHostAllocDefault));
         PRL_CUDA(cudaEventCreateWithFlags(&h_done, cudaEventDisableTiming));
     }
-    PRL_REQUIRE((size_t)count * sizeof(TcLearner) <= 32 * 1024 && (size_t)count * sizeof(MultiSampler) <= 32 * 1024,
-                "too many learners in one group");
     PRL_CUDA(cudaEventSynchronize(h_done));
     size_t samp_smem = 0;
     for (int i = 0; i < count; i++) {
@@ -1109,9 +837,6 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
                     "buffer %d does not match the learner", i);
         PRL_REQUIRE(b->lay.record_words == bufs[0]->lay.record_words && b->lay.off_avail == bufs[0]->lay.off_avail,
                     "buffers must share one record layout");
-        PRL_REQUIRE((b->lay.record_words & 3) == 0 && (b->lay.off_state & 3) == 0 && (b->lay.off_next_state & 3) == 0 &&
-                        ((uintptr_t)b->records & 15) == 0,
-                    "record rows must be 16-byte aligned for the TMA row copies");
         // the per-round AdamW scalars (two double pow() per round, as torch evaluates them) depend only on the shared
         // configuration and the step count: learners at the same step read learner 0's copy
         const bool shared_scal = i > 0 && q->adam_step == q0->adam_step;
@@ -1126,8 +851,8 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
         h_samp[i].sp.out_logical = out_logical ? out_logical[i] : nullptr;
         TcLearner &L = h_learn[i];
         L.records = b->records; L.slots = q->slots;
-        L.w = q->w; L.wt = q->wt; L.m = q->m; L.v = q->v; L.vmax = q->vmax;
         L.tiles = q->tc_tiles;
+        L.w = q->w; L.wt = q->wt; L.m = q->m; L.v = q->v; L.vmax = q->vmax;
         L.scal = shared_scal ? q0->scal_dev : q->scal_dev;
         L.out_mae = out_mae[i]; L.out_q = out_q ? out_q[i] : nullptr; L.out_y = out_y ? out_y[i] : nullptr;
         L.steps0 = training_steps0[i];
