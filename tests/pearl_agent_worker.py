@@ -32,7 +32,7 @@ OBS, A, CAP, B, ROUNDS, STEPS = 12, 4, 300, 32, 3, 90
 
 
 def make(kind, double):
-    space = DiscreteActionSpace([torch.tensor([i]) for i in range(A)])
+    space = DiscreteActionSpace([torch.tensor([i]) for i in range(A)], seed=123)   # same exploration draws for both agents
     kw = dict(state_dim=OBS, action_space=space, hidden_dims=[64, 64], training_rounds=ROUNDS, batch_size=B,
               target_update_freq=4, soft_update_tau=0.6, exploration_module=EGreedyExploration(0.3),
               action_representation_module=OneHotActionTensorRepresentationModule(A))
