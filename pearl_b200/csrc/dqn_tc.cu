@@ -128,9 +128,11 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // Operand-layout copies of one network's matrices in global memory (floats):
-//   [W1 hi: 64 x obs][W1 lo][W2 hi: 64 x 64][W2 lo][W2^T hi][W2^T lo]      (the shared-memory images, tile by tile)
-struct NetTiles { float *w1hi, *w1lo, *w2; };   // w2: the 4 x 4096-float block W2 hi | W2 lo | W2^T hi | W2^T lo
-__host__ __device__ inline int net_tile_floats(int obs) { return 128 * obs + 4 * HID * HID; }
+//   [W1 hi: 64 x obs][W1 lo][W2 hi: 64 x 64][W2 lo]      (the shared-memory images, tile by tile; the W2^T tiles of the
+//   online network are transposed out of the W2 tiles in shared memory: keeping them in global memory too cost AdamW eight
+//   scattered 4-byte stores per 16-byte group, more than the transposition)
+struct NetTiles { float *w1hi, *w1lo, *w2; };   // w2: the 2 x 4096-float block W2 hi | W2 lo
+__host__ __device__ inline int net_tile_floats(int obs) { return 128 * obs + 2 * HID * HID; }
 __device__ __forceinline__ NetTiles net_tiles(float *base, int obs) { return NetTiles{base, base + 64 * obs, base + 128 * obs}; }
 // all tiles of one network from its flat parameter vector (kernel prologue, soft target update)
 __device__ void rebuild_tiles(const float *__restrict__ net, const Dims &d, const NetTiles &t, int tid) {
@@ -142,9 +144,9 @@ __device__ void rebuild_tiles(const float *__restrict__ net, const Dims &d, cons
     }
     for (int e = tid; e < HID * HID; e += NTH) {
         const int j = e >> 6, k = e & 63;
-        const float x = __ldcg(net + d.oW2 + e), lo = tf32_lo(x);
-        const int i1 = umma::tile_index(j, k, HID), i2 = umma::tile_index(k, j, HID);
-        t.w2[i1] = x; t.w2[4096 + i1] = lo; t.w2[8192 + i2] = x; t.w2[12288 + i2] = lo;
+        const float x = __ldcg(net + d.oW2 + e);
+        const int i1 = umma::tile_index(j, k, HID);
+        t.w2[i1] = x; t.w2[4096 + i1] = tf32_lo(x);
     }
 }
 // the small fp32 vectors of a network (action columns + b1, b2, w3, b3); all loads of a thread issued before the first use
@@ -319,9 +321,9 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         bulk_g2s(smem + REG1, t.w1hi, w1_bytes, b);
         bulk_g2s(smem + REG1 + HALF, t.w1lo, w1_bytes, b);
     };
-    auto tma_w2 = [&](const NetTiles &t, uint64_t *b, bool with_w2t) {
-        mbar_expect_tx(b, (with_w2t ? 2 : 1) * w2_bytes);
-        bulk_g2s(smem + REG3, t.w2, (with_w2t ? 2 : 1) * w2_bytes, b);
+    auto tma_w2 = [&](const NetTiles &t, uint64_t *b) {
+        mbar_expect_tx(b, w2_bytes);
+        bulk_g2s(smem + REG3, t.w2, w2_bytes, b);
     };
     const uint32_t tm = mi.tmem_base;
     const uint32_t tlane = tm + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
@@ -448,10 +450,19 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
 
         // ================= phase O: online forward, loss, backward =================
         TC_STAMP(4);
-        if (tid == 0) tma_w2(To, bar + 8, true);   // region 3 held the target W2 until the last all-actions product
+        if (tid == 0) tma_w2(To, bar + 8);         // region 3 held the target W2 until the last all-actions product
         load_smalls(L.w, d, mi);
-        umma::mbar_wait(bar + 7, round & 1);
         umma::mbar_wait(bar + 8, round & 1);
+        {   // W2^T tiles (B operand of dH1 = dZ2 W2) out of the W2 tiles: element (k, j) <- (j, k)
+            const float *w2 = reinterpret_cast<const float *>(smem + REG3);
+            float *w2t = reinterpret_cast<float *>(smem + REG3 + 32768);
+            for (int e = tid; e < HID * HID; e += NTH) {
+                const int j = e >> 6, k = e & 63, i1 = umma::tile_index(j, k, HID), i2 = umma::tile_index(k, j, HID);
+                w2t[i2] = w2[i1]; w2t[4096 + i2] = w2[4096 + i1];
+            }
+            umma::fence_async_smem();
+        }
+        umma::mbar_wait(bar + 7, round & 1);
         __syncthreads();
         TC_STAMP(5);
         layer1_all_tiles(a, L, mi, smem, a.lay.off_state, tm, tlane, parg, round, true);
@@ -707,12 +718,6 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         const int ti = umma::tile_index(row, c, HID);
                         *reinterpret_cast<float4 *>(To.w2 + ti) = w4;
                         *reinterpret_cast<float4 *>(To.w2 + 4096 + ti) = l4;
-                        const float hh[4] = {w4.x, w4.y, w4.z, w4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {       // W2^T tile: element (k = c + u, j = row)
-                            const int tt = umma::tile_index(c + u, row, HID);
-                            To.w2[8192 + tt] = hh[u]; To.w2[12288 + tt] = ll[u];
-                        }
                     }
                 }
             } else {

@@ -23,6 +23,10 @@ using namespace prl;
 namespace {
 
 // arrays are in TIME order (index 0 = oldest stored transition)
+// One thread per transition decides whether it is the newest element ("head") of a chain = an episode segment; a head
+// walks its chain newest -> oldest in the reference's fp32 operation order (ppo.py:271-293), so the result is bit-identical
+// to the Python loop.  The walk is latency-bound (one lane per warp, a dependent recurrence), so it moves 4 transitions
+// per step with 16-byte loads / stores and keeps the next group's loads in flight while the current one is evaluated.
 __global__ void k_ppo_gae(int n, const float *__restrict__ values, float last_next_value_host,
                           const float *__restrict__ last_next_value_dev, float incoming_gae, const float *__restrict__ reward, const uint8_t *__restrict__ terminated,
                           const uint8_t *__restrict__ truncated, float gamma, float c_live,
@@ -35,17 +39,71 @@ __global__ void k_ppo_gae(int n, const float *__restrict__ values, float last_ne
     // the chain headed by the newest element continues a chain of NEWER transitions held elsewhere (a later time
     // shard): it starts from that chain's gae instead of 0 (multiplied by 0 below if the newest element ends an episode)
     float gae = (t == n - 1) ? incoming_gae : 0.f;
-    for (int s = t; s >= 0; s--) {
-        const bool term = terminated[s] != 0, cut = term || truncated[s] != 0;
-        if (s != t && cut) break;                                       // the next chain's head
-        const float nv = (s == n - 1) ? last_next_value : values[s + 1];
-        const float v = values[s];
+    float nv = (t == n - 1) ? last_next_value : values[t + 1];          // value of the next (newer) stored transition
+    auto step = [&](int s, float v, float r, bool term, bool cut) {
         // reward + gamma * next_value * (~terminated) - V[i]   (left to right, fp32)
-        const float td = __fsub_rn(__fadd_rn(reward[s], __fmul_rn(__fmul_rn(gamma, nv), term ? 0.f : 1.f)), v);
+        const float td = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nv), term ? 0.f : 1.f)), v);
         // td + (gamma * lambda * mask) * gae ; the scalar product is evaluated in double by Python
         gae = __fadd_rn(td, __fmul_rn(cut ? 0.f : c_live, gae));
-        out_gae[s] = gae;
-        out_lam_return[s] = __fadd_rn(gae, v);
+        nv = v;
+        return gae;
+    };
+    int s = t;
+    // scalar steps until [s - 3, s] is an aligned group of four (the head itself is always a scalar step)
+    bool first = true;
+    while (s >= 0 && (first || (s & 3) != 3)) {
+        const bool term = terminated[s] != 0, cut = term || truncated[s] != 0;
+        if (!first && cut) return;                                      // the next chain's head
+        const float v = values[s], g = step(s, v, reward[s], term, cut);
+        out_gae[s] = g;
+        out_lam_return[s] = __fadd_rn(g, v);
+        first = false;
+        s--;
+    }
+    const bool vec = ((reinterpret_cast<uintptr_t>(values) | reinterpret_cast<uintptr_t>(reward) | reinterpret_cast<uintptr_t>(out_gae) |
+                       reinterpret_cast<uintptr_t>(out_lam_return)) & 15) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(terminated) | reinterpret_cast<uintptr_t>(truncated)) & 3) == 0;
+    if (vec && s >= 3) {
+        float4 v4 = *reinterpret_cast<const float4 *>(values + s - 3), r4 = *reinterpret_cast<const float4 *>(reward + s - 3);
+        uint32_t te = *reinterpret_cast<const uint32_t *>(terminated + s - 3), tr = *reinterpret_cast<const uint32_t *>(truncated + s - 3);
+        while (true) {
+            // the next group's loads are issued before this group's recurrence (they do not depend on it)
+            const bool more = s >= 7;
+            float4 nv4 = v4, nr4 = r4;
+            uint32_t nte = 0, ntr = 0;
+            if (more) {
+                nv4 = *reinterpret_cast<const float4 *>(values + s - 7); nr4 = *reinterpret_cast<const float4 *>(reward + s - 7);
+                nte = *reinterpret_cast<const uint32_t *>(terminated + s - 7); ntr = *reinterpret_cast<const uint32_t *>(truncated + s - 7);
+            }
+            const float vv[4] = {v4.x, v4.y, v4.z, v4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
+            if (((te | tr) & 0xffffffffu) == 0) {                       // no episode end inside the group: four steps, two 16-byte stores
+                float g[4];
+#pragma unroll
+                for (int u = 3; u >= 0; u--) g[u] = step(s - 3 + u, vv[u], rr[u], false, false);
+                *reinterpret_cast<float4 *>(out_gae + s - 3) = make_float4(g[0], g[1], g[2], g[3]);
+                *reinterpret_cast<float4 *>(out_lam_return + s - 3) =
+                    make_float4(__fadd_rn(g[0], vv[0]), __fadd_rn(g[1], vv[1]), __fadd_rn(g[2], vv[2]), __fadd_rn(g[3], vv[3]));
+            } else {
+#pragma unroll
+                for (int u = 3; u >= 0; u--) {
+                    const bool term = ((te >> (8 * u)) & 0xffu) != 0, cut = term || ((tr >> (8 * u)) & 0xffu) != 0;
+                    if (cut) return;                                    // the next chain's head
+                    const float g = step(s - 3 + u, vv[u], rr[u], false, false);
+                    out_gae[s - 3 + u] = g;
+                    out_lam_return[s - 3 + u] = __fadd_rn(g, vv[u]);
+                }
+            }
+            s -= 4;
+            if (!more) break;
+            v4 = nv4; r4 = nr4; te = nte; tr = ntr;
+        }
+    }
+    for (; s >= 0; s--) {                                               // the oldest 0..3 transitions (or unaligned arrays)
+        const bool term = terminated[s] != 0, cut = term || truncated[s] != 0;
+        if (cut) return;
+        const float v = values[s], g = step(s, v, reward[s], term, cut);
+        out_gae[s] = g;
+        out_lam_return[s] = __fadd_rn(g, v);
     }
 }
 
