@@ -371,6 +371,40 @@ int prl_sac_learn(prl_sac *sac, prl_buf *buf, int rounds, int batch, const float
 int prl_sac_set_graph(prl_sac *sac, int enable);
 int64_t prl_sac_last_launches(const prl_sac *sac);
 
+/* ---- TD3 / DDPG ----------------------------------------------------------------------------------
+ * Replaces TD3.learn_batch (policy_learners/sequential_decision_making/td3.py:106-202) and, with
+ * actor_update_freq = 1 and no noise, DeepDeterministicPolicyGradient (ddpg.py:105-157 on
+ * actor_critic_base.py:309-366), driven by PolicyLearner.learn (policy_learner.py:162-204) over a
+ * continuous-action ring: per round sample -> [if training_steps % actor_update_freq == 0: actor step,
+ * maximise Q1(s, pi(s)), VanillaContinuousActorNetwork tanh head + action_scaling, actor_networks.py:29-51,448-485]
+ * -> twin-critic step against min(Q1', Q2')(s', clamp(pi'(s') + clipped noise)) -> [on the same rounds: soft
+ * update of the critic targets and of the actor target].  The actor optimizer's step count advances only on its
+ * update rounds.  Flat layouts (fp32, row-major [out][in]):
+ *   actor : W1[h1][obs] b1 W2[h2][h1] b2 W3[A][h2] b3       critic: as prl_sac (q1 then q2)
+ * noise_dev: device f32[rounds][batch][A] = the torch.normal(0, actor_update_noise, ...) draws (null: DDPG). */
+typedef struct prl_td3_cfg {
+    int32_t obs_dim, act_dim, actor_h1, actor_h2, critic_h1, critic_h2;
+    int32_t actor_update_freq;
+    int32_t max_batch, max_rounds;
+    double actor_lr, critic_lr, beta1, beta2, eps, weight_decay, gamma, actor_tau, critic_tau, noise_clip;
+} prl_td3_cfg;
+typedef struct prl_td3 prl_td3;
+int64_t prl_td3_actor_param_count(const prl_td3_cfg *cfg);
+int64_t prl_td3_critic_param_count(const prl_td3_cfg *cfg);   /* ONE critic */
+int64_t prl_td3_workspace_bytes(const prl_td3_cfg *cfg);
+int prl_td3_create(prl_td3 **out, const prl_td3_cfg *cfg, float *actor_w, float *actor_m, float *actor_v,
+                   float *actor_vmax, float *actor_target_w, float *critic_w, float *critic_m, float *critic_v,
+                   float *critic_vmax, float *critic_target_w, const float *low_dev, const float *high_dev,
+                   int64_t actor_adam_step, int64_t critic_adam_step, void *workspace);
+int prl_td3_destroy(prl_td3 *td3);
+int64_t prl_td3_actor_adam_step(const prl_td3 *td3);
+int64_t prl_td3_critic_adam_step(const prl_td3 *td3);
+/* training_steps0 = learner._training_steps before the call; out_*_loss: device f32[rounds] */
+int prl_td3_learn(prl_td3 *td3, prl_buf *buf, int rounds, int batch, int64_t training_steps0, const float *noise_dev,
+                  float *out_actor_loss_dev, float *out_critic_loss_dev, int32_t *out_logical_dev, void *stream);
+int prl_td3_set_graph(prl_td3 *td3, int enable);
+int64_t prl_td3_last_launches(const prl_td3 *td3);
+
 /* ---- PPO learner ------------------------------------------------------------------------------
  * Replaces ProximalPolicyOptimization.learn (policy_learners/sequential_decision_making/ppo.py:195-293):
  * prl_ppo_preprocess = preprocess_replay_buffer (state values, taken-action probabilities under the current

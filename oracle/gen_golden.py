@@ -388,8 +388,79 @@ def gen_sac_golden():
     print("sac_small.npz: actor_loss", rep["actor_loss"][:2], "critic_loss", rep["critic_loss"][:2])
 
 
+def gen_td3_golden(kind: str):
+    """TD3 / DDPG: PearlAgent(TD3 | DeepDeterministicPolicyGradient, BasicReplayBuffer).learn() with the sampled indices and
+    (TD3) the `torch.normal` target-noise draws recorded."""
+    from pearl.policy_learners.exploration_modules.common.no_exploration import NoExploration
+    from pearl.policy_learners.sequential_decision_making.ddpg import DeepDeterministicPolicyGradient
+    from pearl.policy_learners.sequential_decision_making.td3 import TD3
+    from pearl.utils.instantiations.spaces.box_action import BoxActionSpace
+    torch.manual_seed(61 if kind == "td3" else 62)
+    random.seed(61 if kind == "td3" else 62)
+    torch.set_num_threads(1)
+    obs, act, n, B, rounds = 9, 3, 260, 48, 8
+    low, high = torch.tensor([-0.5, -1.0, -0.25]), torch.tensor([0.5, 1.0, 1.25])
+    space = BoxActionSpace(low=low, high=high)
+    hp = dict(actor_lr=3e-4, critic_lr=6e-4, actor_tau=0.03, critic_tau=0.05, gamma=0.97)
+    common = dict(state_dim=obs, action_space=space, actor_hidden_dims=[32, 32], critic_hidden_dims=[32, 32], training_rounds=rounds,
+                  batch_size=B, actor_learning_rate=hp["actor_lr"], critic_learning_rate=hp["critic_lr"],
+                  actor_soft_update_tau=hp["actor_tau"], critic_soft_update_tau=hp["critic_tau"], discount_factor=hp["gamma"],
+                  exploration_module=NoExploration())
+    if kind == "td3":
+        hp.update(freq=2, noise_std=0.2, noise_clip=0.5)
+        pl = TD3(actor_update_freq=2, actor_update_noise=0.2, actor_update_noise_clip=0.5, **common)
+    else:
+        hp.update(freq=1, noise_std=0.0, noise_clip=0.0)
+        pl = DeepDeterministicPolicyGradient(**common)
+    buf = BasicReplayBuffer(n)
+    agent = PearlAgent(policy_learner=pl, replay_buffer=buf, device_id=-1)
+    rng = np.random.Generator(np.random.PCG64(19))
+    q8 = lambda x: (np.rint(x * 256) / 256).astype(np.float32)
+    st, ns, rw = q8(rng.standard_normal((n, obs))), q8(rng.standard_normal((n, obs))), q8(rng.standard_normal(n))
+    ac = q8(rng.uniform(low.numpy(), high.numpy(), size=(n, act)))
+    term = rng.random(n) < 0.05
+    for i in range(n):
+        buf.push(state=torch.from_numpy(st[i]), action=torch.from_numpy(ac[i]), reward=float(rw[i]), terminated=bool(term[i]),
+                 truncated=False, curr_available_actions=space, next_state=torch.from_numpy(ns[i]), next_available_actions=space)
+    fl = lambda m: np.concatenate([p.detach().numpy().ravel() for p in m.parameters()])
+    nets = lambda: dict(actor=fl(pl._actor), actor_t=fl(pl._actor_target), q1=fl(pl._critic._critic_1), q2=fl(pl._critic._critic_2),
+                        q1t=fl(pl._critic_target._critic_1), q2t=fl(pl._critic_target._critic_2))
+    init = nets()
+    noises, idxs = [], []
+    orig_normal = torch.normal
+
+    def normal_spy(*a, **k):
+        x = orig_normal(*a, **k)
+        noises.append(x.numpy().copy())
+        return x
+    torch.normal = normal_spy
+    orig_sample = buf.sample
+
+    def sample_spy(k):
+        pos = {id(t): j for j, t in enumerate(buf.memory)}
+        stt = random.getstate()
+        idxs.append([pos[id(t)] for t in random.sample(buf.memory, k)])
+        random.setstate(stt)
+        return orig_sample(k)
+    buf.sample = sample_spy
+    rep = agent.learn()
+    torch.normal = orig_normal
+    assert len(noises) == (rounds if kind == "td3" else 0)
+    out = dict(kind=kind, obs=obs, act=act, n=n, batch=B, rounds=rounds, low=low.numpy(), high=high.numpy(), state=st, next_state=ns,
+               reward=rw, action=ac, terminated=term, idx=np.asarray(idxs, dtype=np.int32),
+               noise=np.asarray(noises, dtype=np.float32).reshape(len(noises), B, act) if noises else np.zeros((0, B, act), np.float32),
+               actor_loss=np.asarray(rep["actor_loss"]), critic_loss=np.asarray(rep["critic_loss"]),
+               **{f"init_{k}": v for k, v in init.items()}, **{f"{k}_after": v for k, v in nets().items()}, **hp)
+    np.savez_compressed(os.path.join(GOLDEN, f"{kind}_small.npz"), **out)
+    print(f"{kind}_small.npz: actor_loss", rep["actor_loss"][:3], "critic_loss", rep["critic_loss"][:2])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "td3":
+        gen_td3_golden("td3")
+        gen_td3_golden("ddpg")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sac":
         gen_sac_golden()
         sys.exit(0)
