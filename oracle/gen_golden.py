@@ -455,8 +455,47 @@ def gen_td3_golden(kind: str):
     print(f"{kind}_small.npz: actor_loss", rep["actor_loss"][:3], "critic_loss", rep["critic_loss"][:2])
 
 
+def gen_her_golden():
+    """HindsightExperienceReplayBuffer: the deque contents (oldest first) after three episodes pushed through the reference."""
+    from pearl.replay_buffers.sequential_decision_making.hindsight_experience_replay_buffer import HindsightExperienceReplayBuffer
+    goal_dim, n_act, cap = 3, 4, 40
+    space = DiscreteActionSpace(actions=list(torch.arange(n_act).view(-1, 1)))
+    reward_fn = lambda s, a: float((s[:goal_dim] - s[-goal_dim:]).abs().sum() < 0.75) - 0.5      # noqa: E731
+    terminated_fn = lambda s, a: bool((s[:goal_dim] - s[-goal_dim:]).abs().sum() < 0.25)        # noqa: E731
+    rng = np.random.Generator(np.random.PCG64(77))
+    q8 = lambda x: (np.rint(x * 8) / 8).astype(np.float32)
+    lens = [7, 12, 5]
+    total = sum(lens)
+    st, ns = q8(rng.standard_normal((total, 2 * goal_dim))), q8(rng.standard_normal((total, 2 * goal_dim)))
+    rw = q8(rng.standard_normal(total))
+    ac = rng.integers(0, n_act, size=total).astype(np.int64)
+    ends = np.zeros(total, dtype=bool); ends[np.cumsum(lens) - 1] = True
+    trunc = np.zeros(total, dtype=bool); trunc[lens[0] - 1] = True          # the first episode is truncated, the others terminate
+    term = ends & ~trunc
+    out = {}
+    for tag, tf in (("a", None), ("b", terminated_fn)):
+        buf = HindsightExperienceReplayBuffer(cap, goal_dim, reward_fn, tf)
+        for i in range(total):
+            buf.push(state=torch.from_numpy(st[i].copy()), action=torch.tensor(int(ac[i])), reward=float(rw[i]), terminated=bool(term[i]),
+                     truncated=bool(trunc[i]), curr_available_actions=space, next_state=torch.from_numpy(ns[i].copy()),
+                     next_available_actions=space, max_number_actions=n_act)
+        mem = list(buf.memory)
+        out[f"state_{tag}"] = np.stack([t.state.reshape(-1).numpy() for t in mem])
+        out[f"next_state_{tag}"] = np.stack([t.next_state.reshape(-1).numpy() for t in mem])
+        out[f"reward_{tag}"] = np.asarray([float(t.reward) for t in mem], dtype=np.float32)
+        out[f"action_{tag}"] = np.asarray([int(t.action.reshape(-1)[0]) for t in mem], dtype=np.int64)
+        out[f"terminated_{tag}"] = np.asarray([bool(t.terminated) for t in mem])
+        out[f"truncated_{tag}"] = np.asarray([bool(t.truncated) for t in mem])
+    np.savez_compressed(os.path.join(GOLDEN, "her_small.npz"), goal_dim=goal_dim, n_act=n_act, capacity=cap, state=st, next_state=ns, reward=rw,
+                        action=ac, terminated=term, truncated=trunc, **out)
+    print("her_small.npz:", len(out["reward_a"]), "stored transitions")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "her":
+        gen_her_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "td3":
         gen_td3_golden("td3")
         gen_td3_golden("ddpg")

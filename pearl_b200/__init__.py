@@ -10,6 +10,7 @@ from ._compat import HAVE_PEARL, OneHotActionTensorRepresentationModule, Transit
 from .dqn import B200DeepQLearning, B200DoubleDQN, B200LearnerGroup  # noqa: F401
 from .replay_buffer import B200ReplayBuffer  # noqa: F401
 from .per import B200PrioritizedReplayBuffer  # noqa: F401
+from .her import B200HindsightExperienceReplayBuffer  # noqa: F401
 from .sac import B200ContinuousSoftActorCritic  # noqa: F401
 from .td3 import B200TD3, B200DeepDeterministicPolicyGradient  # noqa: F401
 from .ppo import B200ProximalPolicyOptimization, gae_and_lambda_returns  # noqa: F401
@@ -17,4 +18,4 @@ from .dist import B200Communicator, all_gather_bytes, shard_owner  # noqa: F401
 
 __all__ = ["B200ReplayBuffer", "B200DeepQLearning", "B200DoubleDQN", "TransitionBatch",
            "OneHotActionTensorRepresentationModule", "HAVE_PEARL", "B200Communicator", "B200LearnerGroup", "B200PrioritizedReplayBuffer", "gae_and_lambda_returns", "B200ContinuousSoftActorCritic", "B200ProximalPolicyOptimization",
-           "B200TD3", "B200DeepDeterministicPolicyGradient"]
+           "B200TD3", "B200DeepDeterministicPolicyGradient", "B200HindsightExperienceReplayBuffer"]

@@ -212,3 +212,28 @@ def test_act_is_greedy_over_available_actions_and_explores_like_the_reference():
     for _ in range(20):
         want.append(random.randrange(A) if random.random() < 0.5 else int(q.argmax()))
     assert got == want
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_hindsight_buffer_matches_the_reference_recording(tag):
+    """f1: B200HindsightExperienceReplayBuffer against the contents of the reference's HindsightExperienceReplayBuffer
+    (tests/golden/her_small.npz: three episodes, FIFO eviction at capacity 40; "b" = with a terminated_fn)."""
+    import os
+    import pearl_b200
+    from conftest import GOLDEN
+    fx = np.load(os.path.join(GOLDEN, "her_small.npz"))
+    gd, A, cap = int(fx["goal_dim"]), int(fx["n_act"]), int(fx["capacity"])
+    reward_fn = lambda s, a: float((s[:gd] - s[-gd:]).abs().sum() < 0.75) - 0.5          # noqa: E731 (as in oracle/gen_golden.py)
+    terminated_fn = (lambda s, a: bool((s[:gd] - s[-gd:]).abs().sum() < 0.25)) if tag == "b" else None
+    buf = pearl_b200.B200HindsightExperienceReplayBuffer(cap, gd, reward_fn, terminated_fn)
+    t = torch.from_numpy
+    for i in range(fx["state"].shape[0]):
+        buf.push(state=t(fx["state"][i].copy()), action=torch.tensor(int(fx["action"][i])), reward=float(fx["reward"][i]),
+                 terminated=bool(fx["terminated"][i]), truncated=bool(fx["truncated"][i]), curr_available_actions=_Space(A),
+                 next_state=t(fx["next_state"][i].copy()), next_available_actions=_Space(A), max_number_actions=A)
+    n = len(buf)
+    assert n == fx[f"reward_{tag}"].shape[0]
+    g = buf._gather_logical(torch.arange(n, dtype=torch.int32, device=buf.device))
+    assert np.array_equal(g["state"].cpu().numpy(), fx[f"state_{tag}"]) and np.array_equal(g["next_state"].cpu().numpy(), fx[f"next_state_{tag}"])
+    assert np.array_equal(g["reward"].cpu().numpy(), fx[f"reward_{tag}"]) and np.array_equal(g["action"].cpu().numpy(), fx[f"action_{tag}"])
+    assert np.array_equal(g["terminated"].cpu().numpy(), fx[f"terminated_{tag}"]) and np.array_equal(g["truncated"].cpu().numpy(), fx[f"truncated_{tag}"])
