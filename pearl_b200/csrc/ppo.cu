@@ -23,18 +23,17 @@ using namespace prl;
 namespace {
 
 // arrays are in TIME order (index 0 = oldest stored transition)
-// One thread per transition decides whether it is the newest element ("head") of a chain = an episode segment; a head
-// walks its chain newest -> oldest in the reference's fp32 operation order (ppo.py:271-293), so the result is bit-identical
-// to the Python loop.  The walk is latency-bound (one lane per warp, a dependent recurrence), so it moves 4 transitions
-// per step with 16-byte loads / stores and keeps the next group's loads in flight while the current one is evaluated.
-__global__ void k_ppo_gae(int n, const float *__restrict__ values, float last_next_value_host,
+// A chain = an episode segment; its newest element ("head") is the last stored transition or one with terminated /
+// truncated set.  k_ppo_gae_heads compacts the head positions (order irrelevant: chains are independent), then
+// k_ppo_gae gives every chain its own THREAD — all 32 lanes of a warp walk chains — newest -> oldest in the reference's
+// fp32 operation order (ppo.py:271-293), so the result is bit-identical to the Python loop.  The walk is a dependent
+// recurrence: it moves 4 transitions per step with 16-byte loads / stores and keeps the next group's loads in flight.
+// (Round 1 let the head's own thread of a one-thread-per-transition grid walk the chain: one active lane per warp, 0.04 of
+// the HBM roofline at 16M transitions.)
+__device__ __forceinline__ void gae_walk_chain(int t, int n, const float *__restrict__ values, float last_next_value_host,
                           const float *__restrict__ last_next_value_dev, float incoming_gae, const float *__restrict__ reward, const uint8_t *__restrict__ terminated,
                           const uint8_t *__restrict__ truncated, float gamma, float c_live,
                           float *__restrict__ out_gae, float *__restrict__ out_lam_return) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const bool head = (t == n - 1) || terminated[t] || truncated[t];   // newest element of its chain
-    if (!head) return;
     const float last_next_value = last_next_value_dev ? *last_next_value_dev : last_next_value_host;
     // the chain headed by the newest element continues a chain of NEWER transitions held elsewhere (a later time
     // shard): it starts from that chain's gae instead of 0 (multiplied by 0 below if the newest element ends an episode)
@@ -107,7 +106,41 @@ __global__ void k_ppo_gae(int n, const float *__restrict__ values, float last_ne
     }
 }
 
+__global__ void k_ppo_gae_heads(int n, const uint8_t *__restrict__ terminated, const uint8_t *__restrict__ truncated,
+                                int *__restrict__ heads, int *__restrict__ count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool head = t < n && ((t == n - 1) || terminated[t] || truncated[t]);
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(count, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (head) heads[base + __popc(bal & ((1u << lane) - 1u))] = t;
+}
+__global__ void k_ppo_gae(int n, const int *__restrict__ heads, const int *__restrict__ count, const float *__restrict__ values,
+                          float last_next_value_host, const float *__restrict__ last_next_value_dev, float incoming_gae,
+                          const float *__restrict__ reward, const uint8_t *__restrict__ terminated, const uint8_t *__restrict__ truncated,
+                          float gamma, float c_live, float *__restrict__ out_gae, float *__restrict__ out_lam_return) {
+    const int nh = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += gridDim.x * blockDim.x)
+        gae_walk_chain(heads[i], n, values, last_next_value_host, last_next_value_dev, incoming_gae, reward, terminated, truncated, gamma, c_live,
+                       out_gae, out_lam_return);
+}
+
 }  // namespace
+
+// heads: int32[n] scratch, count: int32[1] scratch (both device)
+static int launch_gae(int n, const float *values, float last_next_value, const float *last_next_value_dev, float incoming_gae,
+                      const float *reward, const uint8_t *term, const uint8_t *trunc, float gamma, float c_live, float *out_gae,
+                      float *out_lam_return, int *heads, int *count, cudaStream_t st) {
+    PRL_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+    k_ppo_gae_heads<<<(n + 255) / 256, 256, 0, st>>>(n, term, trunc, heads, count);
+    const int blocks = (n + 127) / 128 < 148 * 8 ? (n + 127) / 128 : 148 * 8;
+    k_ppo_gae<<<blocks, 128, 0, st>>>(n, heads, count, values, last_next_value, last_next_value_dev, incoming_gae, reward, term, trunc, gamma,
+                                      c_live, out_gae, out_lam_return);
+    PRL_CUDA(cudaGetLastError());
+    return PRL_OK;
+}
 
 extern "C" int prl_ppo_gae(int n, const float *values_dev, float last_next_value, const float *reward_dev,
                            const uint8_t *terminated_dev, const uint8_t *truncated_dev, double gamma, double lam,
@@ -116,12 +149,13 @@ extern "C" int prl_ppo_gae(int n, const float *values_dev, float last_next_value
     if (n == 0) return PRL_OK;
     PRL_REQUIRE(values_dev && reward_dev && terminated_dev && truncated_dev && out_gae_dev && out_lam_return_dev,
                 "null argument");
-    const int threads = 256;
-    k_ppo_gae<<<(n + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-        n, values_dev, last_next_value, nullptr, 0.f, reward_dev, terminated_dev, truncated_dev, (float)gamma, (float)(gamma * lam),
-        out_gae_dev, out_lam_return_dev);
-    PRL_CUDA(cudaGetLastError());
-    return PRL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int *scratch = nullptr;                     // chain heads + their count, stream-ordered allocation
+    PRL_CUDA(cudaMallocAsync((void **)&scratch, ((size_t)n + 1) * sizeof(int), st));
+    const int rc = launch_gae(n, values_dev, last_next_value, nullptr, 0.f, reward_dev, terminated_dev, truncated_dev, (float)gamma,
+                              (float)(gamma * lam), out_gae_dev, out_lam_return_dev, scratch + 1, scratch, st);
+    PRL_CUDA(cudaFreeAsync(scratch, st));
+    return rc;
 }
 
 // ====================================================================================================
@@ -271,6 +305,7 @@ struct prl_ppo {
     float *S, *h1, *h2, *logits, *v, *gae, *lam, *old, *ap, *dlogits, *dh2, *dh1, *dv, *g_actor, *g_critic, *reward, *last_value;
     int32_t *act, *slots, *logical;
     uint8_t *term, *trunc;
+    int *gae_heads;           // [1 + max_rollout]: count, then the chain-head positions of the GAE pass
     float2 *scal_a, *scal_c;
     PpoCall *call;
     int *round_idx;
@@ -331,6 +366,7 @@ static PpoWs ppo_ws(const prl_ppo_cfg *c, int Pa, int Pc) {
     add(R * 4); add((int64_t)c->max_rounds * c->max_batch * 4); add((int64_t)c->max_rounds * c->max_batch * 4);     // act slots logical
     add(c->max_rollout); add(c->max_rollout);                                                                        // term trunc
     add((int64_t)c->max_rounds * 16 + 256);                                                                          // scal_a | scal_c | call | round_idx
+    add((c->max_rollout + 1) * 4);                                                                                   // GAE chain heads + count
     w.total = o;
     return w;
 }
@@ -362,6 +398,7 @@ extern "C" int prl_ppo_create(prl_ppo **out, const prl_ppo_cfg *cfg, float *acto
     s->term = (uint8_t *)(b + w.off[k++]); s->trunc = (uint8_t *)(b + w.off[k++]);
     s->scal_a = (float2 *)(b + w.off[k++]); s->scal_c = s->scal_a + cfg->max_rounds;
     s->call = (PpoCall *)(s->scal_c + cfg->max_rounds); s->round_idx = (int *)(s->call + 1);
+    s->gae_heads = (int *)(b + w.off[k++]);
     static_assert(sizeof(PpoCall) + 4 <= 256, "call block fits the reserved tail");
     s->scal_next = 0; s->use_graph = true; s->graph_exec = nullptr; s->graph_batch = 0; s->graph_buf = nullptr; s->last_launches = 0;
     s->pre_n = 0;
@@ -428,8 +465,11 @@ extern "C" int prl_ppo_preprocess(prl_ppo *s, prl_buf *buf, float *out_values, f
     }
     k_ppo_last_next_state<<<1, 128, 0, st>>>(buf->records, buf->lay, c.obs_dim, (head + n - 1) % cap, s->S);
     ppo_critic_forward(s, L, 1, s->last_value);
-    k_ppo_gae<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, out_values, 0.f, s->last_value, 0.f, s->reward, s->term, s->trunc, (float)c.gamma,
-                                                      (float)(c.gamma * c.lam), out_gae, out_lam_return);
+    {
+        const int rc = launch_gae((int)n, out_values, 0.f, s->last_value, 0.f, s->reward, s->term, s->trunc, (float)c.gamma,
+                                  (float)(c.gamma * c.lam), out_gae, out_lam_return, s->gae_heads + 1, s->gae_heads, st);
+        if (rc) return rc;
+    }
     if (out_cut) k_ppo_cuts<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, s->term, s->trunc, out_cut);
     PRL_CUDA(cudaGetLastError());
     s->pre_n = n;
@@ -446,10 +486,8 @@ extern "C" int prl_ppo_gae_redo(prl_ppo *s, const float *values_dev, float next_
     PRL_REQUIRE(s->pre_n > 0, "prl_ppo_preprocess has not run on this handle");
     const prl_ppo_cfg &c = s->cfg;
     const int64_t n = s->pre_n;
-    k_ppo_gae<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((int)n, values_dev, next_value, nullptr, incoming_gae, s->reward, s->term,
-                                                                      s->trunc, (float)c.gamma, (float)(c.gamma * c.lam), out_gae, out_lam_return);
-    PRL_CUDA(cudaGetLastError());
-    return PRL_OK;
+    return launch_gae((int)n, values_dev, next_value, nullptr, incoming_gae, s->reward, s->term, s->trunc, (float)c.gamma,
+                      (float)(c.gamma * c.lam), out_gae, out_lam_return, s->gae_heads + 1, s->gae_heads, (cudaStream_t)stream_);
 }
 
 static int ppo_round(prl_ppo *s, prl_buf *buf, int B, cudaStream_t st) {
