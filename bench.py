@@ -40,7 +40,7 @@ OBS, N_ACT, HIDDEN, BATCH = 128, 16, (64, 64), 256
 METRIC = "learner gradient-steps/sec (batch=256, 1e6 replay)"
 
 
-TC_DRAM_BYTES_PER_STEP = 796e3   # measured under ncu, see profiles/r1_k_dqn_tc_summary.md
+TC_DRAM_BYTES_PER_STEP = 1.176e6   # measured under ncu (5.417 GB over 144 learners x 32 rounds), profiles/r2_k_dqn_tc_ncu.csv
 
 
 def flops_per_step(obs=OBS, A=N_ACT, H1=HIDDEN[0], H2=HIDDEN[1], B=BATCH, double=False):
@@ -411,7 +411,8 @@ def run_b200(args) -> None:
             "roofline": {"bound": "tensor", "kernel": "k_dqn_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": TC_DRAM_BYTES_PER_STEP * rounds * R,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full` capture of k_dqn_tc in "
-                                           "profiles/r1_k_dqn_tc_summary.md (796 KB per gradient step; algorithmic gather 266 KB), "
+                                           "profiles/r2_k_dqn_tc_ncu.csv (1.18 MB per gradient step with 144 learners' parameters, AdamW state and operand "
+                                           "tiles competing for L2; algorithmic gather 266 KB), "
                                            "scaled to the gradient steps of one bench launch",
                          "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
                          "flops_per_gradient_step_factored": fact, "flops_per_gradient_step_as_written": as_written,
@@ -574,6 +575,8 @@ def other_paths(dev, args) -> dict:
     import torch
     import pearl_b200
     out = {}
+    from pearl_b200 import _lib
+    lib = _lib.init(dev.index if isinstance(dev, torch.device) and dev.index is not None else 0)
     gen = torch.Generator(device=dev).manual_seed(777)
     rn = lambda *shape: torch.randn(*shape, device=dev, generator=gen)
     cores = os.cpu_count() or 1
@@ -621,13 +624,19 @@ def other_paths(dev, args) -> dict:
                            torch.rand(m, device=dev, generator=gen) < 0.01,
                            torch.zeros(m, dtype=torch.bool, device=dev))
         buf.seed(5)
-        pl = pearl_b200.B200ContinuousSoftActorCritic(state_dim=obs, low=[-0.4] * act, high=[0.4] * act, actor_hidden_dims=[256, 256],
-                                                       critic_hidden_dims=[256, 256], training_rounds=R, batch_size=B, device=dev, seed=1)
-        sec = timed(lambda: pl.learn(buf), 3)
+        def run(engine):       # the engine is read when the learner's round is captured into its CUDA graph
+            _lib.check(lib.prl_set_contraction_engine(engine))
+            pl = pearl_b200.B200ContinuousSoftActorCritic(state_dim=obs, low=[-0.4] * act, high=[0.4] * act, actor_hidden_dims=[256, 256],
+                                                           critic_hidden_dims=[256, 256], training_rounds=R, batch_size=B, device=dev, seed=1)
+            sec = timed(lambda: pl.learn(buf), 3)
+            return sec, int(pl._lib.prl_sac_last_launches(pl._handle)) // R
+        sec0, _ = run(0)
+        sec, kps = run(1)
         out["sac"] = {"workload": "SAC continuous obs_dim=376 act_dim=17, 1M replay, batch=512 (configs[2])", "value": R / sec,
                       "unit": "gradient-steps/s (actor + twin-critic + entropy steps)", "us_per_step": sec / R * 1e6,
-                      "kernels_per_step": int(pl._lib.prl_sac_last_launches(pl._handle)) // R, "engine": "fp32 SIMT tiled contractions, CUDA-graph replay"}
-        del pl, buf
+                      "kernels_per_step": kps, "engine": "3xTF32 tcgen05 contractions (k_gemm_tc), CUDA-graph replay",
+                      "with_simt_contractions": {"value": R / sec0, "us_per_step": sec0 / R * 1e6}}
+        del buf
         if not args.no_cpu:
             from oracle.sac_oracle import OracleSAC
             orc = OracleSAC(obs, act, (256, 256), (256, 256), [-0.4] * act, [0.4] * act)
@@ -646,17 +655,22 @@ def other_paths(dev, args) -> dict:
         buf.push_batch(rn(n, obs), torch.randint(0, A, (n,), device=dev, generator=gen).to(torch.int32), rn(n), rn(n, obs),
                        (torch.arange(n, device=dev) % 500) == 499, torch.zeros(n, dtype=torch.bool, device=dev), max_number_actions=A)
         buf.seed(6)
-        pl = pearl_b200.B200ProximalPolicyOptimization(state_dim=obs, n_actions=A, actor_hidden_dims=hid, critic_hidden_dims=hid,
-                                                        training_rounds=R, batch_size=B, epsilon=0.1, discount_factor=0.99,
-                                                        trace_decay_param=0.95, device=dev, seed=2)
-        pre_sec = timed(lambda: pl.preprocess_replay_buffer(buf), 5)
-        sec = timed(lambda: pl.learn(buf), 3)
+        def run(engine):
+            _lib.check(lib.prl_set_contraction_engine(engine))
+            pl = pearl_b200.B200ProximalPolicyOptimization(state_dim=obs, n_actions=A, actor_hidden_dims=hid, critic_hidden_dims=hid,
+                                                            training_rounds=R, batch_size=B, epsilon=0.1, discount_factor=0.99,
+                                                            trace_decay_param=0.95, device=dev, seed=2)
+            pre = timed(lambda: pl.preprocess_replay_buffer(buf), 5)
+            return pre, timed(lambda: pl.learn(buf), 3)
+        pre0, sec0 = run(0)
+        pre_sec, sec = run(1)
         out["ppo"] = {"workload": "PPO 64k-step rollout obs_dim=210, 16 actions, [64,64] networks, GAE + clipped surrogate, batch=256 "
                                   "(configs[3] / SURVEY cfg4, one GPU)",
                       "preprocess_ms": pre_sec * 1e3, "preprocess_transitions_per_s": n / pre_sec,
                       "value": R / (sec - pre_sec), "unit": "gradient-steps/s (actor + critic steps, preprocessing excluded)",
-                      "learn_ms": sec * 1e3, "training_rounds": R}
-        del pl, buf
+                      "learn_ms": sec * 1e3, "training_rounds": R, "engine": "3xTF32 tcgen05 contractions (k_gemm_tc), CUDA-graph replay",
+                      "with_simt_contractions": {"value": R / (sec0 - pre0), "preprocess_ms": pre0 * 1e3}}
+        del buf
         if not args.no_cpu:
             from oracle.ppo_oracle import OraclePPO
             orc = OraclePPO(obs, A, tuple(hid), tuple(hid), epsilon=0.1, batch_size=B, training_rounds=1)

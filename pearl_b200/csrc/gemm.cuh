@@ -150,11 +150,17 @@ __global__ void __launch_bounds__((TM / MR) * (TN / 4)) k_gemm(const GemmArgs g)
     }
 }
 
+// gemm_tc.cu: the same contraction on tcgen05 (3xTF32).  Returns false when the engine is off / the shape is not covered.
+bool gemm_tc_launch(const GemmArgs &g, int nets, bool ao, bool bo, cudaStream_t st, int engine);
+cudaError_t gemm_tc_prepare();
+
 struct GemmLauncher {
     cudaStream_t st;
     int count = 0;
+    int engine = -1;   // -1: library default (prl_set_contraction_engine); 0: SIMT tiles; 1 / 64 / 32: tcgen05 tiles
     template <bool AO, bool BO>
     void run(const GemmArgs &g, int nets) {
+        if (gemm_tc_launch(g, nets, AO, BO, st, engine)) { count++; return; }
         const long long big = (long long)((g.Mo + 63) / 64) * ((g.No + 63) / 64) * nets;
         if (big >= 96) {       // enough 64x64 tiles to occupy the chip
             dim3 grid((g.Mo + 63) / 64, (g.No + 63) / 64, nets);

@@ -63,38 +63,45 @@ __device__ __forceinline__ void gae_walk_chain(int t, int n, const float *__rest
                        reinterpret_cast<uintptr_t>(out_lam_return)) & 15) == 0 &&
                      ((reinterpret_cast<uintptr_t>(terminated) | reinterpret_cast<uintptr_t>(truncated)) & 3) == 0;
     if (vec && s >= 3) {
-        float4 v4 = *reinterpret_cast<const float4 *>(values + s - 3), r4 = *reinterpret_cast<const float4 *>(reward + s - 3);
-        uint32_t te = *reinterpret_cast<const uint32_t *>(terminated + s - 3), tr = *reinterpret_cast<const uint32_t *>(truncated + s - 3);
-        while (true) {
-            // the next group's loads are issued before this group's recurrence (they do not depend on it)
-            const bool more = s >= 7;
-            float4 nv4 = v4, nr4 = r4;
-            uint32_t nte = 0, ntr = 0;
-            if (more) {
-                nv4 = *reinterpret_cast<const float4 *>(values + s - 7); nr4 = *reinterpret_cast<const float4 *>(reward + s - 7);
-                nte = *reinterpret_cast<const uint32_t *>(terminated + s - 7); ntr = *reinterpret_cast<const uint32_t *>(truncated + s - 7);
-            }
-            const float vv[4] = {v4.x, v4.y, v4.z, v4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
-            if (((te | tr) & 0xffffffffu) == 0) {                       // no episode end inside the group: four steps, two 16-byte stores
-                float g[4];
+        // PF groups of four are in flight per thread (a thread's chain is a dependent recurrence, so the memory
+        // parallelism has to come from prefetch depth x chains: at 33k chains one group in flight was 0.1 of the roofline)
+        constexpr int PF = 6;
+        float4 v4[PF], r4[PF];
+        uint32_t te[PF], tr[PF];
+        auto load = [&](int p, int top) {                               // group [top - 3, top]
+            v4[p] = *reinterpret_cast<const float4 *>(values + top - 3); r4[p] = *reinterpret_cast<const float4 *>(reward + top - 3);
+            te[p] = *reinterpret_cast<const uint32_t *>(terminated + top - 3); tr[p] = *reinterpret_cast<const uint32_t *>(truncated + top - 3);
+        };
 #pragma unroll
-                for (int u = 3; u >= 0; u--) g[u] = step(s - 3 + u, vv[u], rr[u], false, false);
-                *reinterpret_cast<float4 *>(out_gae + s - 3) = make_float4(g[0], g[1], g[2], g[3]);
-                *reinterpret_cast<float4 *>(out_lam_return + s - 3) =
-                    make_float4(__fadd_rn(g[0], vv[0]), __fadd_rn(g[1], vv[1]), __fadd_rn(g[2], vv[2]), __fadd_rn(g[3], vv[3]));
-            } else {
+        for (int p = 0; p < PF; p++)
+            if (s - 4 * p >= 3) load(p, s - 4 * p);
+        bool more = true;
+        while (more) {
 #pragma unroll
-                for (int u = 3; u >= 0; u--) {
-                    const bool term = ((te >> (8 * u)) & 0xffu) != 0, cut = term || ((tr >> (8 * u)) & 0xffu) != 0;
-                    if (cut) return;                                    // the next chain's head
-                    const float g = step(s - 3 + u, vv[u], rr[u], false, false);
-                    out_gae[s - 3 + u] = g;
-                    out_lam_return[s - 3 + u] = __fadd_rn(g, vv[u]);
+            for (int p = 0; p < PF; p++) {
+                if (s < 3) { more = false; break; }
+                const float vv[4] = {v4[p].x, v4[p].y, v4[p].z, v4[p].w}, rr[4] = {r4[p].x, r4[p].y, r4[p].z, r4[p].w};
+                const uint32_t cte = te[p], ctr = tr[p];
+                if (s - 4 * PF >= 3) load(p, s - 4 * PF);               // refill the slot: independent of the recurrence below
+                if ((cte | ctr) == 0) {                                 // no episode end inside the group: four steps, two 16-byte stores
+                    float g[4];
+#pragma unroll
+                    for (int u = 3; u >= 0; u--) g[u] = step(s - 3 + u, vv[u], rr[u], false, false);
+                    *reinterpret_cast<float4 *>(out_gae + s - 3) = make_float4(g[0], g[1], g[2], g[3]);
+                    *reinterpret_cast<float4 *>(out_lam_return + s - 3) =
+                        make_float4(__fadd_rn(g[0], vv[0]), __fadd_rn(g[1], vv[1]), __fadd_rn(g[2], vv[2]), __fadd_rn(g[3], vv[3]));
+                } else {
+#pragma unroll
+                    for (int u = 3; u >= 0; u--) {
+                        const bool cut = (((cte | ctr) >> (8 * u)) & 0xffu) != 0;
+                        if (cut) return;                                // the next chain's head
+                        const float g = step(s - 3 + u, vv[u], rr[u], false, false);
+                        out_gae[s - 3 + u] = g;
+                        out_lam_return[s - 3 + u] = __fadd_rn(g, vv[u]);
+                    }
                 }
+                s -= 4;
             }
-            s -= 4;
-            if (!more) break;
-            v4 = nv4; r4 = nr4; te = nte; tr = ntr;
         }
     }
     for (; s >= 0; s--) {                                               // the oldest 0..3 transitions (or unaligned arrays)

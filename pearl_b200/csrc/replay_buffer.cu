@@ -23,6 +23,8 @@ using namespace prl;
 extern "C" int prl_abi_version(void) { return PRL_ABI_VERSION; }
 extern "C" const char *prl_last_error(void) { return g_err; }
 
+namespace prl { cudaError_t gemm_tc_prepare(); }   // gemm_tc.cu: opt the tensor-core contraction kernels into > 48 KB of shared memory
+
 extern "C" int prl_init(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -36,6 +38,7 @@ extern "C" int prl_init(int device) {
     if (p.major != 10)
         return fail(PRL_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
                     device, p.major, p.minor);
+    PRL_CUDA(prl::gemm_tc_prepare());
     return PRL_OK;
 }
 

@@ -38,11 +38,9 @@ _lib.check(ls[0]._libh.prl_dqn_set_profile(ls[0]._handle, C.c_void_p(st.data_ptr
 grp.learn()
 torch.cuda.synchronize()
 s = st.cpu()[4:].double()
-names = ["soft upd + barrier A", "target layer 1", "all-actions", "online layer 1 (+h1)", "L2 + loss + dH1", "barrier B + zero", "weight-grad passes", "AdamW"]
+names = ["row scalars + soft upd", "load target weights", "target layer 1 (2 tiles)", "all-actions (32 tiles)", "load online weights",
+         "online layer 1", "tile0: fwd L2 + dZ2 + dH1", "rest (weight grads t0, tile1 all)", "AdamW"]
 tot = (s[1:, 0] - s[:-1, 0]).mean()
-print(f"{tot:.0f} clk/round (CTA 0, group 0)")
+print(f"{tot:.0f} clk/round (CTA 0 with {R} learners resident)")
 for i, n in enumerate(names):
-    print(f"  {n:28s} {(s[:, i+1]-s[:, i]).mean():10.0f} clk")
-d = lambda a, b: (s[:, a] - s[:, b]).mean()
-print(f"  AdamW region: next row + chunks {d(9,7):.0f} | G1 part {d(10,9):.0f} | G2 / W3 part {d(11,10):.0f} | rows_sync {d(12,11):.0f} | smalls {d(8,12):.0f}")
-print(f"  action slot 2: epilogue(0)+loop {d(13,2):.0f} since phase start | wait MMA {d(14,13):.0f} | build + publish {d(15,14):.0f}")
+    print(f"  {n:36s} {(s[:, i+1]-s[:, i]).mean():10.0f} clk")
