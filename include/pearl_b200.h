@@ -483,6 +483,10 @@ int prl_get_contraction_engine(void);
 int prl_test_contraction(int op, int engine, int M, int N, int K, const float *a, const float *b, const float *a2, int split,
                          const float *bias, const float *mask, int relu, int accumulate, float *c, float *c_tail, int nets,
                          void *stream);
+/* Developer profiling of the tcgen05 contraction: device int64[33][8] receiving SM-clock stamps of CTA 0 (per 32-deep
+ * chunk: loader warp 0 at iteration start / loads issued / stage free / tile stored, issuer at operands ready / MMAs
+ * issued) for the following prl_test_contraction calls; NULL = off. */
+int prl_test_contraction_stamps(long long *stamps_dev);
 
 #ifdef __cplusplus
 }

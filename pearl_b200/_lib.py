@@ -155,6 +155,7 @@ _SIGNATURES = {
     "prl_set_contraction_engine": (C.c_int, [C.c_int]),
     "prl_get_contraction_engine": (C.c_int, []),
     "prl_test_contraction": (C.c_int, [C.c_int] * 5 + [_P, _P, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "prl_test_contraction_stamps": (C.c_int, [_P]),
     "prl_dqn_last_launch_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                            C.POINTER(C.c_int32)]),
 }

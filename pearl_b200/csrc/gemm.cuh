@@ -45,6 +45,7 @@ struct GemmArgs {
     int relu;                                                   // max(., 0)
     const float *mask; int ldm; long long mask_net_stride;     // keep only where mask[i][j] > 0
     int accumulate;                                             // C += (before relu / mask)
+    long long *stamps;                                          // developer profiling of k_gemm_tc (CTA 0): [chunk][8] SM clocks
 };
 
 constexpr int GK = 32;   // contraction chunk
@@ -157,9 +158,11 @@ cudaError_t gemm_tc_prepare();
 struct GemmLauncher {
     cudaStream_t st;
     int count = 0;
+    long long *stamps = nullptr;
     int engine = -1;   // -1: library default (prl_set_contraction_engine); 0: SIMT tiles; 1 / 64 / 32: tcgen05 tiles
     template <bool AO, bool BO>
     void run(const GemmArgs &g, int nets) {
+        if (stamps) { GemmArgs gs = g; gs.stamps = stamps; if (gemm_tc_launch(gs, nets, AO, BO, st, engine)) { count++; return; } }
         if (gemm_tc_launch(g, nets, AO, BO, st, engine)) { count++; return; }
         const long long big = (long long)((g.Mo + 63) / 64) * ((g.No + 63) / 64) * nets;
         if (big >= 96) {       // enough 64x64 tiles to occupy the chip

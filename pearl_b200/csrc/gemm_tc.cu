@@ -23,7 +23,11 @@ int g_contraction_engine = 1;   // 1: tcgen05 tiles, 0: SIMT tiles (prl_set_cont
 
 namespace {
 
-constexpr int TM = 128, GKT = 32, LBO = 144, SBO = 8 * LBO, NSTAGE = 3, NSET = 3, NTHR = 256;
+constexpr int TM = 128, GKT = 32, LBO = 144, SBO = 8 * LBO, NSTAGE = 3, NSET = 3, NLOAD = 256, NTHR = NLOAD + 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
 
 // which (row of the tile, 16-byte K chunk) a thread's slot u covers.  XO: the Mat's rows are the tile's rows (features are
 // contracted, contiguous along k): 8 lanes read one row's 128 contiguous bytes.  !XO: the Mat's rows are contracted
@@ -40,131 +44,231 @@ __device__ __forceinline__ void slot_coords(int u, int w, int lane, int &r, int 
     }
 }
 
+// One operand (ROWS x 32 per chunk) as seen by one loader thread.  Everything that does not change from chunk to chunk
+// is computed once.  Loads never need a predicate: indices are clamped into the operand (a tile row past the operand's
+// extent repeats its last row — its products land in rows / columns of C that the epilogue never stores — and an index past
+// the end of the contraction axis repeats the last one and is zeroed when the tile is stored).  The loop body is kept
+// small on purpose: the first version inlined four paths per operand and ran out of the instruction cache at ~10 clocks
+// per instruction.
 template <int ROWS, bool XO>
-__device__ __forceinline__ void fetch_op(const Mat &m, int z, int out0, int out_lim, int Kc, int c, int w, int lane,
-                                         float (&reg)[ROWS / 32][4]) {
+struct Operand {
+    static constexpr int S = ROWS / 32;
+    const Mat &m;
+    int Kc, kc4;                // contraction length; XO: this thread's 16-byte chunk (floats) inside a 32-deep chunk
+    const float *zb1, *zb2;     // part bases with the network offset applied (zb2 also with -split)
+    int off1[S], off2[S];       // XO: float offset of the slot's row in part 1 / part 2
+    int kcu[S];                 // !XO: first contraction index of slot u inside a chunk
+    int soff[S];                // byte offset of the slot's 16-byte chunk inside the UMMA tile
+    const float *fbase;         // !XO: this thread's feature column
+    int fld;                    // !XO: its row pitch
+    bool isone, vec1, vec2;
+
+    __device__ __forceinline__ Operand(const Mat &m_, int z, int out0, int out_lim, int Kc_, int w, int lane) : m(m_), Kc(Kc_) {
+        zb1 = m.p1 + z * m.net_stride1;
+        zb2 = m.p2 + z * m.net_stride2 - m.split;
+        fbase = zb1; fld = 0; isone = false; kc4 = 0; vec1 = vec2 = false;
 #pragma unroll
-    for (int u = 0; u < ROWS / 32; u++) {
-        int r, kc;
-        slot_coords<ROWS, XO>(u, w, lane, r, kc);
-        const int out = out0 + r;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int con = c * GKT + kc * 4 + e;
-            const int row = XO ? out : con, f = XO ? con : out;
-            const bool ld = out < out_lim && con < Kc && f != m.ones_at;
-            reg[u][e] = __ldg(ld ? m.addr(row, f, z) : m.p1);   // unconditional loads: all of a chunk's are in flight together
+        for (int u = 0; u < S; u++) {
+            int r, kc;
+            slot_coords<ROWS, XO>(u, w, lane, r, kc);
+            soff[u] = (r >> 3) * SBO + kc * LBO + (r & 7) * 16;
+            kcu[u] = kc * 4;
+            const int row = min(out0 + r, out_lim - 1);
+            off1[u] = XO ? row * m.ld1 : 0;
+            off2[u] = XO ? row * m.ld2 : 0;
+            if (XO) kc4 = kc * 4;
+        }
+        if (XO) {
+            vec1 = ((reinterpret_cast<uintptr_t>(zb1) & 15) | (m.ld1 & 3)) == 0;
+            vec2 = m.p2 != nullptr && ((reinterpret_cast<uintptr_t>(zb2) & 15) | (m.ld2 & 3)) == 0;
+        } else {
+            int r, kc;
+            slot_coords<ROWS, XO>(0, w, lane, r, kc);
+            const int out = out0 + r;
+            isone = out == m.ones_at && out < out_lim;
+            int f = min(out, out_lim - 1);
+            if (f == m.ones_at) f = 0;                      // any valid address: the value is replaced by 1.0 / never used
+            fbase = f < m.split ? zb1 + f : zb2 + f;
+            fld = f < m.split ? m.ld1 : m.ld2;
         }
     }
-}
-
-template <int ROWS, bool XO>
-__device__ __forceinline__ void store_op(const Mat &m, int out0, int out_lim, int Kc, int c, int w, int lane,
-                                         const float (&reg)[ROWS / 32][4], unsigned char *hi, unsigned char *lo) {
-#pragma unroll
-    for (int u = 0; u < ROWS / 32; u++) {
-        int r, kc;
-        slot_coords<ROWS, XO>(u, w, lane, r, kc);
-        const int out = out0 + r;
-        float v[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int con = c * GKT + kc * 4 + e;
-            const int f = XO ? con : out;
-            const bool ok = out < out_lim && con < Kc;
-            v[e] = ok ? (f == m.ones_at ? 1.f : reg[u][e]) : 0.f;
-            l[e] = v[e] - __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);   // the tensor core truncates hi itself
-        }
-        const int off = (r >> 3) * SBO + kc * LBO + (r & 7) * 16;
-        *reinterpret_cast<float4 *>(hi + off) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    // XO: chunk c lies inside one source, away from the end of the contraction axis and the ones column
+    __device__ __forceinline__ bool interior(int f0) const {
+        return f0 + GKT <= Kc && (f0 + GKT <= m.split || f0 >= m.split) && !(m.ones_at >= f0 && m.ones_at < f0 + GKT);
     }
-}
+    __device__ __forceinline__ void fetch(int c, float (&reg)[S][4]) const {
+        const int f0 = c * GKT;
+        if (XO) {
+            const bool second = f0 >= m.split;
+            if (interior(f0) && (second ? vec2 : vec1)) {
+                const float *base = (second ? zb2 : zb1) + f0 + kc4;
+#pragma unroll
+                for (int u = 0; u < S; u++) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(base + (second ? off2[u] : off1[u])));
+                    reg[u][0] = q.x; reg[u][1] = q.y; reg[u][2] = q.z; reg[u][3] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    int f = min(f0 + kc4 + e, Kc - 1);
+                    if (f == m.ones_at) f = 0;
+                    const bool sec = f >= m.split;
+                    const float *base = (sec ? zb2 : zb1) + f;
+#pragma unroll
+                    for (int u = 0; u < S; u++) reg[u][e] = __ldg(base + (sec ? off2[u] : off1[u]));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < S; u++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) reg[u][e] = __ldg(fbase + (size_t)min(f0 + kcu[u] + e, Kc - 1) * fld);
+        }
+    }
+    // split into hi (the value itself: the tensor core truncates) / lo and store as 16-byte chunks of the UMMA tiles
+    __device__ __forceinline__ void store(int c, const float (&reg)[S][4], unsigned char *hi, unsigned char *lo) const {
+        const int f0 = c * GKT;
+        const bool edge = XO ? !interior(f0) : f0 + GKT > Kc;
+#pragma unroll
+        for (int u = 0; u < S; u++) {
+            float v[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                v[e] = (!XO && isone) ? 1.f : reg[u][e];
+                if (edge) {
+                    const int con = f0 + (XO ? kc4 : kcu[u]) + e;
+                    if (XO && con == m.ones_at) v[e] = 1.f;
+                    if (con >= Kc) v[e] = 0.f;
+                }
+                l[e] = v[e] - __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+            }
+            *reinterpret_cast<float4 *>(hi + soff[u]) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(lo + soff[u]) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+    }
+};
 
+// warps 0-7: loaders + epilogue; warp 8: TMEM owner, one lane issues the MMAs.  288 threads put three warps on one
+// sub-partition, which caps the kernel at 168 registers per thread.
 template <int TN, bool AO, bool BO>
-__global__ void __launch_bounds__(NTHR, 1) k_gemm_tc(const GemmArgs g) {
+__global__ void __maxnreg__(168) k_gemm_tc(const GemmArgs g) {
     extern __shared__ __align__(128) unsigned char dsm[];
-    __shared__ __align__(8) uint64_t bar[NSTAGE + 1];
+    __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE], done;
     __shared__ uint32_t tmem_slot;
     constexpr int A_B = (TM / 8) * SBO, B_B = (TN / 8) * SBO, STAGE_B = 2 * A_B + 2 * B_B;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, z = blockIdx.z;
     const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
-
-    if (w == 0) umma::tmem_alloc(&tmem_slot, TN);
-    if (tid == 32)
-        for (int b = 0; b <= NSTAGE; b++) umma::mbar_init(&bar[b], 1);
     const int nch = (g.Kc + GKT - 1) / GKT;
-    float ra[NSET][TM / 32][4], rb[NSET][TN / 32][4];
-#pragma unroll
-    for (int p = 0; p < NSET - 1; p++)
-        if (p < nch) {
-            fetch_op<TM, AO>(g.A, z, i0, g.Mo, g.Kc, p, w, lane, ra[p]);
-            fetch_op<TN, BO>(g.B, z, j0, g.No, g.Kc, p, w, lane, rb[p]);
-        }
-    umma::fence_before_thread_sync();
-    __syncthreads();
-    umma::fence_after_thread_sync();
-    const uint32_t tmem = tmem_slot;
+    const bool prof = g.stamps != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && z == 0 && lane == 0 && (w == 0 || w == 8);
 
-    for (int c0 = 0; c0 < nch; c0 += NSET) {
-#pragma unroll
-        for (int u = 0; u < NSET; u++) {
-            const int c = c0 + u;
-            if (c < nch) {
-            if (c + NSET - 1 < nch) {
-                fetch_op<TM, AO>(g.A, z, i0, g.Mo, g.Kc, c + NSET - 1, w, lane, ra[(u + NSET - 1) % NSET]);
-                fetch_op<TN, BO>(g.B, z, j0, g.No, g.Kc, c + NSET - 1, w, lane, rb[(u + NSET - 1) % NSET]);
-            }
-            static_assert(NSET == NSTAGE, "stage index == register set index");
-            if (c >= NSTAGE) umma::mbar_wait(&bar[u], ((c / NSTAGE) - 1) & 1);   // the MMAs that read this stage are done
-            unsigned char *st = dsm + u * STAGE_B;
-            store_op<TM, AO>(g.A, i0, g.Mo, g.Kc, c, w, lane, ra[u], st, st + A_B);
-            store_op<TN, BO>(g.B, j0, g.No, g.Kc, c, w, lane, rb[u], st + 2 * A_B, st + 2 * A_B + B_B);
-            umma::fence_async_smem();
-            __syncthreads();
-            if (tid == 0) {
+    if (w == 8) {
+        umma::tmem_alloc(&tmem_slot, TN);
+        if (lane == 0) {
+            for (int b = 0; b < NSTAGE; b++) { umma::mbar_init(&full[b], NLOAD / 32); umma::mbar_init(&empty[b], 1); }
+            umma::mbar_init(&done, 1);
+        }
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        umma::fence_after_thread_sync();
+        if (lane == 0) {
+            const uint32_t tmem = tmem_slot, idesc = umma::make_idesc_tf32(TM, TN);
+            const uint64_t dproto = umma::make_desc2(0, LBO, SBO);
+            const uint32_t base = umma::smem_u32(dsm);
+            for (int c = 0; c < nch; c++) {
+                const int s = c % NSTAGE;
+                umma::mbar_wait(&full[s], (c / NSTAGE) & 1);
+                if (prof && c < 32) g.stamps[c * 8 + 5] = clock64();
                 umma::fence_after_thread_sync();
-                const uint32_t a = umma::smem_u32(st);
-                const umma::Tile ah{a, LBO, SBO}, al{a + A_B, LBO, SBO}, bh{a + 2 * A_B, LBO, SBO}, bl{a + 2 * A_B + B_B, LBO, SBO};
-                umma::gemm3(tmem, ah, al, bh, bl, TM, TN, GKT, c > 0);
-                umma::mma_commit(&bar[u]);
-            }
-            }
-        }
-    }
-    if (tid == 0) umma::mma_commit(&bar[NSTAGE]);
-    umma::mbar_wait(&bar[NSTAGE], 0);
-    umma::fence_after_thread_sync();
-
-    const int q = w & 3, h = w >> 2;
-    if (h * 32 < TN) {
-        float v[32];
-        umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), v);
-        float *tb = reinterpret_cast<float *>(dsm) + w * (32 * 33);   // the stages are free: every MMA has completed
+                const uint32_t a = (base + s * STAGE_B) >> 4;
+                const uint64_t ah = dproto + a, al = ah + (A_B >> 4), bh = al + (A_B >> 4), bl = bh + (B_B >> 4);
 #pragma unroll
-        for (int t = 0; t < 32; t++) tb[lane * 33 + t] = v[t];
+                for (int ks = 0; ks < GKT / 8; ks++) {
+                    const uint64_t o = (uint64_t)(ks * ((2 * LBO) >> 4));
+                    umma::mma_tf32(tmem, al + o, bh + o, idesc, c > 0 || ks > 0);   // small terms first
+                    umma::mma_tf32(tmem, ah + o, bl + o, idesc, true);
+                    umma::mma_tf32(tmem, ah + o, bh + o, idesc, true);
+                }
+                umma::mma_commit(&empty[s]);      // arrives when the MMAs that read stage s have completed
+                if (prof && c < 32) g.stamps[c * 8 + 6] = clock64();
+            }
+            umma::mma_commit(&done);
+        }
         __syncwarp();
-        const int j = j0 + h * 32 + lane;
-        if (j < g.No) {
-            const float bj = g.bias ? __ldg(g.bias + z * g.bias_net_stride + j) : 0.f;
-            const bool tail = g.C_tail && j == g.tail_col;
-            for (int rr = 0; rr < 32; rr++) {
-                const int i = i0 + q * 32 + rr;
-                if (i >= g.Mo) break;
-                float x = tb[rr * 33 + lane];
-                if (tail) { g.C_tail[z * g.tail_net_stride + i] = x; continue; }
-                float *dst = g.C + z * g.c_net_stride + (size_t)i * g.ldc + j;
-                if (g.bias) x += bj;
-                if (g.accumulate) x += *dst;
-                if (g.relu) x = fmaxf(x, 0.f);
-                if (g.mask && !(__ldg(g.mask + z * g.mask_net_stride + (size_t)i * g.ldm + j) > 0.f)) x = 0.f;
-                *dst = x;
+    } else {
+        const Operand<TM, AO> opA(g.A, z, i0, g.Mo, g.Kc, w, lane);
+        const Operand<TN, BO> opB(g.B, z, j0, g.No, g.Kc, w, lane);
+        float ra[NSET][TM / 32][4], rb[NSET][TN / 32][4];
+#pragma unroll
+        for (int p = 0; p < NSET - 1; p++)
+            if (p < nch) { opA.fetch(p, ra[p]); opB.fetch(p, rb[p]); }
+        if (prof) g.stamps[32 * 8 + 2] = clock64();
+        __syncthreads();   // barriers initialised, TMEM allocated
+        if (prof) g.stamps[32 * 8 + 3] = clock64();
+        static_assert(NSET == NSTAGE, "stage index == register set index");
+        for (int c0 = 0; c0 < nch; c0 += NSET) {
+#pragma unroll
+            for (int u = 0; u < NSET; u++) {
+                const int c = c0 + u;
+                if (c < nch) {
+                    if (prof && c < 32) g.stamps[c * 8 + 0] = clock64();
+                    if (c + NSET - 1 < nch) {       // two chunks ahead of the one being stored
+                        opA.fetch(c + NSET - 1, ra[(u + NSET - 1) % NSET]);
+                        opB.fetch(c + NSET - 1, rb[(u + NSET - 1) % NSET]);
+                    }
+                    if (prof && c < 32) g.stamps[c * 8 + 1] = clock64();
+                    if (c >= NSTAGE) umma::mbar_wait(&empty[u], ((c / NSTAGE) - 1) & 1);
+                    if (prof && c < 32) g.stamps[c * 8 + 2] = clock64();
+                    unsigned char *st = dsm + u * STAGE_B;
+                    opA.store(c, ra[u], st, st + A_B);
+                    opB.store(c, rb[u], st + 2 * A_B, st + 2 * A_B + B_B);
+                    if (prof && c < 32) g.stamps[c * 8 + 4] = clock64();
+                    umma::fence_async_smem();       // generic-proxy writes -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (prof && c < 32) g.stamps[c * 8 + 3] = clock64();
+                    if (lane == 0) mbar_arrive(&full[u]);
+                }
             }
         }
+        umma::mbar_wait(&done, 0);
+        if (prof) g.stamps[32 * 8 + 0] = clock64();
+        umma::fence_after_thread_sync();
+
+        const uint32_t tmem = tmem_slot;
+        const int q = w & 3, h = w >> 2;
+        if (h * 32 < TN) {
+            float v[32];
+            umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), v);
+            float *tb = reinterpret_cast<float *>(dsm) + w * (32 * 33);   // the stages are free: every MMA has completed
+#pragma unroll
+            for (int t = 0; t < 32; t++) tb[lane * 33 + t] = v[t];
+            __syncwarp();
+            const int j = j0 + h * 32 + lane;
+            if (j < g.No) {
+                const float bj = g.bias ? __ldg(g.bias + z * g.bias_net_stride + j) : 0.f;
+                const bool tail = g.C_tail && j == g.tail_col;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; rr++) {
+                    const int i = i0 + q * 32 + rr;
+                    if (i >= g.Mo) break;
+                    float x = tb[rr * 33 + lane];
+                    if (tail) { g.C_tail[z * g.tail_net_stride + i] = x; continue; }
+                    float *dst = g.C + z * g.c_net_stride + (size_t)i * g.ldc + j;
+                    if (g.bias) x += bj;
+                    if (g.accumulate) x += *dst;
+                    if (g.relu) x = fmaxf(x, 0.f);
+                    if (g.mask && !(__ldg(g.mask + z * g.mask_net_stride + (size_t)i * g.ldm + j) > 0.f)) x = 0.f;
+                    *dst = x;
+                }
+            }
+        }
+        umma::fence_before_thread_sync();
+        if (prof) g.stamps[32 * 8 + 1] = clock64();
     }
-    umma::fence_before_thread_sync();
     __syncthreads();
-    if (w == 0) umma::tmem_dealloc(tmem, TN);
+    if (w == 8) {
+        umma::fence_after_thread_sync();
+        umma::tmem_dealloc(tmem_slot, TN);
+    }
 }
 
 template <int TN>
@@ -227,15 +331,19 @@ extern "C" int prl_get_contraction_engine(void) { return prl::g_contraction_engi
 //   op 1  dx[M x K] (+)= dy W  (masked)       a = dy [M x N], b = W [N x K], mask [M x K]
 //   op 2  dW[N x K] = dy^T x, db = dy^T 1     a = dy [M x N], b = x [M x K] (or split with a2), c_tail = db [N]
 // `nets` stacked problems are laid out contiguously in every operand.
+static long long *g_test_stamps = nullptr;
+/* developer profiling: device int64[33][8] receiving SM-clock stamps of CTA 0 of the next prl_test_contraction calls */
+extern "C" int prl_test_contraction_stamps(long long *stamps_dev) { g_test_stamps = stamps_dev; return PRL_OK; }
+
 extern "C" int prl_test_contraction(int op, int engine, int M, int N, int K, const float *a, const float *b, const float *a2, int split,
                                     const float *bias, const float *mask, int relu, int accumulate, float *c, float *c_tail, int nets,
                                     void *stream) {
     using namespace prl;
     PRL_REQUIRE(op >= 0 && op <= 2 && M > 0 && N > 0 && K > 0 && a && b && c && nets >= 1, "bad argument");
-    PRL_CUDA(gemm_tc_prepare());
-    GemmLauncher L;
+    GemmLauncher L;   // prl_init has prepared the kernels
     L.st = (cudaStream_t)stream;
     L.engine = engine;
+    L.stamps = g_test_stamps;
     const long long MK = (long long)M * K, MN = (long long)M * N, NK = (long long)N * K;
     if (op == 0) {
         Mat X = a2 ? mat2(a, split, split, a2, K - split, (long long)M * split, (long long)M * (K - split)) : mat(a, K, MK);

@@ -1,6 +1,6 @@
 """Developer tool: time the learners' contraction shapes on the SIMT tiles and on the tcgen05 tiles (CUDA events around
-`reps` back-to-back launches on one stream, so the figure is the issue-to-issue time of a launch-bound kernel — what a
-CUDA-graph replay of a learner round sees).  python tools/gemm_bench.py [reps]"""
+replays of a CUDA graph of 20 launches, so the figure is the device-side issue-to-issue time — what the CUDA-graph
+replay of a learner round sees).  python tools/gemm_bench.py [reps]"""
 import ctypes as C
 import os
 import sys
@@ -44,19 +44,30 @@ def main():
         flops = 2.0 * M * N * K * nets
         out = []
         for engine in (0, 64, 32):
+            side = torch.cuda.Stream()
+            sp = C.c_void_p(side.cuda_stream)
+
             def run():
                 _lib.check(lib.prl_test_contraction(op, engine, M, N, K, p(a), p(b), None, 0, p(bias), None, 1 if op == 0 else 0, 0,
-                                                    p(c), p(ct), nets, None))
-            for _ in range(5):
-                run()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                run()
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / reps
+                                                    p(c), p(ct), nets, sp))
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    run()
+                side.synchronize()
+                graph = torch.cuda.CUDAGraph()       # 20 launches per replay: device-side issue-to-issue time, no host in the loop
+                with torch.cuda.graph(graph, stream=side):
+                    for _ in range(20):
+                        run()
+                graph.replay()
+                side.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(side)
+                for _ in range(max(reps // 20, 1)):
+                    graph.replay()
+                e1.record(side)
+                side.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (max(reps // 20, 1) * 20)
             out.append(f"{['simt', 'tc64', 'tc32'][(0, 64, 32).index(engine)]} {us:7.2f} us ({flops / us * 1e-6:7.2f} TF/s)")
         print(f"{name:42s} " + "  ".join(out), flush=True)
 
