@@ -470,16 +470,18 @@ int prl_test_umma_gemm2(const float *a_dev, const float *b_dev, float *draw_dev,
 
 /* ---- contraction engine of the actor-critic learners (SAC, PPO, TD3 / DDPG) --------------------------------
  * The dense layers of those learners (the torch matmuls of pearl/neural_networks/common/utils.py:mlp_block as used by
- * actor_networks.py / value_networks.py, forward and autograd backward) run as 3xTF32 tcgen05 tiles (engine 1, default)
- * or as fp32 SIMT tiles (engine 0).  Process-wide; read when a learner's round is launched or captured into its CUDA
- * graph, so set it before the first learn() of a learner. */
+ * actor_networks.py / value_networks.py, forward and autograd backward) run as 3xTF32 tcgen05 tiles or as fp32 SIMT tiles:
+ * engine 1 (default) picks per product whichever is faster on a B200 (profiles/r2_gemm_tc.md), 0 = SIMT only,
+ * 2 = tcgen05 always.  Process-wide; read when a learner's round is launched or captured into its CUDA graph, so set it
+ * before the first learn() of a learner. */
 int prl_set_contraction_engine(int engine);
 int prl_get_contraction_engine(void);
 /* Test hook: one contraction of the three kinds the learners use, `nets` stacked problems contiguous in every operand.
  *   op 0  c[M x N]   = act(x W^T + bias)      a = x [M x K] (or [M x split] and a2 = [M x (K - split)]), b = W [N x K]
  *   op 1  c[M x K] (+)= dy W, masked          a = dy [M x N], b = W [N x K], mask [M x K] (keep where mask > 0)
  *   op 2  c[N x K]   = dy^T x, c_tail = dy^T 1  a = dy [M x N], b = x [M x K] (or split with a2)
- * engine: -1 library default, 0 SIMT, 1 tcgen05, 64 / 32 tcgen05 with that tile width. */
+ * engine: -1 library default, 0 SIMT, 1 automatic, 2 tcgen05 always; 64 / 32: the shared-memory-operand form with that tile
+ * width, 164 / 132: the tensor-memory-operand form with tile width 64 / 32. */
 int prl_test_contraction(int op, int engine, int M, int N, int K, const float *a, const float *b, const float *a2, int split,
                          const float *bias, const float *mask, int relu, int accumulate, float *c, float *c_tail, int nets,
                          void *stream);

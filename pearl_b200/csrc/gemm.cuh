@@ -51,13 +51,36 @@ struct GemmArgs {
 constexpr int GK = 32;   // contraction chunk
 
 // AO / BO: true = the Mat's ROW index is the output index (features are contracted); false = rows are contracted
-// MR x 4 outputs per thread: MR = 4 for the big tiles, MR = 2 doubles the warps of the small (latency-bound) tiles
-template <int TM, int TN, int MR, bool AO, bool BO>
-__global__ void __launch_bounds__((TM / MR) * (TN / 4)) k_gemm(const GemmArgs g) {
+// MR x 4 outputs per thread: MR = 4 for the big tiles, MR = 2 doubles the warps of the small (latency-bound) tiles.
+// KS > 1 ("slice-K"): KS groups of NT threads walk interleaved chunks of the contraction axis of the SAME tile and their
+// partial sums are added in a fixed order through shared memory.  The learners' small products (batch 256-512, widths
+// 64-256) fill one CTA per SM at most and a CTA's chunk loop is a chain of global-load latencies; KS = 4 puts four such
+// chains on the SM at once without any global workspace.
+__device__ __forceinline__ void gemm_emit(const GemmArgs &g, int z, int i, int j, float v) {
+    if (g.C_tail && j == g.tail_col) { g.C_tail[z * g.tail_net_stride + i] = v; return; }
+    float *dst = g.C + z * g.c_net_stride + (size_t)i * g.ldc + j;
+    if (g.bias) v += __ldg(g.bias + z * g.bias_net_stride + j);
+    if (g.accumulate) v += *dst;
+    if (g.relu) v = fmaxf(v, 0.f);
+    if (g.mask && !(__ldg(g.mask + z * g.mask_net_stride + (size_t)i * g.ldm + j) > 0.f)) v = 0.f;
+    *dst = v;
+}
+
+template <int TM, int TN, int MR, int KS, bool AO, bool BO>
+__global__ void __launch_bounds__((TM / MR) * (TN / 4) * KS) k_gemm(const GemmArgs g) {
+    static_assert(KS == 1 || KS == 4, "slice_sync names four barriers");
     constexpr int NT = (TM / MR) * (TN / 4), LA = TM * GK / NT, LB = TN * GK / NT;
-    __shared__ __align__(16) float As[GK][TM + 4], Bs[GK][TN + 4];
-    const int tid = threadIdx.x, tx = tid % (TN / 4), ty = tid / (TN / 4), z = blockIdx.z;
+    __shared__ __align__(16) float As[KS][GK][TM + 4], Bs[KS][GK][TN + 4];
+    static_assert(KS == 1 || KS * TM * TN <= KS * GK * (TM + 4), "the slice sums are staged in As");
+    const int tid = threadIdx.x % NT, slice = threadIdx.x / NT, tx = tid % (TN / 4), ty = tid / (TN / 4), z = blockIdx.z;
     const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+    auto slice_sync = [&]() {
+        if (KS == 1) __syncthreads();
+        else if (slice == 0) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");   // literal ids: ptxas reserves all 16 otherwise
+        else if (slice == 1) asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
+        else if (slice == 2) asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory");
+        else asm volatile("bar.sync 4, %0;" ::"n"(NT) : "memory");
+    };
     float acc[MR][4];
 #pragma unroll
     for (int a = 0; a < MR; a++)
@@ -90,15 +113,15 @@ __global__ void __launch_bounds__((TM / MR) * (TN / 4)) k_gemm(const GemmArgs g)
         fetch_one(g.A, AO, i0, g.Mo, c0, fa_off, ra_off, RSA, ra, LA);
         fetch_one(g.B, BO, j0, g.No, c0, fb_off, rb_off, RSB, rb, LB);
     };
-    fetch(0);
-    for (int c0 = 0; c0 < g.Kc; c0 += GK) {
+    if (slice * GK < g.Kc) fetch(slice * GK);
+    for (int c0 = slice * GK; c0 < g.Kc; c0 += KS * GK) {
         {
             const int f = (AO ? c0 : i0) + fa_off, f_lim = AO ? g.Kc : g.Mo, row_lim = AO ? g.Mo : g.Kc, row0 = (AO ? i0 : c0) + ra_off;
             const bool one = f == g.A.ones_at && f < f_lim, f_ok = f < f_lim;
 #pragma unroll
             for (int u = 0; u < LA; u++) {
                 const float v = (f_ok && row0 + u * RSA < row_lim) ? (one ? 1.f : ra[u]) : 0.f;
-                if (AO) As[fa_off][ra_off + u * RSA] = v; else As[ra_off + u * RSA][fa_off] = v;
+                if (AO) As[slice][fa_off][ra_off + u * RSA] = v; else As[slice][ra_off + u * RSA][fa_off] = v;
             }
         }
         {
@@ -107,58 +130,70 @@ __global__ void __launch_bounds__((TM / MR) * (TN / 4)) k_gemm(const GemmArgs g)
 #pragma unroll
             for (int u = 0; u < LB; u++) {
                 const float v = (f_ok && row0 + u * RSB < row_lim) ? (one ? 1.f : rb[u]) : 0.f;
-                if (BO) Bs[fb_off][rb_off + u * RSB] = v; else Bs[rb_off + u * RSB][fb_off] = v;
+                if (BO) Bs[slice][fb_off][rb_off + u * RSB] = v; else Bs[slice][rb_off + u * RSB][fb_off] = v;
             }
         }
-        __syncthreads();
-        if (c0 + GK < g.Kc) fetch(c0 + GK);
+        slice_sync();
+        if (c0 + KS * GK < g.Kc) fetch(c0 + KS * GK);
 #pragma unroll
         for (int c = 0; c < GK; c++) {
             float av[MR];
             if constexpr (MR == 4) {
-                const float4 a = *reinterpret_cast<const float4 *>(&As[c][ty * 4]);
+                const float4 a = *reinterpret_cast<const float4 *>(&As[slice][c][ty * 4]);
                 av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
             } else {
-                const float2 a = *reinterpret_cast<const float2 *>(&As[c][ty * 2]);
+                const float2 a = *reinterpret_cast<const float2 *>(&As[slice][c][ty * 2]);
                 av[0] = a.x; av[1] = a.y;
             }
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[c][tx * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[slice][c][tx * 4]);
             const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int p = 0; p < MR; p++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
         }
-        __syncthreads();
+        slice_sync();
     }
+    if constexpr (KS == 1) {
 #pragma unroll
-    for (int p = 0; p < MR; p++) {
-        const int i = i0 + ty * MR + p;
-        if (i >= g.Mo) continue;
+        for (int p = 0; p < MR; p++) {
+            const int i = i0 + ty * MR + p;
+            if (i >= g.Mo) continue;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int j = j0 + tx * 4 + q;
-            if (j >= g.No) continue;
-            float v = acc[p][q];
-            if (g.C_tail && j == g.tail_col) { g.C_tail[z * g.tail_net_stride + i] = v; continue; }
-            float *dst = g.C + z * g.c_net_stride + (size_t)i * g.ldc + j;
-            if (g.bias) v += __ldg(g.bias + z * g.bias_net_stride + j);
-            if (g.accumulate) v += *dst;
-            if (g.relu) v = fmaxf(v, 0.f);
-            if (g.mask && !(__ldg(g.mask + z * g.mask_net_stride + (size_t)i * g.ldm + j) > 0.f)) v = 0.f;
-            *dst = v;
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + tx * 4 + q;
+                if (j < g.No) gemm_emit(g, z, i, j, acc[p][q]);
+            }
+        }
+    } else {
+        __syncthreads();                                           // every slice is done with As / Bs
+        float *red = &As[0][0][0];                                 // [KS][TM][TN]
+#pragma unroll
+        for (int p = 0; p < MR; p++)
+            *reinterpret_cast<float4 *>(red + ((size_t)slice * TM + ty * MR + p) * TN + tx * 4) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+        __syncthreads();
+        for (int o = threadIdx.x; o < TM * TN; o += NT * KS) {    // coalesced along j; slices added in the order 0, 1, ...
+            float v = red[o];
+#pragma unroll
+            for (int s2 = 1; s2 < KS; s2++) v += red[(size_t)s2 * TM * TN + o];
+            const int i = i0 + o / TN, j = j0 + o % TN;
+            if (i < g.Mo && j < g.No) gemm_emit(g, z, i, j, v);
         }
     }
 }
 
 // gemm_tc.cu: the same contraction on tcgen05 (3xTF32).  Returns false when the engine is off / the shape is not covered.
 bool gemm_tc_launch(const GemmArgs &g, int nets, bool ao, bool bo, cudaStream_t st, int engine);
+// the TS form (the 128-row operand in tensor memory); gs in the kernel's own orientation, see gemm_tc.cu
+bool gemm_ts_launch(const GemmArgs &gs, int nets, bool bo, bool swap, cudaStream_t st, int engine);
+void transpose_weights(int rows, int cols, int nets, const float *src, float *dst, cudaStream_t st);
 cudaError_t gemm_tc_prepare();
 
 struct GemmLauncher {
     cudaStream_t st;
     int count = 0;
     long long *stamps = nullptr;
+    bool fixed_order = false;   // SIMT tiles: never slice the contraction axis (a row's sum must not depend on the launch's shape)
     int engine = -1;   // -1: library default (prl_set_contraction_engine); 0: SIMT tiles; 1 / 64 / 32: tcgen05 tiles
     template <bool AO, bool BO>
     void run(const GemmArgs &g, int nets) {
@@ -167,10 +202,11 @@ struct GemmLauncher {
         const long long big = (long long)((g.Mo + 63) / 64) * ((g.No + 63) / 64) * nets;
         if (big >= 96) {       // enough 64x64 tiles to occupy the chip
             dim3 grid((g.Mo + 63) / 64, (g.No + 63) / 64, nets);
-            k_gemm<64, 64, 4, AO, BO><<<grid, 256, 0, st>>>(g);
-        } else {               // small problem: 4x the CTAs, 4 warps each (2 x 4 outputs per thread)
+            k_gemm<64, 64, 4, 1, AO, BO><<<grid, 256, 0, st>>>(g);
+        } else {               // small problem: 4x the CTAs, 4 warps each (2 x 4 outputs per thread), x 4 K slices
             dim3 grid((g.Mo + 31) / 32, (g.No + 31) / 32, nets);
-            k_gemm<32, 32, 2, AO, BO><<<grid, 128, 0, st>>>(g);
+            if (g.Kc > 2 * GK && !fixed_order) k_gemm<32, 32, 2, 4, AO, BO><<<grid, 512, 0, st>>>(g);
+            else k_gemm<32, 32, 2, 1, AO, BO><<<grid, 128, 0, st>>>(g);
         }
         count++;
     }
@@ -180,12 +216,17 @@ struct GemmLauncher {
         g.tail_col = -1;
         return g;
     }
-    // y[M x N] = act(x W^T + b)
+    // y[M x N] = act(x W^T + b).  Wt (optional): W transposed, [K x N] with row pitch ldwt — offered to the TS-form kernel
     void fwd(Mat X, int M, const float *W, int ldw, long long w_ns, const float *b, long long b_ns, int N, int K, bool relu, float *Y,
-             int ldy, long long y_ns, int nets = 1) {
+             int ldy, long long y_ns, int nets = 1, const float *Wt = nullptr, int ldwt = 0, long long wt_ns = 0) {
         GemmArgs g = base();
-        g.A = X; g.B = mat(W, ldw, w_ns);
         g.Mo = M; g.No = N; g.Kc = K; g.C = Y; g.ldc = ldy; g.c_net_stride = y_ns; g.bias = b; g.bias_net_stride = b_ns; g.relu = relu;
+        if (Wt) {                                        // D[n][m] = sum_k Wt[k][n] x[m][k]
+            GemmArgs t = g;
+            t.A = mat(Wt, ldwt, wt_ns); t.B = X; t.Mo = N; t.No = M; t.stamps = stamps;
+            if (gemm_ts_launch(t, nets, true, true, st, engine)) { count++; return; }
+        }
+        g.A = X; g.B = mat(W, ldw, w_ns);
         run<true, true>(g, nets);
     }
     // dx[M x Kx] (+)= dy[M x N] W[:, col0 : col0 + Kx]   (kept only where mask > 0)
@@ -196,6 +237,11 @@ struct GemmLauncher {
         g.B = mat(W + col0, ldw, w_ns);                  // B(out = k, c = n) = W[n][col0 + k]
         g.Mo = M; g.No = Kx; g.Kc = N; g.C = dX; g.ldc = ldx; g.c_net_stride = dx_ns;
         g.mask = mask; g.ldm = ldm; g.mask_net_stride = m_ns; g.accumulate = accumulate;
+        {                                                // D[k][m] = sum_n W[n][col0 + k] dy[m][n]
+            GemmArgs t = g;
+            t.A = g.B; t.B = g.A; t.Mo = Kx; t.No = M; t.stamps = stamps;
+            if (gemm_ts_launch(t, nets, true, true, st, engine)) { count++; return; }
+        }
         run<true, false>(g, nets);
     }
     // dW[N x K] = dy^T x ; db[N] = column sums of dy (x extended with a ones column)
@@ -207,6 +253,11 @@ struct GemmLauncher {
         g.B = X;                                         // B(out = k, c = m) = x[m][k]
         g.Mo = N; g.No = K + 1; g.Kc = M; g.C = dW; g.ldc = ldw; g.c_net_stride = dw_ns;
         g.C_tail = db; g.tail_col = K; g.tail_net_stride = db_ns;
+        {
+            GemmArgs t = g;
+            t.stamps = stamps;
+            if (gemm_ts_launch(t, nets, false, false, st, engine)) { count++; return; }
+        }
         run<false, false>(g, nets);
     }
 };

@@ -12,8 +12,12 @@
 //     to the stage's mbarrier, which is what the loaders wait on before they overwrite the stage three chunks later;
 //   * epilogue: tcgen05.ld of the accumulator (warp w: lanes 32(w%4).., columns 32(w/4)..), a per-warp transpose through
 //     shared memory so that bias / mask / accumulate reads and the C stores are coalesced along j.
-// The launch is latency-bound for the learners' shapes (batch 256-512, widths 64-256): what it buys over the SIMT
-// tiles is ~0.35 us per 32-deep chunk instead of ~1.2 us, see profiles/r2_gemm_tc.md.
+// What bounds it (profiles/r2_gemm_tc.md): not the tensor pipe (12 % active) and not shared memory (the TS form below, which
+// keeps the 128-row operand out of shared memory altogether, runs at the same speed) but the operand loads: a CTA moves
+// 24 KB from L2 per 32-deep chunk of its 128 x 64 tile, ~1500 clk per chunk alone and ~2800 clk with every SM busy, i.e.
+// 21 FLOP per byte at the ~2.5 TB/s the chip delivers to this access pattern = the measured 52 TFLOP/s on 65536 x 256 x
+// 256.  That is 2.1x the SIMT tiles on large products and a tie (or a loss) on the learners' own batch-256 / 512 products,
+// which is how gemm_tc_launch chooses.
 #include "gemm.cuh"
 #include "umma.cuh"
 
@@ -118,6 +122,18 @@ struct Operand {
                     for (int u = 0; u < S; u++) reg[u][e] = __ldg(base + (sec ? off2[u] : off1[u]));
                 }
             }
+        } else if (isone) {                      // the ones column (bias gradient): no load, the stored value is 1
+#pragma unroll
+            for (int u = 0; u < S; u++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) reg[u][e] = 1.f;
+        } else if (f0 + GKT <= Kc) {
+#pragma unroll
+            for (int u = 0; u < S; u++) {
+                const float *q = fbase + (size_t)(f0 + kcu[u]) * fld;
+#pragma unroll
+                for (int e = 0; e < 4; e++) reg[u][e] = __ldg(q + (size_t)e * fld);
+            }
         } else {
 #pragma unroll
             for (int u = 0; u < S; u++)
@@ -125,26 +141,61 @@ struct Operand {
                 for (int e = 0; e < 4; e++) reg[u][e] = __ldg(fbase + (size_t)min(f0 + kcu[u] + e, Kc - 1) * fld);
         }
     }
+    __device__ __forceinline__ bool edge(int c) const { return XO ? !interior(c * GKT) : c * GKT + GKT > Kc; }
+    // the value of element (slot u, e) of an EDGE chunk as the product sees it (ones column, zero past the contraction axis);
+    // in every other chunk it is the loaded value itself
+    __device__ __forceinline__ float edge_elem(int c, int u, int e, float loaded) const {
+        const int con = c * GKT + (XO ? kc4 : kcu[u]) + e;
+        float v = loaded;
+        if (XO && con == m.ones_at) v = 1.f;
+        if (con >= Kc) v = 0.f;
+        return v;
+    }
     // split into hi (the value itself: the tensor core truncates) / lo and store as 16-byte chunks of the UMMA tiles
     __device__ __forceinline__ void store(int c, const float (&reg)[S][4], unsigned char *hi, unsigned char *lo) const {
-        const int f0 = c * GKT;
-        const bool edge = XO ? !interior(f0) : f0 + GKT > Kc;
+        if (edge(c)) {                               // uniform branch, taken for at most two chunks of a product
+#pragma unroll
+            for (int u = 0; u < S; u++) {
+                float v[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    v[e] = edge_elem(c, u, e, reg[u][e]);
+                    l[e] = v[e] - __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
+                }
+                *reinterpret_cast<float4 *>(hi + soff[u]) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(lo + soff[u]) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+            return;
+        }
 #pragma unroll
         for (int u = 0; u < S; u++) {
-            float v[4], l[4];
+            float l[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                v[e] = (!XO && isone) ? 1.f : reg[u][e];
-                if (edge) {
-                    const int con = f0 + (XO ? kc4 : kcu[u]) + e;
-                    if (XO && con == m.ones_at) v[e] = 1.f;
-                    if (con >= Kc) v[e] = 0.f;
-                }
-                l[e] = v[e] - __uint_as_float(__float_as_uint(v[e]) & 0xffffe000u);
-            }
-            *reinterpret_cast<float4 *>(hi + soff[u]) = make_float4(v[0], v[1], v[2], v[3]);
+            for (int e = 0; e < 4; e++) l[e] = reg[u][e] - __uint_as_float(__float_as_uint(reg[u][e]) & 0xffffe000u);
+            *reinterpret_cast<float4 *>(hi + soff[u]) = make_float4(reg[u][0], reg[u][1], reg[u][2], reg[u][3]);
             *reinterpret_cast<float4 *>(lo + soff[u]) = make_float4(l[0], l[1], l[2], l[3]);
         }
+    }
+    // ROWS = 128, !XO only: this thread's 16 values of chunk c (tile row = 32 (w % 4) + lane, k = 16 (w / 4) .. + 16) go to
+    // tensor memory as the A operand of the TS-form MMA: hi at column a_col + 16 (w / 4), lo 32 columns further
+    __device__ __forceinline__ void store_tmem(int c, const float (&reg)[S][4], uint32_t taddr_hi) const {
+        static_assert(!XO || ROWS != 128, "TMEM operands are loaded with the lanes along the tile rows");
+        const bool is_edge = edge(c);
+        float v[16], l[16];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[u * 4 + e] = reg[u][e];
+        if (is_edge) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) v[u * 4 + e] = edge_elem(c, u, e, v[u * 4 + e]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) l[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xffffe000u);
+        umma::tmem_st16(taddr_hi, v);
+        umma::tmem_st16(taddr_hi + 32, l);
     }
 };
 
@@ -271,6 +322,146 @@ __global__ void __maxnreg__(168) k_gemm_tc(const GemmArgs g) {
     }
 }
 
+// ---- TS form: the A operand lives in tensor memory -----------------------------------------------------------------
+// The SS kernel above moves 120 KB through shared memory per 32-deep chunk of a 128 x 64 tile (48 KB of hi / lo stores and
+// 72 KB of operand reads by the 12 MMAs).  This form was written to test whether that is what bounds it — it is not: the two
+// run within 10 % of each other.  Here the 128-row operand never touches shared memory: it must be the operand whose Mat
+// has the tile rows along the contiguous axis ("rows contracted"), so that lane l of warp w loads row 32 (w % 4) + l for
+// 16 consecutive contraction indices with coalesced loads and writes hi / lo straight into its own TMEM lane
+// (tcgen05.st).  Shared memory only carries the TN-row operand: 16 KB of stores + 24 KB of MMA reads per chunk.
+//   nn.Linear forward     D[n][m] = sum_k Wt[k][n] x[m][k]     A = a transposed copy of W kept by the learner, SWAP
+//   backward-data         D[k][m] = sum_n W[n][k] dy[m][n]      A = W as stored, SWAP
+//   backward-weight       D[n][k] = sum_m dy[m][n] x[m][k]      A = dy as stored
+// SWAP: the accumulator is C transposed (lanes = C's column index): the epilogue stores straight from registers, coalesced.
+constexpr int TS_ACC_COLS = 64, TS_STAGE_COLS = 64, TS_TMEM_COLS = 256;
+
+template <int TN, bool BO, bool SWAP>
+__global__ void __maxnreg__(168) k_gemm_ts(const GemmArgs g) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE], done;
+    __shared__ uint32_t tmem_slot;
+    constexpr int B_B = (TN / 8) * SBO, STAGE_B = 2 * B_B;
+    static_assert(TN <= TS_ACC_COLS && TS_ACC_COLS + NSTAGE * TS_STAGE_COLS <= TS_TMEM_COLS, "TMEM column budget");
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, z = blockIdx.z;
+    const int a0 = blockIdx.x * TM, b0 = blockIdx.y * TN;
+    const int nch = (g.Kc + GKT - 1) / GKT;
+
+    if (w == 8) {
+        umma::tmem_alloc(&tmem_slot, TS_TMEM_COLS);
+        if (lane == 0) {
+            for (int b = 0; b < NSTAGE; b++) { umma::mbar_init(&full[b], NLOAD / 32); umma::mbar_init(&empty[b], 1); }
+            umma::mbar_init(&done, 1);
+        }
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        umma::fence_after_thread_sync();
+        if (lane == 0) {
+            const uint32_t tmem = tmem_slot, idesc = umma::make_idesc_tf32(TM, TN);
+            const uint64_t dproto = umma::make_desc2(0, LBO, SBO);
+            const uint32_t base = umma::smem_u32(dsm);
+            for (int c = 0; c < nch; c++) {
+                const int s = c % NSTAGE;
+                umma::mbar_wait(&full[s], (c / NSTAGE) & 1);
+                umma::fence_after_thread_sync();
+                const uint64_t bh = dproto + ((base + s * STAGE_B) >> 4), bl = bh + (B_B >> 4);
+                const uint32_t ah = tmem + TS_ACC_COLS + s * TS_STAGE_COLS, al = ah + 32;
+#pragma unroll
+                for (int ks = 0; ks < GKT / 8; ks++) {
+                    const uint64_t o = (uint64_t)(ks * ((2 * LBO) >> 4));
+                    umma::mma_tf32_ts(tmem, al + ks * 8, bh + o, idesc, c > 0 || ks > 0);   // small terms first
+                    umma::mma_tf32_ts(tmem, ah + ks * 8, bl + o, idesc, true);
+                    umma::mma_tf32_ts(tmem, ah + ks * 8, bh + o, idesc, true);
+                }
+                umma::mma_commit(&empty[s]);
+            }
+            umma::mma_commit(&done);
+        }
+        __syncwarp();
+    } else {
+        const Operand<TM, false> opA(g.A, z, a0, g.Mo, g.Kc, w, lane);
+        const Operand<TN, BO> opB(g.B, z, b0, g.No, g.Kc, w, lane);
+        float ra[NSET][TM / 32][4], rb[NSET][TN / 32][4];
+#pragma unroll
+        for (int p = 0; p < NSET - 1; p++)
+            if (p < nch) { opA.fetch(p, ra[p]); opB.fetch(p, rb[p]); }
+        __syncthreads();   // barriers initialised, TMEM allocated
+        const uint32_t tmem = tmem_slot;
+        const uint32_t my_a = tmem + ((uint32_t)((w & 3) * 32) << 16) + TS_ACC_COLS + (w >> 2) * 16;   // this warp's lanes, its half of the chunk
+        for (int c0 = 0; c0 < nch; c0 += NSET) {
+#pragma unroll
+            for (int u = 0; u < NSET; u++) {
+                const int c = c0 + u;
+                if (c < nch) {
+                    if (c + NSET - 1 < nch) {
+                        opA.fetch(c + NSET - 1, ra[(u + NSET - 1) % NSET]);
+                        opB.fetch(c + NSET - 1, rb[(u + NSET - 1) % NSET]);
+                    }
+                    if (c >= NSTAGE) {
+                        umma::mbar_wait(&empty[u], ((c / NSTAGE) - 1) & 1);
+                        umma::fence_after_thread_sync();
+                    }
+                    unsigned char *st = dsm + u * STAGE_B;
+                    opA.store_tmem(c, ra[u], my_a + u * TS_STAGE_COLS);
+                    opB.store(c, rb[u], st, st + B_B);
+                    umma::tmem_st_wait();
+                    umma::fence_async_smem();
+                    umma::fence_before_thread_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[u]);
+                }
+            }
+        }
+        umma::mbar_wait(&done, 0);
+        umma::fence_after_thread_sync();
+
+        const int q = w & 3, h = w >> 2;
+        if (h * 32 < TN) {
+            float v[32];
+            umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), v);
+            if (SWAP) {      // lane = C's column j, accumulator column = C's row i: every store instruction covers 32 consecutive j
+                const int j = a0 + q * 32 + lane;
+                if (j < g.Mo) {
+#pragma unroll
+                    for (int t = 0; t < 32; t++) {
+                        const int i = b0 + h * 32 + t;
+                        if (i < g.No) gemm_emit(g, z, i, j, v[t]);
+                    }
+                }
+            } else {         // lane = C's row: transpose through shared memory (the stages are free) for coalesced stores
+                float *tb = reinterpret_cast<float *>(dsm) + w * (32 * 33);
+#pragma unroll
+                for (int t = 0; t < 32; t++) tb[lane * 33 + t] = v[t];
+                __syncwarp();
+                const int j = b0 + h * 32 + lane;
+                if (j < g.No) {
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; rr++) {
+                        const int i = a0 + q * 32 + rr;
+                        if (i < g.Mo) gemm_emit(g, z, i, j, tb[rr * 33 + lane]);
+                    }
+                }
+            }
+        }
+        umma::fence_before_thread_sync();
+    }
+    __syncthreads();
+    if (w == 8) {
+        umma::fence_after_thread_sync();
+        umma::tmem_dealloc(tmem_slot, TS_TMEM_COLS);
+    }
+}
+
+template <int TN>
+constexpr int ts_smem_bytes() {
+    constexpr int stages = NSTAGE * 2 * (TN / 8) * SBO, transpose = 8 * 32 * 33 * 4;
+    return stages > transpose ? stages : transpose;
+}
+template <int TN, bool BO, bool SWAP>
+void launch_ts(const GemmArgs &g, int nets, cudaStream_t st) {
+    dim3 grid((g.Mo + TM - 1) / TM, (g.No + TN - 1) / TN, nets);
+    k_gemm_ts<TN, BO, SWAP><<<grid, NTHR, ts_smem_bytes<TN>(), st>>>(g);
+}
+
 template <int TN>
 constexpr int smem_bytes() { return NSTAGE * (2 * (TM / 8) * SBO + 2 * (TN / 8) * SBO); }
 
@@ -302,14 +493,22 @@ cudaError_t gemm_tc_prepare() {
     if ((e = prepare_one<32, true, false>()) != cudaSuccess) return e;
     if ((e = prepare_one<64, false, false>()) != cudaSuccess) return e;
     if ((e = prepare_one<32, false, false>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm_ts<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts_smem_bytes<64>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm_ts<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts_smem_bytes<32>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm_ts<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts_smem_bytes<64>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_gemm_ts<32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts_smem_bytes<32>())) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
-// engine: -1 = the library default (g_contraction_engine), 0 = SIMT, 1 = tcgen05 (TN by shape), 64 / 32 = tcgen05 with that TN
+// engine: -1 = the library default (g_contraction_engine); 0 = SIMT tiles; 1 = automatic: tcgen05 tiles from 4096 output
+// rows on, where they are the faster of the two (see the header of this file), SIMT tiles below; 2 = tcgen05 always (callers
+// whose results must not depend on how many rows a launch sees: PPO's rollout passes); 64 / 32 = tcgen05 with that tile width.
 bool gemm_tc_launch(const GemmArgs &g, int nets, bool ao, bool bo, cudaStream_t st, int engine) {
     if (engine < 0) engine = g_contraction_engine;
     if (engine == 0 || g.Mo <= 0 || g.No <= 0 || g.Kc <= 0) return false;
     if (!ao && bo) return false;   // not a shape the learners use
+    if (engine == 1 && g.Mo < 4096) return false;
+    if (engine == 164 || engine == 132) engine = 2;    // the TS form declined the shape
     const int tn = engine == 64 || engine == 32 ? engine : (g.No > 32 ? 64 : 32);
     if (ao && bo) launch_tn<true, true>(g, nets, st, tn);
     else if (ao) launch_tn<true, false>(g, nets, st, tn);
@@ -317,24 +516,55 @@ bool gemm_tc_launch(const GemmArgs &g, int nets, bool ao, bool bo, cudaStream_t 
     return true;
 }
 
+// TS form.  gs is already in the kernel's orientation: gs.A = the 128-row operand (its Mat rows are contracted), gs.Mo its
+// extent, gs.B / gs.No the other operand; swap = the accumulator is C transposed.  Only on request (engine 164 / 132 = this
+// form with tile width 64 / 32): measured on a B200 it is within +-10 % of the SS form on every shape of the learners
+// (profiles/r2_gemm_tc.md) — neither form is bound by shared-memory bandwidth or by the tensor pipe, both wait for the
+// global loads of their operands — so the automatic choice never needs it and no learner has to keep transposed weights.
+bool gemm_ts_launch(const GemmArgs &gs, int nets, bool bo, bool swap, cudaStream_t st, int engine) {
+    if (engine < 0) engine = g_contraction_engine;
+    if ((engine != 164 && engine != 132) || gs.Mo <= 0 || gs.No <= 0 || gs.Kc <= 0) return false;
+    if (bo != swap) return false;   // the two combinations the learners use
+    const int tn = engine == 164 ? 64 : 32;
+    if (swap) { if (tn == 64) launch_ts<64, true, true>(gs, nets, st); else launch_ts<32, true, true>(gs, nets, st); }
+    else { if (tn == 64) launch_ts<64, false, false>(gs, nets, st); else launch_ts<32, false, false>(gs, nets, st); }
+    return true;
+}
+
+// dst[z][c][r] = src[z][r][c]  (the transposed weight copies the TS-form forward reads)
+__global__ void k_transpose(int rows, int cols, const float *__restrict__ src, float *__restrict__ dst) {
+    __shared__ float t[32][33];
+    const size_t zo = (size_t)blockIdx.z * rows * cols;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y)
+        if (r0 + y < rows && c0 + threadIdx.x < cols) t[y][threadIdx.x] = src[zo + (size_t)(r0 + y) * cols + c0 + threadIdx.x];
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y)
+        if (c0 + y < cols && r0 + threadIdx.x < rows) dst[zo + (size_t)(c0 + y) * rows + r0 + threadIdx.x] = t[threadIdx.x][y];
+}
+void transpose_weights(int rows, int cols, int nets, const float *src, float *dst, cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, nets), block(32, 8);
+    k_transpose<<<grid, block, 0, st>>>(rows, cols, src, dst);
+}
+
 }  // namespace prl
 
 extern "C" int prl_set_contraction_engine(int engine) {
-    PRL_REQUIRE(engine == 0 || engine == 1, "engine must be 0 (SIMT tiles) or 1 (tcgen05 tiles)");
+    PRL_REQUIRE(engine >= 0 && engine <= 2, "engine must be 0 (SIMT tiles), 1 (automatic) or 2 (tcgen05 tiles always)");
     prl::g_contraction_engine = engine;
     return PRL_OK;
 }
 extern "C" int prl_get_contraction_engine(void) { return prl::g_contraction_engine; }
+
+static long long *g_test_stamps = nullptr;
+/* developer profiling: device int64[33][8] receiving SM-clock stamps of CTA 0 of the next prl_test_contraction calls */
+extern "C" int prl_test_contraction_stamps(long long *stamps_dev) { g_test_stamps = stamps_dev; return PRL_OK; }
 
 // Test hook: one contraction of the learners' three kinds through GemmLauncher.
 //   op 0  y[M x N]  = act(x W^T + b)          a = x [M x K] (or [M x split] with a2 = [M x (K - split)]), b = W [N x K]
 //   op 1  dx[M x K] (+)= dy W  (masked)       a = dy [M x N], b = W [N x K], mask [M x K]
 //   op 2  dW[N x K] = dy^T x, db = dy^T 1     a = dy [M x N], b = x [M x K] (or split with a2), c_tail = db [N]
 // `nets` stacked problems are laid out contiguously in every operand.
-static long long *g_test_stamps = nullptr;
-/* developer profiling: device int64[33][8] receiving SM-clock stamps of CTA 0 of the next prl_test_contraction calls */
-extern "C" int prl_test_contraction_stamps(long long *stamps_dev) { g_test_stamps = stamps_dev; return PRL_OK; }
-
 extern "C" int prl_test_contraction(int op, int engine, int M, int N, int K, const float *a, const float *b, const float *a2, int split,
                                     const float *bias, const float *mask, int relu, int accumulate, float *c, float *c_tail, int nets,
                                     void *stream) {
@@ -347,7 +577,13 @@ extern "C" int prl_test_contraction(int op, int engine, int M, int N, int K, con
     const long long MK = (long long)M * K, MN = (long long)M * N, NK = (long long)N * K;
     if (op == 0) {
         Mat X = a2 ? mat2(a, split, split, a2, K - split, (long long)M * split, (long long)M * (K - split)) : mat(a, K, MK);
-        L.fwd(X, M, b, K, NK, bias, N, N, K, relu != 0, c, N, MN, nets);
+        float *wt = nullptr;
+        if (engine == 164 || engine == 132) {          // a learner using this form would keep the copy up to date itself
+            PRL_CUDA(cudaMallocAsync((void **)&wt, sizeof(float) * NK * nets, L.st));
+            transpose_weights(N, K, nets, b, wt, L.st);
+        }
+        L.fwd(X, M, b, K, NK, bias, N, N, K, relu != 0, c, N, MN, nets, wt, N, NK);
+        if (wt) PRL_CUDA(cudaFreeAsync(wt, L.st));
     } else if (op == 1) {
         L.bwd_x(a, N, MN, M, N, b, K, NK, 0, K, c, K, MK, mask, K, MK, accumulate != 0, nets);
     } else {

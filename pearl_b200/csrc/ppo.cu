@@ -462,6 +462,10 @@ extern "C" int prl_ppo_preprocess(prl_ppo *s, prl_buf *buf, float *out_values, f
     cudaStream_t st = (cudaStream_t)stream_;
     const int64_t cap = buf->desc.capacity, head = (buf->write_pos - buf->len + cap) % cap;
     GemmLauncher L; L.st = st;
+    // a transition's value / action probability must not depend on how the rollout is cut into passes or time shards
+    // (prl_ppo_gae_redo promises bit-identity with the unsharded rollout): one engine and one summation order for every pass
+    L.fixed_order = true;
+    L.engine = prl_get_contraction_engine() ? 2 : 0;
     for (int64_t i0 = 0; i0 < n; i0 += kPpoChunk) {
         const int rows = (int)((n - i0 < kPpoChunk) ? n - i0 : kPpoChunk);
         k_ppo_rollout_rows<<<(rows * 32 + 255) / 256, 256, 0, st>>>(buf->records, buf->lay, c.obs_dim, head, cap, i0, rows, s->S, s->act, s->reward,

@@ -13,7 +13,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = [0, 64, 32]
+ENGINES = [0, 64, 32, 164, 132]   # SIMT tiles; tcgen05 with both operands in shared memory; tcgen05 with A in tensor memory
 
 
 def _p(t):

@@ -43,7 +43,7 @@ def main():
         ct = torch.empty((nets, N), device=dev) if op == 2 else None
         flops = 2.0 * M * N * K * nets
         out = []
-        for engine in (0, 64, 32):
+        for engine in (0, 64, 164, 132):
             side = torch.cuda.Stream()
             sp = C.c_void_p(side.cuda_stream)
 
@@ -68,7 +68,7 @@ def main():
                 e1.record(side)
                 side.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (max(reps // 20, 1) * 20)
-            out.append(f"{['simt', 'tc64', 'tc32'][(0, 64, 32).index(engine)]} {us:7.2f} us ({flops / us * 1e-6:7.2f} TF/s)")
+            out.append(f"{['simt', 'ss64', 'ts64', 'ts32'][(0, 64, 164, 132).index(engine)]} {us:7.2f} us ({flops / us * 1e-6:7.2f} TF/s)")
         print(f"{name:42s} " + "  ".join(out), flush=True)
 
 
