@@ -751,8 +751,8 @@ def other_paths(dev, args) -> dict:
         from pearl_b200.ppo import gae_and_lambda_returns
         ng = 1 << 24
         vals, rws = rn(ng), rn(ng)
-        te = (torch.arange(ng, device=dev) % 500) == 499
-        tu = torch.zeros(ng, dtype=torch.bool, device=dev)
+        te = ((torch.arange(ng, device=dev) % 500) == 499).to(torch.uint8)   # the flags as the rollout kernels hold them
+        tu = torch.zeros(ng, dtype=torch.uint8, device=dev)
         entry("k_ppo_gae (GAE + lambda returns)", ng * 18, timed(lambda: gae_and_lambda_returns(vals, 0.1, rws, te, tu, 0.99, 0.95), 10),
               f"{ng} transitions, episodes of 500: 10 bytes read + 8 written per transition (the reference's Python loop: ppo.py:271-293)")
         del vals, rws, te, tu
