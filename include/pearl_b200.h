@@ -326,10 +326,11 @@ int prl_dqn_learn_per(prl_dqn *dqn, prl_buf *buf, prl_per *per, int rounds, int 
  * TIME order (index 0 = oldest stored transition): values[i] = critic(state_i), last_next_value =
  * critic(next_state of the newest transition), reward f32, terminated / truncated u8.  Outputs gae[i],
  * lam_return[i] are bit-identical to the reference loop (same fp32 operation order); episodes
- * (chains between terminated / truncated transitions) are processed in parallel. */
+ * (chains between terminated / truncated transitions) are processed in parallel.  scratch_dev: device int32[n + 1]
+ * owned by the caller (the compacted chain heads and their count; contents are overwritten). */
 int prl_ppo_gae(int n, const float *values_dev, float last_next_value, const float *reward_dev,
                 const uint8_t *terminated_dev, const uint8_t *truncated_dev, double gamma, double lam,
-                float *out_gae_dev, float *out_lam_return_dev, void *stream);
+                float *out_gae_dev, float *out_lam_return_dev, int32_t *scratch_dev, void *stream);
 
 /* ---- continuous Soft Actor-Critic ---------------------------------------------------------------
  * Replaces ContinuousSoftActorCritic.learn_batch (policy_learners/sequential_decision_making/

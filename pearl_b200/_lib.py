@@ -115,7 +115,7 @@ _SIGNATURES = {
     "prl_per_sample": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "prl_per_set_priorities": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "prl_dqn_learn_per": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P]),
-    "prl_ppo_gae": (C.c_int, [C.c_int, _P, C.c_float, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P]),
+    "prl_ppo_gae": (C.c_int, [C.c_int, _P, C.c_float, _P, _P, _P, C.c_double, C.c_double, _P, _P, _P, _P]),
     "prl_sac_actor_param_count": (C.c_int64, [C.POINTER(SacCfg)]),
     "prl_sac_critic_param_count": (C.c_int64, [C.POINTER(SacCfg)]),
     "prl_sac_workspace_bytes": (C.c_int64, [C.POINTER(SacCfg)]),

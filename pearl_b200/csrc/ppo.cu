@@ -24,114 +24,177 @@ namespace {
 
 // arrays are in TIME order (index 0 = oldest stored transition)
 // A chain = an episode segment; its newest element ("head") is the last stored transition or one with terminated /
-// truncated set.  k_ppo_gae_heads compacts the head positions (order irrelevant: chains are independent), then
-// k_ppo_gae gives every chain its own THREAD — all 32 lanes of a warp walk chains — newest -> oldest in the reference's
-// fp32 operation order (ppo.py:271-293), so the result is bit-identical to the Python loop.  The walk is a dependent
-// recurrence: it moves 4 transitions per step with 16-byte loads / stores and keeps the next group's loads in flight.
-// (Round 1 let the head's own thread of a one-thread-per-transition grid walk the chain: one active lane per warp, 0.04 of
-// the HBM roofline at 16M transitions.)
-__device__ __forceinline__ void gae_walk_chain(int t, int n, const float *__restrict__ values, float last_next_value_host,
-                          const float *__restrict__ last_next_value_dev, float incoming_gae, const float *__restrict__ reward, const uint8_t *__restrict__ terminated,
-                          const uint8_t *__restrict__ truncated, float gamma, float c_live,
-                          float *__restrict__ out_gae, float *__restrict__ out_lam_return) {
-    const float last_next_value = last_next_value_dev ? *last_next_value_dev : last_next_value_host;
-    // the chain headed by the newest element continues a chain of NEWER transitions held elsewhere (a later time
-    // shard): it starts from that chain's gae instead of 0 (multiplied by 0 below if the newest element ends an episode)
-    float gae = (t == n - 1) ? incoming_gae : 0.f;
-    float nv = (t == n - 1) ? last_next_value : values[t + 1];          // value of the next (newer) stored transition
-    auto step = [&](int s, float v, float r, bool term, bool cut) {
-        // reward + gamma * next_value * (~terminated) - V[i]   (left to right, fp32)
-        const float td = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nv), term ? 0.f : 1.f)), v);
-        // td + (gamma * lambda * mask) * gae ; the scalar product is evaluated in double by Python
-        gae = __fadd_rn(td, __fmul_rn(cut ? 0.f : c_live, gae));
-        nv = v;
-        return gae;
-    };
-    int s = t;
-    // scalar steps until [s - 3, s] is an aligned group of four (the head itself is always a scalar step)
-    bool first = true;
-    while (s >= 0 && (first || (s & 3) != 3)) {
-        const bool term = terminated[s] != 0, cut = term || truncated[s] != 0;
-        if (!first && cut) return;                                      // the next chain's head
-        const float v = values[s], g = step(s, v, reward[s], term, cut);
-        out_gae[s] = g;
-        out_lam_return[s] = __fadd_rn(g, v);
-        first = false;
-        s--;
-    }
-    const bool vec = ((reinterpret_cast<uintptr_t>(values) | reinterpret_cast<uintptr_t>(reward) | reinterpret_cast<uintptr_t>(out_gae) |
-                       reinterpret_cast<uintptr_t>(out_lam_return)) & 15) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(terminated) | reinterpret_cast<uintptr_t>(truncated)) & 3) == 0;
-    if (vec && s >= 3) {
-        // PF groups of four are in flight per thread (a thread's chain is a dependent recurrence, so the memory
-        // parallelism has to come from prefetch depth x chains: at 33k chains one group in flight was 0.1 of the roofline)
-        constexpr int PF = 6;
-        float4 v4[PF], r4[PF];
-        uint32_t te[PF], tr[PF];
-        auto load = [&](int p, int top) {                               // group [top - 3, top]
-            v4[p] = *reinterpret_cast<const float4 *>(values + top - 3); r4[p] = *reinterpret_cast<const float4 *>(reward + top - 3);
-            te[p] = *reinterpret_cast<const uint32_t *>(terminated + top - 3); tr[p] = *reinterpret_cast<const uint32_t *>(truncated + top - 3);
-        };
-#pragma unroll
-        for (int p = 0; p < PF; p++)
-            if (s - 4 * p >= 3) load(p, s - 4 * p);
-        bool more = true;
-        while (more) {
-#pragma unroll
-            for (int p = 0; p < PF; p++) {
-                if (s < 3) { more = false; break; }
-                const float vv[4] = {v4[p].x, v4[p].y, v4[p].z, v4[p].w}, rr[4] = {r4[p].x, r4[p].y, r4[p].z, r4[p].w};
-                const uint32_t cte = te[p], ctr = tr[p];
-                if (s - 4 * PF >= 3) load(p, s - 4 * PF);               // refill the slot: independent of the recurrence below
-                if ((cte | ctr) == 0) {                                 // no episode end inside the group: four steps, two 16-byte stores
-                    float g[4];
-#pragma unroll
-                    for (int u = 3; u >= 0; u--) g[u] = step(s - 3 + u, vv[u], rr[u], false, false);
-                    *reinterpret_cast<float4 *>(out_gae + s - 3) = make_float4(g[0], g[1], g[2], g[3]);
-                    *reinterpret_cast<float4 *>(out_lam_return + s - 3) =
-                        make_float4(__fadd_rn(g[0], vv[0]), __fadd_rn(g[1], vv[1]), __fadd_rn(g[2], vv[2]), __fadd_rn(g[3], vv[3]));
-                } else {
-#pragma unroll
-                    for (int u = 3; u >= 0; u--) {
-                        const bool cut = (((cte | ctr) >> (8 * u)) & 0xffu) != 0;
-                        if (cut) return;                                // the next chain's head
-                        const float g = step(s - 3 + u, vv[u], rr[u], false, false);
-                        out_gae[s - 3 + u] = g;
-                        out_lam_return[s - 3 + u] = __fadd_rn(g, vv[u]);
-                    }
-                }
-                s -= 4;
-            }
-        }
-    }
-    for (; s >= 0; s--) {                                               // the oldest 0..3 transitions (or unaligned arrays)
-        const bool term = terminated[s] != 0, cut = term || truncated[s] != 0;
-        if (cut) return;
-        const float v = values[s], g = step(s, v, reward[s], term, cut);
-        out_gae[s] = g;
-        out_lam_return[s] = __fadd_rn(g, v);
-    }
-}
+// truncated set.  k_ppo_gae_heads compacts the head positions (order irrelevant: chains are independent); k_ppo_gae then
+// gives a CTA 32 chains at a time and moves them newest -> oldest in blocks of 64 transitions:
+//   A  all four warps: a chain's block is 256 contiguous bytes per array, so every global access is coalesced; the
+//      temporal-difference term td (it depends only on a transition and its newer neighbour) is computed here, in the
+//      reference's fp32 operation order, and staged in shared memory with the chain-end flags;
+//   B  warp 0, one lane per chain: the dependent recurrence gae = td + c * gae over the 64 staged values (two flops per
+//      transition on the serial path, four transitions per flag word), results written back in place;
+//   C  all four warps: coalesced stores of gae and gae + V.
+// Results are bit-identical to the Python loop (ppo.py:271-293).  History: round 1 let the head's own thread of a
+// one-thread-per-transition grid walk the chain (one active lane per warp, 0.04 of the HBM roofline at 16M transitions);
+// a chain per THREAD with register prefetch reached 0.14: 32 lanes 2 KB apart make every access a lone 32-byte sector.
+constexpr int kGaeBlk = 64;
 
 __global__ void k_ppo_gae_heads(int n, const uint8_t *__restrict__ terminated, const uint8_t *__restrict__ truncated,
                                 int *__restrict__ heads, int *__restrict__ count) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool head = t < n && ((t == n - 1) || terminated[t] || truncated[t]);
-    const unsigned bal = __ballot_sync(0xffffffffu, head);
-    const int lane = threadIdx.x & 31;
+    // four transitions per thread (one flag word per array when the arrays are word-aligned)
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, t0 = q * 4, lane = threadIdx.x & 31;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(terminated) | reinterpret_cast<uintptr_t>(truncated)) & 3) == 0;
+    uint32_t f = 0;
+    if (t0 + 3 < n && aligned) {
+        f = *reinterpret_cast<const uint32_t *>(terminated + t0) | *reinterpret_cast<const uint32_t *>(truncated + t0);
+    } else {
+        for (int u = 0; u < 4; u++)
+            if (t0 + u < n && (terminated[t0 + u] | truncated[t0 + u])) f |= 0xffu << (8 * u);
+    }
+    unsigned mask = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+        if (t0 + u < n && (((f >> (8 * u)) & 0xffu) != 0 || t0 + u == n - 1)) mask |= 1u << u;
+    const int mine = __popc(mask);
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
     int base = 0;
-    if (lane == 0 && bal) base = atomicAdd(count, __popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (head) heads[base + __popc(bal & ((1u << lane) - 1u))] = t;
+    if (lane == 31 && total) base = atomicAdd(count, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+        if (mask & (1u << u)) heads[base++] = t0 + u;
 }
-__global__ void k_ppo_gae(int n, const int *__restrict__ heads, const int *__restrict__ count, const float *__restrict__ values,
+
+__global__ void __launch_bounds__(128) k_ppo_gae(int n, const int *__restrict__ heads, const int *__restrict__ count, const float *__restrict__ values,
                           float last_next_value_host, const float *__restrict__ last_next_value_dev, float incoming_gae,
                           const float *__restrict__ reward, const uint8_t *__restrict__ terminated, const uint8_t *__restrict__ truncated,
                           float gamma, float c_live, float *__restrict__ out_gae, float *__restrict__ out_lam_return) {
-    const int nh = *count;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += gridDim.x * blockDim.x)
-        gae_walk_chain(heads[i], n, values, last_next_value_host, last_next_value_dev, incoming_gae, reward, terminated, truncated, gamma, c_live,
-                       out_gae, out_lam_return);
+    __shared__ float s_td[32][kGaeBlk + 1], s_v[32][kGaeBlk + 1];
+    __shared__ __align__(4) uint8_t s_cut[32][kGaeBlk + 4];
+    __shared__ int s_top[32], s_len[32], s_any;
+    const int nh = *count, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const float last_next_value = last_next_value_dev ? *last_next_value_dev : last_next_value_host;
+    for (int g0 = blockIdx.x * 32; g0 < nh; g0 += gridDim.x * 32) {
+        // chain state lives in warp 0, lane = chain
+        int top = -1;
+        float gae = 0.f;
+        bool first = true;
+        if (w == 0) {
+            if (g0 + lane < nh) top = heads[g0 + lane];
+            // the chain headed by the newest element continues a chain of NEWER transitions held elsewhere (a later time
+            // shard): it starts from that chain's gae instead of 0 (multiplied by 0 below if the newest element ends an episode)
+            if (top == n - 1) gae = incoming_gae;
+            s_top[lane] = top;
+        }
+        __syncthreads();
+        while (true) {
+            // ---- A: stage td, V and the chain-end flags of every live chain's next block.  All of a warp's loads for
+            //         four chains are issued before any is used (one memory round trip per four chains, not per chain)
+#pragma unroll 1
+            for (int jb = 0; jb < 8; jb += 4) {
+                float v[4][kGaeBlk / 32], r[4][kGaeBlk / 32], nv[4][kGaeBlk / 32];
+                uint8_t te[4][kGaeBlk / 32], tr[4][kGaeBlk / 32];
+                int tjs[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int tj = s_top[w + 4 * (jb + q)];
+                    tjs[q] = tj;
+#pragma unroll
+                    for (int e = 0; e < kGaeBlk / 32; e++) {
+                        const int idx = tj - lane - 32 * e;
+                        const bool ok = tj >= 0 && idx >= 0;
+                        const int ia = ok ? idx : 0, ib = (ok && idx + 1 < n) ? idx + 1 : 0;
+                        v[q][e] = values[ia]; r[q][e] = reward[ia]; nv[q][e] = values[ib];
+                        te[q][e] = terminated[ia]; tr[q][e] = truncated[ia];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int j = w + 4 * (jb + q), tj = tjs[q];
+                    if (tj < 0) continue;
+#pragma unroll
+                    for (int e = 0; e < kGaeBlk / 32; e++) {
+                        const int k = lane + 32 * e, idx = tj - k;
+                        float td = 0.f;
+                        uint8_t cut = 1;                                // below the oldest transition: stops the walk
+                        if (idx >= 0) {
+                            const float nvx = idx + 1 < n ? nv[q][e] : last_next_value;   // the next STORED transition's value
+                            const bool term = te[q][e] != 0;
+                            cut = (term || tr[q][e] != 0) ? 1 : 0;
+                            // reward + gamma * next_value * (~terminated) - V[i]   (left to right, fp32)
+                            td = __fsub_rn(__fadd_rn(r[q][e], __fmul_rn(__fmul_rn(gamma, nvx), term ? 0.f : 1.f)), v[q][e]);
+                        }
+                        s_td[j][k] = td;
+                        s_v[j][k] = v[q][e];
+                        s_cut[j][k] = cut;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- B: the recurrence, one lane per chain:  gae = td + (gamma * lambda * mask) * gae
+            //         (the scalar product gamma * lambda is evaluated in double by Python and passed in as c_live)
+            int next_top = -1;
+            if (w == 0 && top >= 0) {
+                int k = 0;
+                bool ended = false;
+                for (; k < kGaeBlk && !ended; k += 4) {
+                    const uint32_t cw = *reinterpret_cast<const uint32_t *>(&s_cut[lane][k]);
+                    const float t0 = s_td[lane][k], t1 = s_td[lane][k + 1], t2 = s_td[lane][k + 2], t3 = s_td[lane][k + 3];
+                    if (cw == 0) {                                     // no episode end among these four
+                        const float g0v = __fadd_rn(t0, __fmul_rn(c_live, gae));
+                        const float g1v = __fadd_rn(t1, __fmul_rn(c_live, g0v));
+                        const float g2v = __fadd_rn(t2, __fmul_rn(c_live, g1v));
+                        gae = __fadd_rn(t3, __fmul_rn(c_live, g2v));
+                        s_td[lane][k] = g0v; s_td[lane][k + 1] = g1v; s_td[lane][k + 2] = g2v; s_td[lane][k + 3] = gae;
+                        continue;
+                    }
+                    const float tt[4] = {t0, t1, t2, t3};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (ended) break;
+                        const bool cut = ((cw >> (8 * u)) & 0xffu) != 0;
+                        float mult = c_live;
+                        if (first && k + u == 0) mult = cut ? 0.f : c_live;   // the head itself
+                        else if (cut) { ended = true; s_len[lane] = k + u; break; }   // the next chain's head
+                        gae = __fadd_rn(tt[u], __fmul_rn(mult, gae));
+                        s_td[lane][k + u] = gae;
+                    }
+                }
+                first = false;
+                if (!ended) { s_len[lane] = kGaeBlk; next_top = top - kGaeBlk; }
+            }
+            __syncthreads();
+            // ---- C: coalesced stores
+#pragma unroll 2
+            for (int jj = 0; jj < 8; jj++) {
+                const int j = w + 4 * jj, tj = s_top[j];
+                if (tj < 0) continue;
+                const int len = s_len[j];
+#pragma unroll
+                for (int e = 0; e < kGaeBlk / 32; e++) {
+                    const int k = lane + 32 * e;
+                    if (k < len) {
+                        const float g = s_td[j][k];
+                        out_gae[tj - k] = g;
+                        out_lam_return[tj - k] = __fadd_rn(g, s_v[j][k]);
+                    }
+                }
+            }
+            __syncthreads();
+            if (w == 0) {
+                top = next_top;
+                s_top[lane] = top;
+                const unsigned live = __ballot_sync(0xffffffffu, top >= 0);
+                if (lane == 0) s_any = live != 0;
+            }
+            __syncthreads();
+            if (!s_any) break;
+        }
+    }
 }
 
 }  // namespace
@@ -141,8 +204,9 @@ static int launch_gae(int n, const float *values, float last_next_value, const f
                       const float *reward, const uint8_t *term, const uint8_t *trunc, float gamma, float c_live, float *out_gae,
                       float *out_lam_return, int *heads, int *count, cudaStream_t st) {
     PRL_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
-    k_ppo_gae_heads<<<(n + 255) / 256, 256, 0, st>>>(n, term, trunc, heads, count);
-    const int blocks = (n + 127) / 128 < 148 * 8 ? (n + 127) / 128 : 148 * 8;
+    k_ppo_gae_heads<<<((n + 3) / 4 + 255) / 256, 256, 0, st>>>(n, term, trunc, heads, count);
+    const int groups = (n + 31) / 32;                              // an upper bound on chains / 32 (the count is on the device)
+    const int blocks = groups < 148 * 16 ? groups : 148 * 16;
     k_ppo_gae<<<blocks, 128, 0, st>>>(n, heads, count, values, last_next_value, last_next_value_dev, incoming_gae, reward, term, trunc, gamma,
                                       c_live, out_gae, out_lam_return);
     PRL_CUDA(cudaGetLastError());
@@ -151,18 +215,13 @@ static int launch_gae(int n, const float *values, float last_next_value, const f
 
 extern "C" int prl_ppo_gae(int n, const float *values_dev, float last_next_value, const float *reward_dev,
                            const uint8_t *terminated_dev, const uint8_t *truncated_dev, double gamma, double lam,
-                           float *out_gae_dev, float *out_lam_return_dev, void *stream) {
+                           float *out_gae_dev, float *out_lam_return_dev, int32_t *scratch_dev, void *stream) {
     PRL_REQUIRE(n >= 0, "negative length");
     if (n == 0) return PRL_OK;
-    PRL_REQUIRE(values_dev && reward_dev && terminated_dev && truncated_dev && out_gae_dev && out_lam_return_dev,
+    PRL_REQUIRE(values_dev && reward_dev && terminated_dev && truncated_dev && out_gae_dev && out_lam_return_dev && scratch_dev,
                 "null argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    int *scratch = nullptr;                     // chain heads + their count, stream-ordered allocation
-    PRL_CUDA(cudaMallocAsync((void **)&scratch, ((size_t)n + 1) * sizeof(int), st));
-    const int rc = launch_gae(n, values_dev, last_next_value, nullptr, 0.f, reward_dev, terminated_dev, truncated_dev, (float)gamma,
-                              (float)(gamma * lam), out_gae_dev, out_lam_return_dev, scratch + 1, scratch, st);
-    PRL_CUDA(cudaFreeAsync(scratch, st));
-    return rc;
+    return launch_gae(n, values_dev, last_next_value, nullptr, 0.f, reward_dev, terminated_dev, truncated_dev, (float)gamma,
+                      (float)(gamma * lam), out_gae_dev, out_lam_return_dev, scratch_dev + 1, scratch_dev, (cudaStream_t)stream);
 }
 
 // ====================================================================================================

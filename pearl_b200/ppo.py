@@ -25,10 +25,11 @@ def gae_and_lambda_returns(values: torch.Tensor, last_next_value: float, reward:
     tr = truncated.reshape(n).to(device=dev, dtype=torch.uint8).contiguous()
     gae = torch.empty(n, dtype=torch.float32, device=dev)
     lam = torch.empty(n, dtype=torch.float32, device=dev)
+    scratch = torch.empty(n + 1, dtype=torch.int32, device=dev)      # chain heads + their count (caching allocator: no driver call)
     with torch.cuda.device(dev):
         _lib.check(lib.prl_ppo_gae(n, _lib.ptr(v), float(last_next_value), _lib.ptr(r), _lib.ptr(te), _lib.ptr(tr),
                                    float(discount_factor), float(trace_decay_param), _lib.ptr(gae), _lib.ptr(lam),
-                                   _stream_ptr(dev)))
+                                   _lib.ptr(scratch), _stream_ptr(dev)))
     return gae, lam
 
 
