@@ -630,12 +630,17 @@ def other_paths(dev, args) -> dict:
                                                            critic_hidden_dims=[256, 256], training_rounds=R, batch_size=B, device=dev, seed=1)
             sec = timed(lambda: pl.learn(buf), 3)
             return sec, int(pl._lib.prl_sac_last_launches(pl._handle)) // R
-        sec0, _ = run(0)
         sec, kps = run(1)
+        sec2, _ = run(2)
+        _lib.check(lib.prl_set_contraction_engine(1))
         out["sac"] = {"workload": "SAC continuous obs_dim=376 act_dim=17, 1M replay, batch=512 (configs[2])", "value": R / sec,
                       "unit": "gradient-steps/s (actor + twin-critic + entropy steps)", "us_per_step": sec / R * 1e6,
-                      "kernels_per_step": kps, "engine": "3xTF32 tcgen05 contractions (k_gemm_tc), CUDA-graph replay",
-                      "with_simt_contractions": {"value": R / sec0, "us_per_step": sec0 / R * 1e6}}
+                      "kernels_per_step": kps,
+                      "engine": "automatic contraction engine: at batch 512 every product runs on the fp32 SIMT tiles with the contraction "
+                                "axis sliced over 4 warp groups (k_gemm<32,32,2,4>); CUDA-graph replay",
+                      "with_tcgen05_contractions_forced": {"value": R / sec2, "us_per_step": sec2 / R * 1e6,
+                                                           "note": "engine 2: every product on k_gemm_tc (3xTF32 tcgen05, 128 x 64 tiles); slower at this "
+                                                                   "batch size, see profiles/r2_gemm_tc.md"}}
         del buf
         if not args.no_cpu:
             from oracle.sac_oracle import OracleSAC
@@ -662,14 +667,17 @@ def other_paths(dev, args) -> dict:
                                                             trace_decay_param=0.95, device=dev, seed=2)
             pre = timed(lambda: pl.preprocess_replay_buffer(buf), 5)
             return pre, timed(lambda: pl.learn(buf), 3)
-        pre0, sec0 = run(0)
         pre_sec, sec = run(1)
+        pre0, sec0 = run(0)
+        _lib.check(lib.prl_set_contraction_engine(1))
         out["ppo"] = {"workload": "PPO 64k-step rollout obs_dim=210, 16 actions, [64,64] networks, GAE + clipped surrogate, batch=256 "
                                   "(configs[3] / SURVEY cfg4, one GPU)",
                       "preprocess_ms": pre_sec * 1e3, "preprocess_transitions_per_s": n / pre_sec,
                       "value": R / (sec - pre_sec), "unit": "gradient-steps/s (actor + critic steps, preprocessing excluded)",
-                      "learn_ms": sec * 1e3, "training_rounds": R, "engine": "3xTF32 tcgen05 contractions (k_gemm_tc), CUDA-graph replay",
-                      "with_simt_contractions": {"value": R / (sec0 - pre0), "preprocess_ms": pre0 * 1e3}}
+                      "learn_ms": sec * 1e3, "training_rounds": R,
+                      "engine": "rollout passes (8192 rows each): 3xTF32 tcgen05 contractions (k_gemm_tc); training rounds at batch 256: fp32 SIMT "
+                                "tiles (k_gemm<32,32,2,*>), CUDA-graph replay",
+                      "with_simt_contractions_only": {"value": R / (sec0 - pre0), "preprocess_ms": pre0 * 1e3}}
         del buf
         if not args.no_cpu:
             from oracle.ppo_oracle import OraclePPO
