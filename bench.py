@@ -811,6 +811,18 @@ def main() -> None:
     ap.add_argument("--no-extras", action="store_true", help="skip the SAC / PPO / prioritized-replay side measurements")
     ap.add_argument("--extras-only", action="store_true", help="developer: run only the side measurements on cuda:0")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner, torch warnings
+    # routed to fd 1) are sent to stderr for the duration of the run; print() is bound to the saved descriptor
+    global print
+    sys.stdout.flush()
+    real_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    import builtins
+
+    def print(*a, **kw):   # noqa: A001
+        kw.setdefault("file", real_out)
+        builtins.print(*a, **kw)
+        real_out.flush()
     if args.extras_only:
         import torch
         torch.cuda.set_device(0)
