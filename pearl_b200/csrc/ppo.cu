@@ -387,7 +387,12 @@ struct prl_ppo {
     int64_t pre_n;      // rollout length of the last prl_ppo_preprocess
 };
 
-static const int kPpoChunk = 8192;   // rollout rows evaluated per pass of the preprocessing
+// rollout rows evaluated per pass of the preprocessing: the whole rollout when it fits 65536 rows (a pass is 8 launches,
+// and at 8192 rows per pass the 64k-step rollout of the benchmark spent more time between launches than in them)
+static inline int64_t ppo_chunk(const prl_ppo_cfg *c) {
+    const int64_t r = c->max_rollout < 65536 ? c->max_rollout : 65536;
+    return r < 8192 ? 8192 : r;
+}
 
 static int ppo_check(const prl_ppo_cfg *c) {
     PRL_REQUIRE(c, "null cfg");
@@ -422,7 +427,7 @@ extern "C" int64_t prl_ppo_critic_param_count(const prl_ppo_cfg *c) {
 struct PpoWs { int64_t off[32]; int64_t total; };
 static PpoWs ppo_ws(const prl_ppo_cfg *c, int Pa, int Pc) {
     PpoWs w; int64_t o = 0; int k = 0;
-    const int64_t R = c->max_batch > kPpoChunk ? c->max_batch : kPpoChunk;   // rows of the widest pass
+    const int64_t R = c->max_batch > ppo_chunk(c) ? c->max_batch : ppo_chunk(c);   // rows of the widest pass
     const int64_t hmax1 = c->actor_h1 > c->critic_h1 ? c->actor_h1 : c->critic_h1, hmax2 = c->actor_h2 > c->critic_h2 ? c->actor_h2 : c->critic_h2;
     auto add = [&](int64_t bytes) { w.off[k++] = o; o = (o + bytes + 255) / 256 * 256; };
     add(R * c->obs_dim * 4); add(R * hmax1 * 4); add(R * hmax2 * 4); add(R * c->n_actions * 4); add(R * 4);     // S h1 h2 logits v
@@ -525,8 +530,9 @@ extern "C" int prl_ppo_preprocess(prl_ppo *s, prl_buf *buf, float *out_values, f
     // (prl_ppo_gae_redo promises bit-identity with the unsharded rollout): one engine and one summation order for every pass
     L.fixed_order = true;
     L.engine = prl_get_contraction_engine() ? 2 : 0;
-    for (int64_t i0 = 0; i0 < n; i0 += kPpoChunk) {
-        const int rows = (int)((n - i0 < kPpoChunk) ? n - i0 : kPpoChunk);
+    const int64_t chunk = ppo_chunk(&c);
+    for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+        const int rows = (int)((n - i0 < chunk) ? n - i0 : chunk);
         k_ppo_rollout_rows<<<(rows * 32 + 255) / 256, 256, 0, st>>>(buf->records, buf->lay, c.obs_dim, head, cap, i0, rows, s->S, s->act, s->reward,
                                                                   s->term, s->trunc);
         ppo_critic_forward(s, L, rows, out_values + i0);
