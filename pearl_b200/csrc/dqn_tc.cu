@@ -237,7 +237,7 @@ __device__ void layer1_all_tiles(const TcArgs &a, const TcLearner &L, Misc &mi, 
             umma::fence_before_thread_sync();
             group_sync(g);
             if (stamp && kc == 1) TC_STAMP(12);
-            if (m == 0) {
+            if (m < 32 && umma::elect_one()) {
                 umma::fence_after_thread_sync();
                 const int keff = min(64, a.d.obs - kc * 64);
                 umma::gemm3_ts(tm + TM_T1 + t * 64, tm + a_hi, tm + a_lo, B_hi.shifted(kc * 2048), B_lo.shifted(kc * 2048), 128, HID,
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     umma::fence_before_thread_sync();
                     group_sync(h);
                     
-                    if (m == 0) {
+                    if (m < 32 && umma::elect_one()) {
                         umma::fence_after_thread_sync();
                         umma::gemm3_ts(tm + acc_col, tm + a_hi, tm + a_lo, B_hi, B_lo, 128, HID, HID, false);
                         umma::mma_commit(&bar[1 + h]);
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             umma::fence_async_smem();
             umma::fence_before_thread_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0 && umma::elect_one()) {
                 umma::fence_after_thread_sync();
                 umma::gemm3(tm + TM_ACC0, R2_hi, R2_lo, W2_hi, W2_lo, 128, HID, HID, false);
                 umma::mma_commit(&bar[4]);
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             umma::fence_async_smem();
             umma::fence_before_thread_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0 && umma::elect_one()) {
                 umma::fence_after_thread_sync();
                 umma::gemm3(tm + TM_ACC1, R2_hi, R2_lo, W2T_hi, W2T_lo, 128, HID, HID, false);   // dH1 = dZ2 W2
                 umma::mma_commit(&bar[5]);
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 umma::fence_async_smem();
                 umma::fence_before_thread_sync();
                 __syncthreads();
-                if (tid == 0) {
+                if (warp == 0 && umma::elect_one()) {
                     umma::fence_after_thread_sync();
                     umma::gemm3(tm + TM_DW2, TA_hi, TA_lo, TB_hi, TB_lo, 64, HID, 64, !first);
                     umma::gemm3(tm + TM_DE2, TA_hi, TA_lo, TE, TE, 64, 32, 64, !first, false, true);
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 umma::fence_async_smem();
                 umma::fence_before_thread_sync();
                 __syncthreads();
-                if (tid == 0) {
+                if (warp == 0 && umma::elect_one()) {
                     umma::fence_after_thread_sync();
                     umma::gemm3(tm + TM_DW1, TA_hi, TA_lo, TB_hi, TB_lo, 64, d.obs, 64, !first);
                     umma::gemm3(tm + TM_DE1, TA_hi, TA_lo, TE, TE, 64, 32, 64, !first, false, true);

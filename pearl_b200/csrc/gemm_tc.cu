@@ -221,7 +221,7 @@ __global__ void __maxnreg__(168) k_gemm_tc(const GemmArgs g) {
         umma::fence_before_thread_sync();
         __syncthreads();
         umma::fence_after_thread_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {   // one lane of the converged issuer warp: back-to-back UTCHMMA, descriptor math on the uniform datapath
             const uint32_t tmem = tmem_slot, idesc = umma::make_idesc_tf32(TM, TN);
             const uint64_t dproto = umma::make_desc2(0, LBO, SBO);
             const uint32_t base = umma::smem_u32(dsm);
@@ -355,7 +355,7 @@ __global__ void __maxnreg__(168) k_gemm_ts(const GemmArgs g) {
         umma::fence_before_thread_sync();
         __syncthreads();
         umma::fence_after_thread_sync();
-        if (lane == 0) {
+        if (umma::elect_one()) {   // one lane of the converged issuer warp: back-to-back UTCHMMA, descriptor math on the uniform datapath
             const uint32_t tmem = tmem_slot, idesc = umma::make_idesc_tf32(TM, TN);
             const uint64_t dproto = umma::make_desc2(0, LBO, SBO);
             const uint32_t base = umma::smem_u32(dsm);

@@ -112,6 +112,18 @@ __device__ __forceinline__ int tile_index2(int r, int k, int K, int lbo) {
 }
 __device__ __forceinline__ Tile make_tile(const void *p, int K, int lbo) { return Tile{smem_u32(p), lbo, (K >> 2) * lbo}; }
 
+// One lane of a CONVERGED warp (call it under a warp-uniform condition, all 32 lanes executing).  MMA issue code must sit
+// under `if (elect_one())`, not under `if (lane == 0)`: tcgen05.mma is a uniform-datapath instruction (UTCHMMA, operands in
+// uniform registers).  Behind a thread-index predicate nvcc wraps EVERY mma in a serialisation loop over the active lanes
+// (ELECT + 4 R2UR.BROADCAST + PLOP3 + BRA.U.ANY: ~13 dependent instructions, 53 clk per 128 x 64 x 8 product against a
+// tensor-pipe floor of 32); behind elect.sync it knows exactly one lane runs and emits back-to-back UTCHMMA with the
+// descriptor arithmetic on the uniform datapath (ncu source view: profiles/r2_k_dqn_tc_stalls.md).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // 3xTF32: D[M x N] (+)= A[M x K] * B[N x K]^T; issued by ONE thread.  *_exact: the operand is exactly
 // representable in TF32 (0/1 indicators), its lo tile is not needed.  Descriptors are built once; a K
 // step of 8 only adds (2*lbo)>>4 to the 14-bit start-address field.

@@ -431,6 +431,43 @@ def test_learner_group_equals_individual_simt_learners():
         assert_close(lt.flat_target_parameters.cpu().numpy(), ls.flat_target_parameters.cpu().numpy(), f"group target {i}")
 
 
+def test_tc_group_chunked_launch_is_bit_identical_to_short_calls():
+    """One `group.learn()` of 80 rounds (index streams produced in chunks on a side stream, two chained
+    learner launches; inside a launch the row scalars are double-buffered one round ahead and the target
+    tiles are requested during the previous round's AdamW) vs the same learners driven by calls of at most
+    20 rounds: same arithmetic in the same order, so losses, parameters, target parameters and AdamW state
+    must be bit-identical — any state carried wrongly across a round or launch boundary shows up here.
+    Soft target updates (freq 4) fall on both sides of the boundaries."""
+    pearl_b200, _, _, _, make_transitions = _imports()
+    obs, A, B, n, rounds, L = 128, 16, 256, 3000, 80, 3
+    out = {}
+    for per_call in (rounds, 20):
+        learners, bufs = [], []
+        for i in range(L):
+            d = make_transitions(n, obs, A, seed=700 + i)
+            buf = pearl_b200.B200ReplayBuffer(n, rng="device")
+            buf.push_batch(*(torch.from_numpy(d[k]) for k in ("state", "action", "reward", "next_state", "terminated", "truncated")),
+                           max_number_actions=A)
+            buf.seed(70 + i)
+            torch.manual_seed(7 + i)
+            learners.append(pearl_b200.B200DeepQLearning(
+                state_dim=obs, action_space=_Space(A), hidden_dims=[64, 64], training_rounds=rounds, batch_size=B,
+                target_update_freq=4, soft_update_tau=0.5, max_rounds_per_call=per_call,
+                action_representation_module=pearl_b200.OneHotActionTensorRepresentationModule(A), engine="tc").to("cuda"))
+            bufs.append(buf)
+        reps = pearl_b200.B200LearnerGroup(learners, bufs).learn()
+        out[per_call] = (learners, bufs, reps)
+    for i in range(L):
+        la, lb = out[rounds][0][i], out[20][0][i]
+        assert np.array_equal(out[rounds][1][i].get_rng_state(), out[20][1][i].get_rng_state())
+        assert out[rounds][2][i]["loss"] == out[20][2][i]["loss"]
+        assert torch.equal(la.flat_parameters, lb.flat_parameters)
+        assert torch.equal(la.flat_target_parameters, lb.flat_target_parameters)
+        sa, sb = la.adam_state(), lb.adam_state()
+        for k in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+            assert torch.equal(sa[k], sb[k]), k
+
+
 @pytest.mark.gpu
 def test_group_push_matches_per_buffer_push():
     """B200LearnerGroup.push_batch (one library call, threaded packing) writes the same ring contents as per-buffer pushes,
