@@ -30,6 +30,7 @@
 // in round 2 as well — bit-correct but slower; see profiles/r2_k_dqn_tc_summary.md.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -77,18 +78,19 @@ struct TcArgs {
     int B, rounds, freq;
     int round0;        // this launch runs rounds [round0, round0 + rounds) of the call (chunked launches)
     float decay, omb1, beta2, omb2, eps, gamma, tau, omtau, inv_b2;
-    long long *prof;   // optional [rounds][16] SM-clock stamps of CTA 0
+    long long *prof;   // optional [rounds][16] SM-clock stamps of one CTA
+    int prof_cta;      // which CTA writes them (PRL_TC_PROF_CTA, default 0: the learners do not all run at the same speed)
 };
 
 #define TC_STAMP(idx)                                                                          \
     do {                                                                                       \
-        if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[(size_t)round * 16 + (idx)] = clock64(); \
+        if (a.prof && blockIdx.x == a.prof_cta && threadIdx.x == 0) a.prof[(size_t)round * 16 + (idx)] = clock64(); \
     } while (0)
 
 struct Misc {
-    float watb[16][HID];     // W1[:, obs + a] + b1 of the network being evaluated
-    float b2[HID], w3[HID];
-    float b3, pad0[3];
+    // small fp32 vectors of a network: W1[:, obs + a] + b1, b2, w3, b3.  [0] online, [1] target (the target's only change at
+    // a scheduled soft update, so they are loaded then and in the prologue, not every round)
+    struct Smalls { float watb[16][HID]; float b2[HID], w3[HID]; float b3, pad0[3]; } sm[2];
     float y[MAX_B];
     float vpart[128][2];
     float vmax2[2][128];
@@ -150,7 +152,7 @@ __device__ void rebuild_tiles(const float *__restrict__ net, const Dims &d, cons
     }
 }
 // the small fp32 vectors of a network (action columns + b1, b2, w3, b3); all loads of a thread issued before the first use
-__device__ void load_smalls(const float *__restrict__ net, const Dims &d, Misc &mi) {
+__device__ void load_smalls(const float *__restrict__ net, const Dims &d, Misc::Smalls &mi) {
     const int tid = threadIdx.x;
     float wa[4], bb[4];                                           // A * 64 <= 1024 elements: <= 4 per thread
 #pragma unroll
@@ -349,7 +351,8 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         }
         // ---- scheduled soft target update happens BEFORE this round's gradient step
         //      (deep_td_learning.py:283-284: (training_steps + 1) % freq == 0)
-        if ((L.steps0 + round + 2) % a.freq == 0) {
+        const bool soft_upd = (L.steps0 + round + 2) % a.freq == 0;
+        if (soft_upd) {
             for (int i = tid; i < d.P; i += NTH) L.wt[i] = soft_update(__ldcg(L.w + i), __ldcg(L.wt + i), a.tau, a.omtau);
             __syncthreads();
             rebuild_tiles(L.wt, d, Tt, tid);
@@ -359,13 +362,13 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
 
         // ================= phase T: y = max_a' Q_target(s', a') * gamma * (1 - term) + r =================
         TC_STAMP(1);
-        if (tid == 0) {     // target tiles: three TMA bulk copies (regions 1 and 3 are free: every product of the last round was waited for)
+        if (tid == 0) {   // target tiles: three TMA bulk copies (regions 1 and 3 are free: every product of the last round was waited for)
             mbar_expect_tx(bar + 6, 2 * w1_bytes + w2_bytes);
             bulk_g2s(smem + REG1, Tt.w1hi, w1_bytes, bar + 6);
             bulk_g2s(smem + REG1 + HALF, Tt.w1lo, w1_bytes, bar + 6);
             bulk_g2s(smem + REG3, Tt.w2, w2_bytes, bar + 6);
         }
-        load_smalls(L.wt, d, mi);
+        if (soft_upd || round == 0) load_smalls(L.wt, d, mi.sm[1]);   // the target's small vectors only change at a soft update
         umma::mbar_wait(bar + 6, round & 1);
         __syncthreads();
         TC_STAMP(2);
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         float hi[32], lo[32];
 #pragma unroll
                         for (int c4 = 0; c4 < 8; c4++) {
-                            const float4 wv = *reinterpret_cast<const float4 *>(&mi.watb[id][half * 32 + 4 * c4]);
+                            const float4 wv = *reinterpret_cast<const float4 *>(&mi.sm[1].watb[id][half * 32 + 4 * c4]);
                             const int c = half * 32 + 4 * c4;
                             umma::split_tf32(fmaxf(t1[c + 0] + wv.x, 0.f), hi[4 * c4 + 0], lo[4 * c4 + 0]);
                             umma::split_tf32(fmaxf(t1[c + 1] + wv.y, 0.f), hi[4 * c4 + 1], lo[4 * c4 + 1]);
@@ -424,14 +427,14 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     float q = 0.f;
 #pragma unroll
                     for (int c4 = 0; c4 < 16; c4++) {
-                        const float4 w3v = *reinterpret_cast<const float4 *>(&mi.w3[4 * c4]);
-                        const float4 b2v = *reinterpret_cast<const float4 *>(&mi.b2[4 * c4]);
+                        const float4 w3v = *reinterpret_cast<const float4 *>(&mi.sm[1].w3[4 * c4]);
+                        const float4 b2v = *reinterpret_cast<const float4 *>(&mi.sm[1].b2[4 * c4]);
                         q = fmaf(w3v.x, fmaxf(acc[4 * c4 + 0] + b2v.x, 0.f), q);
                         q = fmaf(w3v.y, fmaxf(acc[4 * c4 + 1] + b2v.y, 0.f), q);
                         q = fmaf(w3v.z, fmaxf(acc[4 * c4 + 2] + b2v.z, 0.f), q);
                         q = fmaf(w3v.w, fmaxf(acc[4 * c4 + 3] + b2v.w, 0.f), q);
                     }
-                    q += mi.b3;
+                    q += mi.sm[1].b3;
                     if (act >= cnt) q = -INFINITY;   // next_state_action_values[mask] = -inf
                     best = fmaxf(best, q);
                     
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         // ================= phase O: online forward, loss, backward =================
         TC_STAMP(4);
         if (tid == 0) tma_w2(To, bar + 8);         // region 3 held the target W2 until the last all-actions product
-        load_smalls(L.w, d, mi);
+        load_smalls(L.w, d, mi.sm[0]);
         umma::mbar_wait(bar + 8, round & 1);
         {   // W2^T tiles (B operand of dH1 = dZ2 W2) out of the W2 tiles: element (k, j) <- (j, k)
             const float *w2 = reinterpret_cast<const float *>(smem + REG3);
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             {
                 const int ai = mi.act[row];
 #pragma unroll
-                for (int c = 0; c < 32; c++) h1[c] = fmaxf(h1[c] + mi.watb[ai][c0 + c], 0.f);
+                for (int c = 0; c < 32; c++) h1[c] = fmaxf(h1[c] + mi.sm[0].watb[ai][c0 + c], 0.f);
 #pragma unroll
                 for (int c4 = 0; c4 < 8; c4++)
                     st_split4(r2hi, r2lo, umma::tile_index(m, c0 + 4 * c4, 64),
@@ -500,11 +503,11 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             umma::tmem_ld32(tlane + TM_ACC0 + c0, z);
             float part = 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; c++) { z[c] = fmaxf(z[c] + mi.b2[c0 + c], 0.f); part = fmaf(mi.w3[c0 + c], z[c], part); }
+            for (int c = 0; c < 32; c++) { z[c] = fmaxf(z[c] + mi.sm[0].b2[c0 + c], 0.f); part = fmaf(mi.sm[0].w3[c0 + c], z[c], part); }
             mi.vpart[m][h] = part;
             umma::fence_before_thread_sync();
             __syncthreads();
-            const float q = mi.vpart[m][0] + mi.vpart[m][1] + mi.b3;
+            const float q = mi.vpart[m][0] + mi.vpart[m][1] + mi.sm[0].b3;
             const float y = mi.y[row];
             const float dq = (q - y) * a.inv_b2;
             if (h == 0) {
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 dw3_acc += warp_colsum32(cs, lane);   // lane c receives the sum of column c over the 32 rows
             }
 #pragma unroll
-            for (int c = 0; c < 32; c++) z[c] = (z[c] > 0.f) ? dq * mi.w3[c0 + c] : 0.f;   // dZ2
+            for (int c = 0; c < 32; c++) z[c] = (z[c] > 0.f) ? dq * mi.sm[0].w3[c0 + c] : 0.f;   // dZ2
 #pragma unroll
             for (int c4 = 0; c4 < 8; c4++)
                 st_split4(r2hi, r2lo, umma::tile_index(m, c0 + 4 * c4, 64),
@@ -580,6 +583,33 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                     umma::gemm3(tm + TM_DE2, TA_hi, TA_lo, TE, TE, 64, 32, 64, !first, false, true);
                     umma::mma_commit(&bar[3]);
                 }
+                // S^T: every warp reads whole state rows of this half coalesced (lane = k) and scatters them into column rq of
+                // the transposed tile; the first four rows are requested BEFORE waiting for the dW2 product
+                float sv[4][4];
+                auto st_rows_load = [&](int r0) {
+#pragma unroll
+                    for (int ri = 0; ri < 4; ri++) {
+                        const int rq = warp + 8 * (r0 + ri);
+                        const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[t * 128 + hf * 64 + rq] * W) + a.lay.off_state;
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++) sv[ri][jj] = (lane + 32 * jj < d.obs) ? __ldg(src + lane + 32 * jj) : 0.f;
+                    }
+                };
+                auto st_rows_scatter = [&](int r0) {
+#pragma unroll
+                    for (int ri = 0; ri < 4; ri++) {
+                        const int rq = warp + 8 * (r0 + ri);
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++)
+                            if (lane + 32 * jj < d.obs) {
+                                float hi, lo;
+                                umma::split_tf32(sv[ri][jj], hi, lo);
+                                const int idx = umma::tile_index2(lane + 32 * jj, rq, 64, TL);
+                                arena[AR_B_HI / 4 + idx] = hi; arena[AR_B_LO / 4 + idx] = lo;
+                            }
+                    }
+                };
+                st_rows_load(0);
                 umma::mbar_wait(&bar[3], par3);
                 par3 ^= 1;
                 umma::fence_after_thread_sync();
@@ -594,30 +624,9 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                         arena[AR_A_HI / 4 + idx] = hi; arena[AR_A_LO / 4 + idx] = lo;
                     }
                 }
-                // S^T: every warp reads whole state rows of this half coalesced (lane = k) and scatters them
-                // into column rr of the transposed tile
-                for (int r0 = 0; r0 < 8; r0 += 4) {
-                    float v[4][4];
-#pragma unroll
-                    for (int ri = 0; ri < 4; ri++) {
-                        const int rq = warp + 8 * (r0 + ri);
-                        const float *src = reinterpret_cast<const float *>(L.records + (size_t)mi.slot[t * 128 + hf * 64 + rq] * W) + a.lay.off_state;
-#pragma unroll
-                        for (int jj = 0; jj < 4; jj++) v[ri][jj] = (lane + 32 * jj < d.obs) ? __ldg(src + lane + 32 * jj) : 0.f;
-                    }
-#pragma unroll
-                    for (int ri = 0; ri < 4; ri++) {
-                        const int rq = warp + 8 * (r0 + ri);
-#pragma unroll
-                        for (int jj = 0; jj < 4; jj++)
-                            if (lane + 32 * jj < d.obs) {
-                                float hi, lo;
-                                umma::split_tf32(v[ri][jj], hi, lo);
-                                const int idx = umma::tile_index2(lane + 32 * jj, rq, 64, TL);
-                                arena[AR_B_HI / 4 + idx] = hi; arena[AR_B_LO / 4 + idx] = lo;
-                            }
-                    }
-                }
+                st_rows_scatter(0);
+                st_rows_load(4);
+                st_rows_scatter(4);
                 umma::fence_async_smem();
                 umma::fence_before_thread_sync();
                 __syncthreads();
@@ -645,9 +654,9 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         __syncthreads();
         umma::fence_after_thread_sync();
         {
-            // 1) gradients TMEM -> shared staging (arena is free: every product has been waited for).  Row
+            // 1) gradients TMEM -> shared staging in region 2 (the arena is free).  Row
             //    pitches are odd, so the 16 live lanes of a warp (rows 16q .. 16q+15) hit distinct banks.
-            float *gs_w2 = reinterpret_cast<float *>(smem);            // [64][65]
+            float *gs_w2 = reinterpret_cast<float *>(smem + REG2);     // [64][65]
             const int pitch1 = d.D | 1;
             float *gs_w1 = gs_w2 + 64 * 65;                            // [64][pitch1]   (state cols, then action cols)
             float *gs_b1 = gs_w1 + 64 * pitch1, *gs_b2 = gs_b1 + 64;
@@ -680,44 +689,74 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
             }
             umma::fence_before_thread_sync();
             __syncthreads();
-            // 2) AdamW over the flat parameter vector, all 256 threads, fully coalesced 16-byte accesses
+            // 2) AdamW over the flat parameter vector, all 256 threads, fully coalesced 16-byte accesses.  The sweep is bound by
+            //    L2 round trips, not bytes: W1 | W2 are walked as ONE flat list of 16-byte groups (no 4-lane tail passes per W1
+            //    row) in batches of two groups per thread whose 8 loads are issued before the first use, and the loads of the
+            //    small vectors (b1 | b2 | W3 | b3, one parameter per thread) are in flight across the whole sweep.
             const float2 sc = L.scal[round];
             AdamScalarsTc hs;
             hs.decay = a.decay; hs.omb1 = a.omb1; hs.beta2 = a.beta2; hs.omb2 = a.omb2; hs.eps = a.eps;
             hs.step_size = sc.x; hs.bc2_sqrt = sc.y; hs.inv_bc2_sqrt = 1.0f / sc.y;
+            int si = -1;                // this thread's small parameter
+            float sg = 0.f, sw = 0.f, sm = 0.f, sv2 = 0.f, sx = 0.f;
+            if (tid < 64) { si = d.ob1 + tid; sg = gs_b1[tid]; }
+            else if (tid < 128) { si = d.ob2 + tid - 64; sg = gs_b2[tid - 64]; }
+            else if (tid < 192) {       // W3: sum the four row-quarter partials of this column in fixed order
+                const int col = tid - 128, hh = col >> 5, c = col & 31;
+                sg = ((mi.redw[hh * 4 + 0][c] + mi.redw[hh * 4 + 1][c]) + mi.redw[hh * 4 + 2][c]) + mi.redw[hh * 4 + 3][c];
+                si = d.oW3 + col;
+            } else if (tid == 192) {
+                sg = ((mi.reddb3[0] + mi.reddb3[1]) + mi.reddb3[2]) + mi.reddb3[3];
+                si = d.ob3;
+                const float e = ((mi.redmae[0] + mi.redmae[1]) + mi.redmae[2]) + mi.redmae[3];
+                L.out_mae[round] = e / (float)a.B;   // reported "loss": mean |q - y|
+            }
+            if (si >= 0) { sw = __ldcg(L.w + si); sm = __ldcg(L.m + si); sv2 = __ldcg(L.v + si); sx = __ldcg(L.vmax + si); }
             const bool vecD = ((d.D & 3) == 0) && ((d.oW2 & 3) == 0);
             if (vecD) {
-                const int D4 = d.D >> 2;
-                for (int row = warp; row < HID; row += 8)
-                    for (int c4 = lane; c4 < D4; c4 += 32) {
-                        const int i = d.oW1 + row * d.D + c4 * 4;
-                        const float *gp = gs_w1 + row * pitch1 + c4 * 4;
-                        float4 w4 = __ldcg(reinterpret_cast<const float4 *>(L.w + i)), m4 = __ldcg(reinterpret_cast<const float4 *>(L.m + i));
-                        float4 v4 = __ldcg(reinterpret_cast<const float4 *>(L.v + i)), x4 = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i));
-                        w4.x = adam_math(w4.x, m4.x, v4.x, x4.x, gp[0], hs); w4.y = adam_math(w4.y, m4.y, v4.y, x4.y, gp[1], hs);
-                        w4.z = adam_math(w4.z, m4.z, v4.z, x4.z, gp[2], hs); w4.w = adam_math(w4.w, m4.w, v4.w, x4.w, gp[3], hs);
-                        *reinterpret_cast<float4 *>(L.w + i) = w4; *reinterpret_cast<float4 *>(L.m + i) = m4;
-                        *reinterpret_cast<float4 *>(L.v + i) = v4; *reinterpret_cast<float4 *>(L.vmax + i) = x4;
-                        if (c4 * 4 < d.obs) {   // the same 16-byte chunk of the operand-layout tiles (hi = the value, lo = residual)
-                            const int ti = umma::tile_index(row, c4 * 4, d.obs);
-                            *reinterpret_cast<float4 *>(To.w1hi + ti) = w4;
-                            *reinterpret_cast<float4 *>(To.w1lo + ti) = make_float4(tf32_lo(w4.x), tf32_lo(w4.y), tf32_lo(w4.z), tf32_lo(w4.w));
+                constexpr int U = 2;
+                const int D4 = d.D >> 2, n1 = HID * D4, ntot = n1 + HID * HID / 4;
+                for (int q0 = tid; q0 < ntot; q0 += U * NTH) {
+                    float4 w4[U], m4[U], v4[U], x4[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int q = q0 + u * NTH;
+                        if (q < ntot) {
+                            const int i = q < n1 ? d.oW1 + q * 4 : d.oW2 + (q - n1) * 4;   // W1 rows are contiguous: row * D + c4 * 4 == q * 4
+                            w4[u] = __ldcg(reinterpret_cast<const float4 *>(L.w + i)); m4[u] = __ldcg(reinterpret_cast<const float4 *>(L.m + i));
+                            v4[u] = __ldcg(reinterpret_cast<const float4 *>(L.v + i)); x4[u] = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i));
                         }
                     }
-                for (int q4 = tid; q4 < HID * HID / 4; q4 += NTH) {   // W2: 16 float4 per row
-                    const int row = q4 >> 4, c = (q4 & 15) * 4, i = d.oW2 + q4 * 4;
-                    const float *gp = gs_w2 + row * 65 + c;
-                    float4 w4 = __ldcg(reinterpret_cast<const float4 *>(L.w + i)), m4 = __ldcg(reinterpret_cast<const float4 *>(L.m + i));
-                    float4 v4 = __ldcg(reinterpret_cast<const float4 *>(L.v + i)), x4 = __ldcg(reinterpret_cast<const float4 *>(L.vmax + i));
-                    w4.x = adam_math(w4.x, m4.x, v4.x, x4.x, gp[0], hs); w4.y = adam_math(w4.y, m4.y, v4.y, x4.y, gp[1], hs);
-                    w4.z = adam_math(w4.z, m4.z, v4.z, x4.z, gp[2], hs); w4.w = adam_math(w4.w, m4.w, v4.w, x4.w, gp[3], hs);
-                    *reinterpret_cast<float4 *>(L.w + i) = w4; *reinterpret_cast<float4 *>(L.m + i) = m4;
-                    *reinterpret_cast<float4 *>(L.v + i) = v4; *reinterpret_cast<float4 *>(L.vmax + i) = x4;
-                    {
-                        const float4 l4 = make_float4(tf32_lo(w4.x), tf32_lo(w4.y), tf32_lo(w4.z), tf32_lo(w4.w));
-                        const int ti = umma::tile_index(row, c, HID);
-                        *reinterpret_cast<float4 *>(To.w2 + ti) = w4;
-                        *reinterpret_cast<float4 *>(To.w2 + 4096 + ti) = l4;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int q = q0 + u * NTH;
+                        if (q < ntot) {
+                            int i;
+                            const float *gp;
+                            float *thi, *tlo;             // the same 16-byte chunk of the operand-layout tiles (hi = the value, lo = residual)
+                            if (q < n1) {
+                                const int row = q / D4, c = (q - row * D4) * 4;
+                                i = d.oW1 + q * 4;
+                                gp = gs_w1 + row * pitch1 + c;
+                                const int ti = umma::tile_index(row, c, d.obs);
+                                thi = c < d.obs ? To.w1hi + ti : nullptr; tlo = To.w1lo + ti;
+                            } else {
+                                const int q4 = q - n1, row = q4 >> 4, c = (q4 & 15) * 4;
+                                i = d.oW2 + q4 * 4;
+                                gp = gs_w2 + row * 65 + c;
+                                const int ti = umma::tile_index(row, c, HID);
+                                thi = To.w2 + ti; tlo = To.w2 + 4096 + ti;
+                            }
+                            float4 w = w4[u], mm = m4[u], vv = v4[u], xx = x4[u];
+                            w.x = adam_math(w.x, mm.x, vv.x, xx.x, gp[0], hs); w.y = adam_math(w.y, mm.y, vv.y, xx.y, gp[1], hs);
+                            w.z = adam_math(w.z, mm.z, vv.z, xx.z, gp[2], hs); w.w = adam_math(w.w, mm.w, vv.w, xx.w, gp[3], hs);
+                            *reinterpret_cast<float4 *>(L.w + i) = w; *reinterpret_cast<float4 *>(L.m + i) = mm;
+                            *reinterpret_cast<float4 *>(L.v + i) = vv; *reinterpret_cast<float4 *>(L.vmax + i) = xx;
+                            if (thi) {
+                                *reinterpret_cast<float4 *>(thi) = w;
+                                *reinterpret_cast<float4 *>(tlo) = make_float4(tf32_lo(w.x), tf32_lo(w.y), tf32_lo(w.z), tf32_lo(w.w));
+                            }
+                        }
                     }
                 }
             } else {
@@ -738,26 +777,9 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
                 rebuild_tiles(L.w, d, To, tid);         // unaligned shapes (D % 4 != 0): tiles from the flat vector
             }
             fence_proxy_async_all();                    // the tile writes are read by TMA in the next round
-            {   // b1 | b2 | W3 | b3: 64 + 64 + 64 + 1 parameters, one per thread
-                int i = -1;
-                float gg = 0.f;
-                if (tid < 64) { i = d.ob1 + tid; gg = gs_b1[tid]; }
-                else if (tid < 128) { i = d.ob2 + tid - 64; gg = gs_b2[tid - 64]; }
-                else if (tid < 192) {   // W3: sum the four row-quarter partials of this column in fixed order
-                    const int col = tid - 128, hh = col >> 5, c = col & 31;
-                    gg = ((mi.redw[hh * 4 + 0][c] + mi.redw[hh * 4 + 1][c]) + mi.redw[hh * 4 + 2][c]) + mi.redw[hh * 4 + 3][c];
-                    i = d.oW3 + col;
-                } else if (tid == 192) {
-                    gg = ((mi.reddb3[0] + mi.reddb3[1]) + mi.reddb3[2]) + mi.reddb3[3];
-                    i = d.ob3;
-                    const float e = ((mi.redmae[0] + mi.redmae[1]) + mi.redmae[2]) + mi.redmae[3];
-                    L.out_mae[round] = e / (float)a.B;   // reported "loss": mean |q - y|
-                }
-                if (i >= 0) {
-                    float mm = __ldcg(L.m + i), vv = __ldcg(L.v + i), xx = __ldcg(L.vmax + i);
-                    L.w[i] = adam_math(__ldcg(L.w + i), mm, vv, xx, gg, hs);
-                    L.m[i] = mm; L.v[i] = vv; L.vmax[i] = xx;
-                }
+            if (si >= 0) {
+                L.w[si] = adam_math(sw, sm, sv2, sx, sg, hs);
+                L.m[si] = sm; L.v[si] = sv2; L.vmax[si] = sx;
             }
         }
         umma::fence_before_thread_sync();
@@ -887,6 +909,7 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
     a.omtau = (float)(1.0 - c.tau);
     a.inv_b2 = 2.0f / (float)batch;
     a.prof = q0->prof;
+    { static const int c = [] { const char *e = getenv("PRL_TC_PROF_CTA"); return e ? atoi(e) : 0; }(); a.prof_cta = c; }
     const size_t smem = MISC_OFF + sizeof(Misc);
     PRL_REQUIRE(smem <= (size_t)q0->max_smem, "tensor-core learner needs %zu B of shared memory", smem);
     PRL_CUDA(cudaFuncSetAttribute(k_dqn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

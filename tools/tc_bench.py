@@ -41,6 +41,6 @@ s = st.cpu()[4:].double()
 names = ["row scalars + soft upd", "load target weights", "target layer 1 (2 tiles)", "all-actions (32 tiles)", "load online weights",
          "online layer 1", "tile0: fwd L2 + dZ2 + dH1", "rest (weight grads t0, tile1 all)", "AdamW"]
 tot = (s[1:, 0] - s[:-1, 0]).mean()
-print(f"{tot:.0f} clk/round (CTA 0 with {R} learners resident)")
+print(f"{tot:.0f} clk/round (CTA {os.environ.get('PRL_TC_PROF_CTA', '0')} with {R} learners resident)")
 for i, n in enumerate(names):
     print(f"  {n:36s} {(s[:, i+1]-s[:, i]).mean():10.0f} clk")
