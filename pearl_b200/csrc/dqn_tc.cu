@@ -927,7 +927,11 @@ extern "C" int prl_dqn_learn_multi(prl_dqn *const *dqns, prl_buf *const *bufs, i
         for (auto &e : ev_idx) PRL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         PRL_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     }
-    auto chunk_begin = [&](int cix) { return (int)((long long)rounds * cix / nchunks); };
+    // chunk 0 is the only one whose index production is NOT hidden behind a learner launch: keep it short (32 rounds)
+    const int first = nchunks > 1 ? (rounds / nchunks < 32 ? rounds / nchunks : 32) : rounds;
+    auto chunk_begin = [&](int cix) {
+        return cix == 0 ? 0 : first + (int)((long long)(rounds - first) * (cix - 1) / (nchunks > 1 ? nchunks - 1 : 1));
+    };
     k_sample_indices_multi<<<count, kSamplerThreads, samp_smem, stream>>>(d_samp, chunk_begin(1), 0);
     PRL_CUDA(cudaGetLastError());
     if (nchunks > 1) {

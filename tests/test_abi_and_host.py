@@ -100,6 +100,24 @@ def test_plugins_subclass_pearl_when_available():
         "assert issubclass(pearl_b200.B200ReplayBuffer, ReplayBuffer)\n"
         "assert issubclass(pearl_b200.B200DeepQLearning, DeepQLearning)\n"
         "assert issubclass(pearl_b200.B200DoubleDQN, DoubleDQN) and issubclass(pearl_b200.B200DoubleDQN, PolicyLearner)\n"
+        "from pearl.policy_learners.sequential_decision_making.soft_actor_critic_continuous import ContinuousSoftActorCritic\n"
+        "from pearl.policy_learners.sequential_decision_making.ppo import ProximalPolicyOptimization\n"
+        "from pearl.policy_learners.sequential_decision_making.td3 import TD3\n"
+        "from pearl.policy_learners.sequential_decision_making.ddpg import DeepDeterministicPolicyGradient\n"
+        "assert issubclass(pearl_b200.B200ContinuousSoftActorCritic, ContinuousSoftActorCritic)\n"
+        "assert issubclass(pearl_b200.B200ProximalPolicyOptimization, ProximalPolicyOptimization)\n"
+        "assert issubclass(pearl_b200.B200TD3, TD3) and issubclass(pearl_b200.B200DeepDeterministicPolicyGradient, DeepDeterministicPolicyGradient)\n"
+        "assert not issubclass(pearl_b200.B200DeepDeterministicPolicyGradient, TD3)\n"
+        "import torch\n"
+        "from pearl.utils.instantiations.spaces.box_action import BoxActionSpace\n"
+        "l = pearl_b200.B200ContinuousSoftActorCritic(state_dim=6, action_space=BoxActionSpace(-torch.ones(2), torch.ones(2)),\n"
+        "        actor_hidden_dims=[32, 32], critic_hidden_dims=[32, 32], seed=3)\n"
+        "class Buf:\n"
+        "    def __len__(self): return 4\n"
+        "try:\n"
+        "    l.learn(Buf()); raise SystemExit('a CPU learner must not learn')\n"
+        "except RuntimeError as e:\n"
+        "    assert 'no CPU path' in str(e)\n"
         "from pearl.replay_buffers.transition import TransitionBatch\n"
         "assert pearl_b200.TransitionBatch is TransitionBatch\n"
         "print('ok')\n" % (os.path.join(ROOT, "oracle", "stubs"), ROOT))
