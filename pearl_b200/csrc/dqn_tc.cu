@@ -354,8 +354,20 @@ __global__ void __launch_bounds__(NTH, 1) k_dqn_tc(const TcArgs a) {
         const bool soft_upd = (L.steps0 + round + 2) % a.freq == 0;
         if (soft_upd) {
             for (int i = tid; i < d.P; i += NTH) L.wt[i] = soft_update(__ldcg(L.w + i), __ldcg(L.wt + i), a.tau, a.omtau);
-            __syncthreads();
-            rebuild_tiles(L.wt, d, Tt, tid);
+            // The operand-layout tiles get the same elementwise update IN TILE ORDER (the hi tiles hold exactly the fp32 values of
+            // the flat vectors, permuted; lo = residual of the new value): coalesced 16-byte accesses instead of rebuilding the
+            // target tiles from the flat vector with scattered 4-byte stores.  Same function of the same inputs: bit-identical.
+            auto update_tile = [&](const float *on_hi, float *tg_hi, float *tg_lo, int n) {
+                for (int i = tid * 4; i < n; i += NTH * 4) {
+                    const float4 w = __ldcg(reinterpret_cast<const float4 *>(on_hi + i)), t = __ldcg(reinterpret_cast<const float4 *>(tg_hi + i));
+                    const float4 r = make_float4(soft_update(w.x, t.x, a.tau, a.omtau), soft_update(w.y, t.y, a.tau, a.omtau),
+                                                 soft_update(w.z, t.z, a.tau, a.omtau), soft_update(w.w, t.w, a.tau, a.omtau));
+                    *reinterpret_cast<float4 *>(tg_hi + i) = r;
+                    *reinterpret_cast<float4 *>(tg_lo + i) = make_float4(tf32_lo(r.x), tf32_lo(r.y), tf32_lo(r.z), tf32_lo(r.w));
+                }
+            };
+            update_tile(To.w1hi, Tt.w1hi, Tt.w1lo, HID * d.obs);
+            update_tile(To.w2, Tt.w2, Tt.w2 + HID * HID, HID * HID);
             fence_proxy_async_all();
         }
         __syncthreads();

