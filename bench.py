@@ -40,7 +40,7 @@ OBS, N_ACT, HIDDEN, BATCH = 128, 16, (64, 64), 256
 METRIC = "learner gradient-steps/sec (batch=256, 1e6 replay)"
 
 
-TC_DRAM_BYTES_PER_STEP = 1.176e6   # measured under ncu (5.417 GB over 144 learners x 32 rounds), profiles/r2_k_dqn_tc_ncu.csv
+TC_DRAM_BYTES_PER_STEP = 1.165e6   # measured under ncu (4.042 GB read + 1.327 GB written over 144 learners x 32 rounds), profiles/r2b_k_dqn_tc_final_ncu_raw.csv
 
 
 def flops_per_step(obs=OBS, A=N_ACT, H1=HIDDEN[0], H2=HIDDEN[1], B=BATCH, double=False):
@@ -418,7 +418,7 @@ def run_b200(args) -> None:
             "roofline": {"bound": "tensor", "kernel": "k_dqn_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": TC_DRAM_BYTES_PER_STEP * rounds * R,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full` capture of k_dqn_tc in "
-                                           "profiles/r2_k_dqn_tc_ncu.csv (1.18 MB per gradient step with 144 learners' parameters, AdamW state and operand "
+                                           "profiles/r2b_k_dqn_tc_final_ncu_raw.csv (1.17 MB per gradient step with 144 learners' parameters, AdamW state and operand "
                                            "tiles competing for L2; algorithmic gather 266 KB), "
                                            "scaled to the gradient steps of one bench launch",
                          "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
