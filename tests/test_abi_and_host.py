@@ -126,6 +126,17 @@ def test_plugins_subclass_pearl_when_available():
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pearl"), reason="reference not present (GPU box)")
+def test_actor_critic_plugins_bind_reference_modules_to_flat_vectors():
+    """Host logic of pearl_b200/actor_critic.py against a stand-in learner (tests/actor_critic_host_worker.py): constructor
+    arguments, parameters / AdamW state as views, step counts, SAC's entropy block, checkpoint import into a fresh and into an
+    already bound learner, refusal of unsupported optimizers and network shapes."""
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "actor_critic_host_worker.py"), "/root/reference"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "ACTOR_CRITIC_HOST_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-4000:])
+
+
 def test_ctypes_signatures_match_the_header_arity():
     """Every ctypes binding takes exactly as many arguments as the C declaration (a mismatch would corrupt the call
     silently); pointer / integer / floating classes are compared as well."""
