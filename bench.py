@@ -326,7 +326,7 @@ def run_b200(args) -> None:
         e2e_step()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(2, args.steps // 4)
+    e2e_steps = max(3, args.steps // 2)
     f0.record()
     for _ in range(e2e_steps):
         last_loss = e2e_step()
