@@ -450,8 +450,9 @@ int prl_ppo_learn(prl_ppo *ppo, prl_buf *buf, int rounds, int batch, const float
  * the launch stream around the kernel); used by bench.py for the roofline line.
  * prl_dqn_last_kernel_ms synchronises on the end event. */
 int prl_dqn_set_timing(prl_dqn *dqn, int enable);
-/* Developer profiling: device int64[rounds][16] receiving SM-clock stamps of CTA 0 at
- * the phase boundaries of every round of the next prl_dqn_learn calls (NULL = off). */
+/* Developer profiling: device int64[rounds][16] receiving SM-clock stamps of one CTA at
+ * the phase boundaries of every round of the next prl_dqn_learn calls (NULL = off).  The
+ * tensor-core group kernel stamps CTA $PRL_TC_PROF_CTA (default 0), the cooperative kernel CTA 0. */
 int prl_dqn_set_profile(prl_dqn *dqn, long long *stamps_dev);
 int prl_dqn_last_kernel_ms(prl_dqn *dqn, float *ms);
 
