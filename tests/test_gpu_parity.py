@@ -432,11 +432,11 @@ def test_learner_group_equals_individual_simt_learners():
 
 
 def test_tc_group_chunked_launch_is_bit_identical_to_short_calls():
-    """One `group.learn()` of 80 rounds (index streams produced in chunks on a side stream, two chained
-    learner launches; inside a launch the row scalars are double-buffered one round ahead and the target
-    tiles are requested during the previous round's AdamW) vs the same learners driven by calls of at most
-    20 rounds: same arithmetic in the same order, so losses, parameters, target parameters and AdamW state
-    must be bit-identical — any state carried wrongly across a round or launch boundary shows up here.
+    """One `group.learn()` of 80 rounds (index streams produced in chunks on a side stream, a 32-round and a
+    48-round learner launch; inside a launch the target network's small vectors stay cached in shared memory
+    between soft updates and the target tiles are updated in tile order) vs the same learners driven by calls
+    of at most 20 rounds: same arithmetic in the same order, so losses, parameters, target parameters and AdamW
+    state must be bit-identical — any state carried wrongly across a round or launch boundary shows up here.
     Soft target updates (freq 4) fall on both sides of the boundaries."""
     pearl_b200, _, _, _, make_transitions = _imports()
     obs, A, B, n, rounds, L = 128, 16, 256, 3000, 80, 3
