@@ -19,7 +19,8 @@
 //            dW2 = dZ2^T H1, dW1s = dZ1^T S, and [db | dW1a] = dZ^T E with E = [1 | onehot(action)];
 //            their operands are explicitly transposed tiles written with a 144-byte chunk pitch
 //            (bank-conflict-free column scatter).  Accumulators for all of these live in TMEM.
-//   AdamW    gradients read straight from TMEM (M = 64 lane map), parameters / moments in L2.
+//   AdamW    gradients TMEM -> shared staging (M = 64 lane map), then one coalesced 16-byte sweep over the flat parameter
+//            vector (parameters / moments in L2) that also writes the operand-layout weight tiles.
 //
 // Round 2: the weights are kept in global memory a second time IN THE UMMA OPERAND LAYOUT (hi tile = the fp32 values —
 // the tensor core truncates them to TF32 — and lo tile = x - trunc_tf32(x)), written by AdamW / the soft target update
@@ -27,7 +28,10 @@
 // (cp.async.bulk + mbarrier complete_tx) issued by one thread instead of a SIMT split-and-scatter pass of all 256
 // threads (18.5 k of 172 k clk per round in round 1); the online W1 tiles travel while the all-actions products run.
 // A warp-specialised rewrite of this kernel (row groups + issuer / loader / tile-builder warps) was built and measured
-// in round 2 as well — bit-correct but slower; see profiles/r2_k_dqn_tc_summary.md.
+// in round 2 as well — bit-correct but slower; see profiles/r2_k_dqn_tc_summary.md.  What a source-level stall profile of
+// THIS kernel found instead (profiles/r2b_k_dqn_tc_stalls.md): the MMA issue code must sit under elect.sync
+// (umma::elect_one), the target network's small vectors are cached in shared memory between soft updates, AdamW walks one
+// flat list with two groups of loads in flight, the soft target update is applied to the tiles in tile order.
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
