@@ -152,6 +152,13 @@ class _B200ActorCriticMixin:
             for m, flat in pairs:
                 _adopt(m, flat)
         self._bind_extras(core)
+        # learning rates changed since the CUDA learner was configured (a scheduler, or the user editing param_groups): the C
+        # handle is re-created with the new rates at the current AdamW step counts (moments and parameters live in our vectors)
+        lrs = (_adamw_lr(self._actor_optimizer, "actor optimizer"), _adamw_lr(self._critic_optimizer, "critic optimizer"))
+        if lrs != (core._actor_learning_rate, core._critic_learning_rate):
+            steps = self._core_steps(core)
+            core._actor_learning_rate, core._critic_learning_rate = lrs
+            self._restart_core(core, steps)
         triples = self._optimizer_triples(core)
         if not all(_is_bound(o, m, s3) for o, m, s3 in triples):
             cur = self._core_steps(core)

@@ -50,6 +50,7 @@ class Stub:
         self._log_entropy, self._entropy_coef = z(4), torch.ones(1)
         self._adam_step, self._adam_steps, self._training_steps = 0, (0, 0), 0
         self._training_rounds, self._batch_size = kw["training_rounds"], kw["batch_size"]
+        self._actor_learning_rate, self._critic_learning_rate = float(kw["actor_learning_rate"]), float(kw["critic_learning_rate"])
         Stub.made.append(self)
 
     def learn(self, buf):           # "one call": every parameter + 1, moments + 0.5, one AdamW step per round
@@ -138,6 +139,18 @@ assert not ac._is_bound(l._actor_optimizer, l._actor, core._actor_state)        
 l.learn(Buf())
 assert ac._is_bound(l._actor_optimizer, l._actor, core._actor_state) and core._adam_step == 12 + 4
 assert torch.equal(core._actor_state[1], core2._actor_state[1] + 0.5)
+
+# a learning-rate change (scheduler / user) reaches the CUDA learner: same vectors, same step count, new rate
+restarts = []
+orig_restart = type(l)._restart_core
+type(l)._restart_core = lambda self, c, steps: (restarts.append(steps), orig_restart(self, c, steps))[1]
+l.learn(Buf())
+assert restarts == []                                        # nothing changed: the handle is kept
+l._actor_optimizer.param_groups[0]["lr"] = 1e-5
+at = core._adam_step
+l.learn(Buf())
+assert restarts == [(at, at)] and core._actor_learning_rate == 1e-5 and core._critic_learning_rate == 7e-4 and core._adam_step == at + 4
+type(l)._restart_core = orig_restart
 
 # fixed entropy coefficient
 lf = pearl_b200.B200ContinuousSoftActorCritic(**dict(kw, entropy_autotune=False, entropy_coef=0.3))
